@@ -1,0 +1,20 @@
+"""Regenerates tests/golden/ref_alm_golden.npz from the reference's own golden alm files.
+
+Run in the build container only (needs /root/reference): python tests/golden/make_golden.py
+The text files are the outputs of python pixell.curvedsky.map2alm printed with %.60g by the reference's
+test/data_gen/gen_sht_test_data.py:1-43; they are what test/test_transforms.jl:11-77 compares against.
+Only the numbers are kept (float64 binary), keyed by the reference file name.
+"""
+import os
+import numpy as np
+
+SRC = "/root/reference/test/data"
+FILES = ["simple_analytic_sht.txt", "simple_analytic_sht_sliced.txt", "simple_box_analytic_sht.txt",
+         "simple_analytic_sht_fullalm.txt", "simple_pol_analytic_sht.txt", "test_cls_IQU.txt"]
+
+out = {}
+for f in FILES:
+    out[f.replace(".txt", "")] = np.loadtxt(os.path.join(SRC, f))
+np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_alm_golden.npz"), **out)
+for k, v in out.items():
+    print(k, v.shape)

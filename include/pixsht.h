@@ -1,0 +1,103 @@
+/*
+ * pixsht.h -- C ABI of libpixsht.so, the B200-native (sm_100a) spherical-harmonic-transform engine that replaces the
+ * libsharp2 calls on Pixell.jl's map2alm / alm2map hot path.
+ *
+ * What each entry point replaces in the reference (simonsobs/Pixell.jl v0.2.9, file:line under /root/reference):
+ *
+ *   pixsht_plan_create     <- the per-call setup of src/transforms.jl:33-63 (make_cc_geom_info: ring grid, CC weights
+ *                             x 2pi/nphi, phi0, offsets, ccall sharp_make_geom_info) and :94 (make_triangular_alm_info)
+ *                             and the band bookkeeping of :66-82 (create_sht_band: flips + zero padding, done here as
+ *                             index arithmetic inside the FFT kernels instead of a host copy).
+ *   pixsht_execute         <- sharp_execute!(SHARP_MAP2ALM|SHARP_ALM2MAP, spin, alms, maps, geom, alm_info, SHARP_DP)
+ *                             at src/transforms.jl:101-106, 128-132, 185-194, 214-218, 240-244.  ncomp = 1 is the
+ *                             spin-0 job, 2 the spin-2 (Q,U)<->(E,B) job, 3 runs both (the IQU path of :138-165,254).
+ *   pixsht_plan_destroy    <- Libsharp.jl finalizers (sharp_destroy_geom_info / sharp_destroy_alm_info).
+ *   pixsht_stage_*         <- no reference counterpart (the reference is single-process); the m-sharded multi-GPU
+ *                             pipeline of SURVEY.md 8(e) drives these around an NCCL all-to-all.
+ *
+ * A libsharp2-symbol-compatible shim over this API is declared in include/pixsht_sharp_shim.h.
+ *
+ * Conventions (identical to the reference's):  alm = complex (re,im interleaved), triangular m-major,
+ * idx0(l,m) = m(2 lmax+1-m)/2 + l, m >= 0 only;  maps = caller's column-major (nx, ny) arrays (RA index fastest), in
+ * the caller's own orientation -- the flips of get_flip_slices (src/transforms.jl:25-30) are described by pixsht_geom,
+ * not applied by the caller.  All functions return PIXSHT_OK (0) or an error code; pixsht_last_error() gives the text.
+ * Nothing aborts.  There is no CPU fallback: without a CUDA device every compute entry point returns PIXSHT_ERR_NODEVICE.
+ */
+#ifndef PIXSHT_H
+#define PIXSHT_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pixsht_plan pixsht_plan;
+
+enum { PIXSHT_OK = 0, PIXSHT_ERR_ARG = 1, PIXSHT_ERR_CUDA = 2, PIXSHT_ERR_UNSUPPORTED = 3, PIXSHT_ERR_NOMEM = 4, PIXSHT_ERR_NODEVICE = 5 };
+enum { PIXSHT_F64 = 0, PIXSHT_F32 = 1 };             /* element type of maps and alm at the boundary */
+enum { PIXSHT_MAP2ALM = 0, PIXSHT_ALM2MAP = 1 };     /* numerically equal to libsharp2's SHARP_MAP2ALM / SHARP_ALM2MAP */
+enum { PIXSHT_HOST = 0, PIXSHT_DEVICE = 1 };         /* where the alm / map pointers passed to pixsht_execute live */
+
+/* How the caller's (nx, ny) map sits on the full-sky Clenshaw-Curtis ring grid. */
+typedef struct pixsht_geom {
+    int32_t nphi;          /* pixels of a full ring           = fullringsize(wcs)   (src/transforms.jl:3-4)   */
+    int32_t nrings_total;  /* rings of the full-sky grid      = fullringnum(wcs)    (src/transforms.jl:7-8)   */
+    int32_t ring_first;    /* 0-based full-sky index of the band's first ring, rings ascending in theta (:11-22) */
+    int32_t nrings;        /* rings in the map (= ny)                                                            */
+    int32_t nx;            /* columns in the map (<= nphi); band columns nx..nphi-1 are zeros (:70-75)          */
+    int32_t flipx;         /* 1: band column i is map column nx-1-i  (cdelt1 < 0, :25-30)                       */
+    int32_t flipy;         /* 1: band ring r is map row ny-1-r       (cdelt2 > 0, :25-30)                       */
+    int32_t reserved;
+    double phi0;           /* RA (radians) of band column 0 (:41)                                                */
+} pixsht_geom;
+
+/* ---- plans ---------------------------------------------------------------------------------------------- */
+int pixsht_plan_create(pixsht_plan **out, const pixsht_geom *geom, int lmax, int mmax, int dtype, int device);
+/* generic iso-latitude ring set with explicit colatitudes and quadrature weights (all rings nphi samples, first
+ * sample at phi0, rings ascending in theta, maps stored ring-major without flips: nx = nphi).  Used by the shim. */
+int pixsht_plan_create_rings(pixsht_plan **out, int nrings, const double *theta, const double *weight, int nphi,
+                             double phi0, int lmax, int mmax, int dtype, int device);
+void pixsht_plan_destroy(pixsht_plan *plan);
+
+/* ---- transforms ----------------------------------------------------------------------------------------- */
+/* direction: PIXSHT_MAP2ALM | PIXSHT_ALM2MAP.  ncomp: 1 = T (spin 0), 2 = Q,U <-> E,B (spin 2), 3 = T,Q,U <-> T,E,B.
+ * alms[c]: nalm complex numbers of the plan's dtype; maps[c]: nx*ny reals of the plan's dtype.
+ * location: PIXSHT_HOST (pageable or pinned host memory; copies are inside the call) or PIXSHT_DEVICE (pointers on the
+ * plan's device; the call is enqueued on the plan's stream and synchronised before returning).
+ * Outputs are overwritten (SHARP_ADD is never used by the reference). */
+int pixsht_execute(pixsht_plan *plan, int direction, int ncomp, void *const *alms, void *const *maps, int location);
+
+/* per-stage device time (ms, CUDA events) of the last pixsht_execute on this plan:
+ * [0] h2d copy, [1] Legendre stage, [2] FFT stage, [3] d2h copy, [4] whole call (host wall clock), [5..7] reserved */
+int pixsht_get_timings(const pixsht_plan *plan, double ms[8]);
+
+/* ---- stage API for the m-sharded multi-GPU pipeline (device pointers, asynchronous on `stream`) ------------ */
+/* phase buffers are complex double, element (c, row, ring) at ((c*nrows + row)*nrings_buf + ring).              */
+/* Legendre stage over the m values m_list[0..nm) (device array of int32, or NULL for m = 0..nm-1): row = position in m_list. */
+int pixsht_stage_alm2phase(pixsht_plan *plan, int ncomp, const void *const *d_alms, int nm, const int32_t *d_m_list,
+                           void *d_phase, void *stream);
+int pixsht_stage_phase2alm(pixsht_plan *plan, int ncomp, const void *d_phase, int nm, const int32_t *d_m_list,
+                           void *const *d_alms, void *stream);
+/* FFT stage over band rings [ring_begin, ring_begin+ring_count): d_phase holds all m = 0..mmax for those rings,
+ * row of m = d_m_row[m] (or m when NULL), ring index local to the range; d_maps are the full caller-layout maps. */
+int pixsht_stage_phase2map(pixsht_plan *plan, int ncomp, const void *d_phase, const int32_t *d_m_row, int ring_begin,
+                           int ring_count, void *const *d_maps, void *stream);
+int pixsht_stage_map2phase(pixsht_plan *plan, int ncomp, const void *const *d_maps, const int32_t *d_m_row, int ring_begin,
+                           int ring_count, void *d_phase, void *stream);
+
+/* ---- introspection -------------------------------------------------------------------------------------- */
+int64_t pixsht_nalm(int lmax, int mmax);
+int pixsht_plan_info(const pixsht_plan *plan, int32_t info[16]);
+/* info: [0] nphi [1] nrings [2] lmax [3] mmax [4] dtype [5] device [6] npairs (north/south folded ring pairs)
+ *       [7] SM count [8] FFT length [9] kernels launched by the last execute [10..15] reserved */
+int pixsht_plan_weights(const pixsht_plan *plan, double *weights /* nrings */, double *theta /* nrings */);
+const char *pixsht_last_error(void);
+const char *pixsht_version(void);
+int pixsht_device_count(void);
+/* register-resident DFMA / FFMA chain micro-benchmark on `device`: measured peak in TFLOP/s (1 FMA = 2 flop) */
+int pixsht_measure_fma_peak(int device, double *fp64_tflops, double *fp32_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIXSHT_H */

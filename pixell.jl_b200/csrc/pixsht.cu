@@ -1,0 +1,700 @@
+// pixsht.cu -- plan object, C ABI (include/pixsht.h) and launch logic of libpixsht.so.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC (see build.sh).
+#include "common.cuh"
+#include "tables.cuh"
+#include "legendre.cuh"
+#include "fft.cuh"
+#include "../../include/pixsht.h"
+
+#include <algorithm>
+#include <chrono>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace pixsht;
+
+// ---------------------------------------------------------------------------------------------------------------
+// error plumbing: every entry point returns a status, the text is kept per host thread; nothing aborts.
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                                                      \
+    do {                                                                                                              \
+        cudaError_t e__ = (call);                                                                                     \
+        if (e__ != cudaSuccess)                                                                                       \
+            return fail(PIXSHT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                        \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    int alloc(size_t count)
+    {
+        release();
+        if (count == 0) return PIXSHT_OK;
+        if (cudaMalloc((void**)&p, count * sizeof(T)) != cudaSuccess) { p = nullptr; (void)cudaGetLastError(); return PIXSHT_ERR_NOMEM; }
+        n = count; return PIXSHT_OK;
+    }
+    int upload(const std::vector<T>& h)
+    {
+        int rc = alloc(h.size()); if (rc) return rc;
+        if (h.empty()) return PIXSHT_OK;
+        return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess ? PIXSHT_OK : PIXSHT_ERR_CUDA;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct pixsht_plan {
+    int device = 0, dtype = PIXSHT_F64, sm_count = 0;
+    int nphi = 0, nrings = 0, lmax = 0, mmax = 0;
+    int nx = 0, ny = 0, flipx = 0, flipy = 0;
+    double phi0 = 0;
+    long long nalm = 0;
+    int npairs = 0;
+    int R0 = 4, R2 = 2;           // ring pairs per thread in the spin-0 / spin-2 Legendre kernels
+    // FFT
+    int nfft = 0, nfac = 0, fac[FFT_MAXFAC] = {0}, fft_threads = 256;
+    size_t fft_smem = 0;
+    // geometry (host copies kept for introspection)
+    std::vector<double> h_theta, h_wgt;
+    // device tables
+    DevBuf<double> d_x, d_lsh_hi, d_lsh_lo, d_lch_hi, d_lch_lo, d_mlim, d_wgt, d_inv_ll1;
+    DevBuf<int> d_ringN, d_ringS;
+    DevBuf<double> d_lg0_hi, d_lg0_lo, d_lg2_hi, d_lg2_lo;
+    DevBuf<double> d_alpha0, d_gamma0, d_alpha2, d_gamma2;
+    DevBuf<double2> d_tw, d_phi0tw;
+    // work buffers (grown on demand)
+    DevBuf<double2> d_phase; int phase_ncomp = 0;
+    DevBuf<unsigned char> d_map[3], d_alm[3];
+    DevBuf<double2> d_alm64[3];
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    double timings[8] = {0};
+    int launches = 0;
+    std::mutex mu;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// small conversion / utility kernels
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_cvt_f32_to_f64(const float* __restrict__ in, double* __restrict__ out, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += step) out[i] = (double)in[i];
+}
+__global__ void k_cvt_f64_to_f32(const double* __restrict__ in, float* __restrict__ out, long long n)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += step) out[i] = (float)in[i];
+}
+
+#ifndef PIXSHT_EMU
+// register-resident FMA chains: 8 independent accumulators per thread, ITER*8 FMAs per thread
+template <class T>
+__global__ void __launch_bounds__(256) k_fma_peak(T* out, int iters, T a, T b)
+{
+    T v0 = (T)threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+            v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------------------------
+// plan construction
+// ---------------------------------------------------------------------------------------------------------------
+static const long double LPI = 3.14159265358979323846264338327950288L;
+
+static void split_dd(long double v, double& hi, double& lo)
+{
+    if (std::isinf((double)v) || v != v) { hi = (double)v; lo = 0.0; return; }
+    hi = (double)v; lo = (double)(v - (long double)hi);
+}
+
+static int factorize(int n, int* fac, int& nfac)
+{
+    nfac = 0;
+    // pass order = order of fac[]; larger radices first keeps early passes cheap in twiddles
+    while (n % 4 == 0) { if (nfac >= FFT_MAXFAC) return 1; fac[nfac++] = 4; n /= 4; }
+    while (n % 2 == 0) { if (nfac >= FFT_MAXFAC) return 1; fac[nfac++] = 2; n /= 2; }
+    for (int p = 3; n > 1; p += 2) {
+        while (n % p == 0) {
+            if (p > FFT_MAXRADIX || nfac >= FFT_MAXFAC) return 1;
+            fac[nfac++] = p; n /= p;
+        }
+        if ((long long)p * p > n && n > 1) {
+            if (n > FFT_MAXRADIX || nfac >= FFT_MAXFAC) return 1;
+            fac[nfac++] = n; n = 1;
+        }
+    }
+    return 0;
+}
+
+static int env_int(const char* name, int dflt)
+{
+    const char* s = getenv(name);
+    if (!s || !*s) return dflt;
+    return atoi(s);
+}
+
+static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const std::vector<double>& wgt_or_empty, int N_cc, int ring_first)
+{
+    const int nr = P->nrings, lmax = P->lmax, mmax = P->mmax;
+    P->nalm = pixsht_nalm(lmax, mmax);
+    P->h_theta = theta;
+    {
+        int v = env_int("PIXSHT_R0", 4); P->R0 = (v == 1 || v == 2 || v == 4) ? v : 4;
+        v = env_int("PIXSHT_R2", 2); P->R2 = (v == 1 || v == 2 || v == 4) ? v : 2;
+    }
+
+    // ---- north/south pairing (equatorial symmetry): pair rings whose cos(theta) are opposite ----
+    std::vector<long double> xs(nr);
+    for (int i = 0; i < nr; ++i) xs[i] = cosl((long double)theta[i]);
+    std::vector<int> ringN, ringS; std::vector<long double> thn;   // per pair: members and the north colatitude
+    {
+        std::vector<int> order(nr);
+        for (int i = 0; i < nr; ++i) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return xs[a] > xs[b]; });   // north pole first
+        int lo = 0, hi = nr - 1;
+        std::vector<char> used(nr, 0);
+        while (lo <= hi) {
+            const int a = order[lo], b = order[hi];
+            if (lo == hi) {
+                if (xs[a] >= 0) { ringN.push_back(a); ringS.push_back(-1); thn.push_back((long double)theta[a]); }
+                else { ringN.push_back(-1); ringS.push_back(a); thn.push_back(LPI - (long double)theta[a]); }
+                break;
+            }
+            const long double s = xs[a] + xs[b];
+            if (fabsl(s) < 1e-12L && xs[a] > 0) { ringN.push_back(a); ringS.push_back(b); thn.push_back((long double)theta[a]); ++lo; --hi; }
+            else if (xs[a] >= 0 && (s > 0 || xs[b] >= 0)) { ringN.push_back(a); ringS.push_back(-1); thn.push_back((long double)theta[a]); ++lo; }
+            else { ringN.push_back(-1); ringS.push_back(b); thn.push_back(LPI - (long double)theta[b]); --hi; }
+        }
+        // order pairs by north colatitude so that a warp's pairs are neighbours on the sky
+        std::vector<int> po(ringN.size());
+        for (size_t i = 0; i < po.size(); ++i) po[i] = (int)i;
+        std::sort(po.begin(), po.end(), [&](int a, int b) { return thn[a] < thn[b]; });
+        std::vector<int> rn2, rs2; std::vector<long double> th2;
+        for (int i : po) { rn2.push_back(ringN[i]); rs2.push_back(ringS[i]); th2.push_back(thn[i]); }
+        ringN.swap(rn2); ringS.swap(rs2); thn.swap(th2);
+    }
+    const int np = (int)ringN.size();
+    P->npairs = np;
+    std::vector<double> hx(np), lsh_hi(np), lsh_lo(np), lch_hi(np), lch_lo(np), mlim(np);
+    const double ofs = std::max(100.0, 0.01 * lmax) + 4.0;
+    for (int i = 0; i < np; ++i) {
+        const long double t = thn[i];
+        hx[i] = (double)cosl(t);
+        const long double sh = sinl(0.5L * t), ch = cosl(0.5L * t);
+        split_dd(sh > 0 ? log2l(sh) : -HUGE_VALL, lsh_hi[i], lsh_lo[i]);
+        split_dd(ch > 0 ? log2l(ch) : -HUGE_VALL, lch_hi[i], lch_lo[i]);
+        mlim[i] = (double)lmax * (double)sinl(t) + ofs;   // pairs with m > mlim never reach 2^-90 for l <= lmax
+    }
+
+    // ---- seed prefactors per m (long double running sums) ----
+    std::vector<double> lg0_hi(mmax + 1), lg0_lo(mmax + 1), lg2_hi(mmax + 1), lg2_lo(mmax + 1);
+    {
+        // spin 0: lambda_mm = (-1)^m sqrt((2m+1)/(4 pi) prod_{k<=m} (2k-1)/(2k)) (2 sh ch)^m
+        long double acc = 0.0L;
+        for (int m = 0; m <= mmax; ++m) {
+            if (m > 0) acc += log2l((2.0L * m - 1.0L) / (2.0L * m));
+            const long double v = 0.5L * (log2l((2.0L * m + 1.0L) / (4.0L * LPI)) + acc) + (long double)m;
+            split_dd(v, lg0_hi[m], lg0_lo[m]);
+        }
+        // spin 2: sqrt((2 l0+1)/(4 pi) (2 l0)!/((l0-q)!(l0+q)!)), l0 = max(m,2), q = min(m,2)
+        long double cacc = 0.0L;  // log2 C(2m, m+2), m >= 2
+        for (int m = 0; m <= mmax; ++m) {
+            long double v;
+            if (m < 2) v = 0.5L * (log2l(5.0L / (4.0L * LPI)) + log2l(m == 0 ? 6.0L : 4.0L));
+            else {
+                if (m > 2) cacc += log2l((2.0L * m) * (2.0L * m - 1.0L) / ((m + 2.0L) * (m - 2.0L)));
+                v = 0.5L * (log2l((2.0L * m + 1.0L) / (4.0L * LPI)) + cacc);
+            }
+            split_dd(v, lg2_hi[m], lg2_lo[m]);
+        }
+    }
+
+    // ---- e^{+i m phi0} ----
+    std::vector<double2> ph0(mmax + 1);
+    for (int m = 0; m <= mmax; ++m) {
+        const long double ang = fmodl((long double)m * (long double)P->phi0, 2.0L * LPI);
+        ph0[m] = make_double2((double)cosl(ang), (double)sinl(ang));
+    }
+
+    // ---- FFT plan ----
+    if (P->nphi % 2 != 0) return fail(PIXSHT_ERR_UNSUPPORTED, "odd ring length nphi is not supported");
+    P->nfft = P->nphi / 2;
+    if (factorize(P->nfft, P->fac, P->nfac)) return fail(PIXSHT_ERR_UNSUPPORTED, "nphi/2 has a prime factor > 64");
+    const size_t elem = (P->dtype == PIXSHT_F64) ? 16 : 8;
+    P->fft_smem = (size_t)(P->nfft + 1) * elem;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, P->device));
+    P->sm_count = prop.multiProcessorCount;
+    if (P->fft_smem > prop.sharedMemPerBlockOptin)
+        return fail(PIXSHT_ERR_UNSUPPORTED, "ring too long for the single-CTA shared-memory FFT (nphi/2 complex samples must fit in 227 KB)");
+    P->fft_threads = P->nfft >= 4096 ? 1024 : (P->nfft >= 1024 ? 512 : (P->nfft >= 256 ? 256 : 64));
+
+    // ---- upload ----
+    int rc = 0;
+    rc |= P->d_x.upload(hx); rc |= P->d_lsh_hi.upload(lsh_hi); rc |= P->d_lsh_lo.upload(lsh_lo);
+    rc |= P->d_lch_hi.upload(lch_hi); rc |= P->d_lch_lo.upload(lch_lo); rc |= P->d_mlim.upload(mlim);
+    rc |= P->d_ringN.upload(ringN); rc |= P->d_ringS.upload(ringS);
+    rc |= P->d_lg0_hi.upload(lg0_hi); rc |= P->d_lg0_lo.upload(lg0_lo); rc |= P->d_lg2_hi.upload(lg2_hi); rc |= P->d_lg2_lo.upload(lg2_lo);
+    rc |= P->d_phi0tw.upload(ph0);
+    rc |= P->d_wgt.alloc(nr); rc |= P->d_inv_ll1.alloc(lmax + 1); rc |= P->d_tw.alloc(P->nphi);
+    rc |= P->d_alpha0.alloc(P->nalm); rc |= P->d_gamma0.alloc(P->nalm);
+    rc |= P->d_alpha2.alloc(P->nalm); rc |= P->d_gamma2.alloc(P->nalm);
+    if (rc) return fail(PIXSHT_ERR_NOMEM, "device allocation of plan tables failed");
+
+    CU(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
+    for (auto& e : P->ev) CU(cudaEventCreate(&e));
+
+    // ---- device-side precompute ----
+    if (wgt_or_empty.empty()) {
+        PIXSHT_LAUNCH(k_cc_weights, (nr + 127) / 128, 128, 0, P->stream, N_cc, P->nphi, ring_first, nr, P->d_wgt.p);
+    } else {
+        CU(cudaMemcpyAsync(P->d_wgt.p, wgt_or_empty.data(), sizeof(double) * nr, cudaMemcpyHostToDevice, P->stream));
+    }
+    PIXSHT_LAUNCH(k_inv_ll1, (lmax + 128) / 128, 128, 0, P->stream, lmax, P->d_inv_ll1.p);
+    PIXSHT_LAUNCH(k_twiddles, (P->nphi + 127) / 128, 128, 0, P->stream, P->nphi, P->d_tw.p);
+    PIXSHT_LAUNCH(k_coef_tables, (mmax + 64) / 64, 64, 0, P->stream, lmax, mmax, 0, P->d_alpha0.p, P->d_gamma0.p);
+    PIXSHT_LAUNCH(k_coef_tables, (mmax + 64) / 64, 64, 0, P->stream, lmax, mmax, 2, P->d_alpha2.p, P->d_gamma2.p);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(P->stream));
+    P->h_wgt.resize(nr);
+    CU(cudaMemcpy(P->h_wgt.data(), P->d_wgt.p, sizeof(double) * nr, cudaMemcpyDeviceToHost));
+
+#ifndef PIXSHT_EMU
+    // opt in to large dynamic shared memory
+    if (P->dtype == PIXSHT_F64) {
+        CU(cudaFuncSetAttribute(fft_phase2map<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
+        CU(cudaFuncSetAttribute(fft_map2phase<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
+    } else {
+        CU(cudaFuncSetAttribute(fft_phase2map<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
+        CU(cudaFuncSetAttribute(fft_map2phase<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
+    }
+    CU(cudaFuncSetAttribute(leg_anal<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leg_anal_smem<0>()));
+    CU(cudaFuncSetAttribute(leg_anal<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leg_anal_smem<0>()));
+    CU(cudaFuncSetAttribute(leg_anal<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leg_anal_smem<0>()));
+    CU(cudaFuncSetAttribute(leg_anal<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leg_anal_smem<2>()));
+    CU(cudaFuncSetAttribute(leg_anal<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leg_anal_smem<2>()));
+    CU(cudaFuncSetAttribute(leg_anal<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leg_anal_smem<2>()));
+#endif
+    return PIXSHT_OK;
+}
+
+static int check_device(int device)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        return fail(PIXSHT_ERR_NODEVICE, "no CUDA device available: libpixsht has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(PIXSHT_ERR_ARG, "device index out of range");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(PIXSHT_ERR_CUDA, "cudaSetDevice failed");
+    return PIXSHT_OK;
+}
+
+extern "C" int64_t pixsht_nalm(int lmax, int mmax)
+{
+    return (int64_t)(mmax + 1) * (lmax + 1) - (int64_t)mmax * (mmax + 1) / 2;
+}
+
+extern "C" int pixsht_plan_create(pixsht_plan** out, const pixsht_geom* g, int lmax, int mmax, int dtype, int device)
+{
+    if (!out || !g) return fail(PIXSHT_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (lmax < 0 || mmax < 0 || mmax > lmax) return fail(PIXSHT_ERR_ARG, "need 0 <= mmax <= lmax");
+    if (dtype != PIXSHT_F64 && dtype != PIXSHT_F32) return fail(PIXSHT_ERR_ARG, "dtype must be PIXSHT_F64 or PIXSHT_F32");
+    if (g->nphi < 2 || g->nrings_total < 2 || g->nrings < 1 || g->ring_first < 0 || g->ring_first + g->nrings > g->nrings_total)
+        return fail(PIXSHT_ERR_ARG, "inconsistent ring geometry");
+    if (g->nx < 1 || g->nx > g->nphi) return fail(PIXSHT_ERR_ARG, "need 1 <= nx <= nphi");
+    int rc = check_device(device); if (rc) return rc;
+    pixsht_plan* P = new pixsht_plan();
+    P->device = device; P->dtype = dtype; P->nphi = g->nphi; P->nrings = g->nrings; P->lmax = lmax; P->mmax = mmax;
+    P->nx = g->nx; P->ny = g->nrings; P->flipx = g->flipx != 0; P->flipy = g->flipy != 0; P->phi0 = g->phi0;
+    // theta_k = pi k/(N-1) rounded to double, as range(0, pi, length=N)[k] gives the reference (src/transforms.jl:46)
+    std::vector<double> theta(g->nrings);
+    for (int i = 0; i < g->nrings; ++i)
+        theta[i] = (double)(LPI * (long double)(g->ring_first + i) / (long double)(g->nrings_total - 1));
+    rc = plan_build(P, theta, std::vector<double>(), g->nrings_total, g->ring_first);
+    if (rc) { std::string keep = g_err; pixsht_plan_destroy(P); g_err = keep; return rc; }
+    *out = P;
+    return PIXSHT_OK;
+}
+
+extern "C" int pixsht_plan_create_rings(pixsht_plan** out, int nrings, const double* theta, const double* weight, int nphi,
+                                        double phi0, int lmax, int mmax, int dtype, int device)
+{
+    if (!out || !theta || !weight) return fail(PIXSHT_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (lmax < 0 || mmax < 0 || mmax > lmax) return fail(PIXSHT_ERR_ARG, "need 0 <= mmax <= lmax");
+    if (dtype != PIXSHT_F64 && dtype != PIXSHT_F32) return fail(PIXSHT_ERR_ARG, "dtype must be PIXSHT_F64 or PIXSHT_F32");
+    if (nrings < 1 || nphi < 2) return fail(PIXSHT_ERR_ARG, "inconsistent ring geometry");
+    for (int i = 0; i < nrings; ++i)
+        if (!(theta[i] >= 0.0 && theta[i] <= 3.1415926535897936)) return fail(PIXSHT_ERR_ARG, "theta outside [0, pi]");
+    int rc = check_device(device); if (rc) return rc;
+    pixsht_plan* P = new pixsht_plan();
+    P->device = device; P->dtype = dtype; P->nphi = nphi; P->nrings = nrings; P->lmax = lmax; P->mmax = mmax;
+    P->nx = nphi; P->ny = nrings; P->flipx = 0; P->flipy = 0; P->phi0 = phi0;
+    std::vector<double> th(theta, theta + nrings), w(weight, weight + nrings);
+    rc = plan_build(P, th, w, 0, 0);
+    if (rc) { std::string keep = g_err; pixsht_plan_destroy(P); g_err = keep; return rc; }
+    *out = P;
+    return PIXSHT_OK;
+}
+
+extern "C" void pixsht_plan_destroy(pixsht_plan* P)
+{
+    if (!P) return;
+    // may run from a GC finalizer thread, possibly after the CUDA context is gone: every call below tolerates failure
+    (void)cudaSetDevice(P->device);
+    P->d_x.release(); P->d_lsh_hi.release(); P->d_lsh_lo.release(); P->d_lch_hi.release(); P->d_lch_lo.release();
+    P->d_mlim.release(); P->d_wgt.release(); P->d_inv_ll1.release(); P->d_ringN.release(); P->d_ringS.release();
+    P->d_lg0_hi.release(); P->d_lg0_lo.release(); P->d_lg2_hi.release(); P->d_lg2_lo.release();
+    P->d_alpha0.release(); P->d_gamma0.release(); P->d_alpha2.release(); P->d_gamma2.release();
+    P->d_tw.release(); P->d_phi0tw.release(); P->d_phase.release();
+    for (int c = 0; c < 3; ++c) { P->d_map[c].release(); P->d_alm[c].release(); P->d_alm64[c].release(); }
+    for (auto& e : P->ev) if (e) cudaEventDestroy(e);
+    if (P->stream) cudaStreamDestroy(P->stream);
+    (void)cudaGetLastError();
+    delete P;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stage launches
+// ---------------------------------------------------------------------------------------------------------------
+static LegParams leg_params(pixsht_plan* P, int spin, int R, int nm, const int* d_m_list, double2* phase, long long stride_c,
+                            long long stride_m)
+{
+    LegParams L;
+    memset(&L, 0, sizeof(L));
+    L.lmax = P->lmax; L.mmax = P->mmax; L.nm = nm; L.m_list = d_m_list;
+    L.npairs = P->npairs; L.nchunks = (P->npairs + LEG_NT * R - 1) / (LEG_NT * R);
+    L.x = P->d_x.p; L.lsh_hi = P->d_lsh_hi.p; L.lsh_lo = P->d_lsh_lo.p; L.lch_hi = P->d_lch_hi.p; L.lch_lo = P->d_lch_lo.p;
+    L.ringN = P->d_ringN.p; L.ringS = P->d_ringS.p; L.mlim = P->d_mlim.p;
+    if (spin == 0) { L.lgpref_hi = P->d_lg0_hi.p; L.lgpref_lo = P->d_lg0_lo.p; L.alpha = P->d_alpha0.p; L.gamma = P->d_gamma0.p; }
+    else { L.lgpref_hi = P->d_lg2_hi.p; L.lgpref_lo = P->d_lg2_lo.p; L.alpha = P->d_alpha2.p; L.gamma = P->d_gamma2.p; }
+    L.inv_ll1 = P->d_inv_ll1.p;
+    L.phase = phase; L.stride_c = stride_c; L.stride_m = stride_m;
+    return L;
+}
+
+template <int SPIN>
+static void launch_synth(pixsht_plan* P, int R, const LegParams& L, cudaStream_t st)
+{
+    const int grid = L.nm * L.nchunks;
+    void (*k)(const LegParams) = (R == 1) ? leg_synth<SPIN, 1> : (R == 2 ? leg_synth<SPIN, 2> : leg_synth<SPIN, 4>);
+    PIXSHT_LAUNCH(k, grid, LEG_NT, 0, st, L);
+    P->launches++;
+}
+template <int SPIN>
+static void launch_anal(pixsht_plan* P, int R, const LegParams& L, cudaStream_t st)
+{
+    const int grid = L.nm * L.nchunks;
+    const size_t sm = leg_anal_smem<SPIN>();
+    void (*k)(const LegParams) = (R == 1) ? leg_anal<SPIN, 1> : (R == 2 ? leg_anal<SPIN, 2> : leg_anal<SPIN, 4>);
+    PIXSHT_LAUNCH(k, grid, LEG_NT, sm, st, L);
+    P->launches++;
+}
+
+// alm component layout per ncomp: ncomp 1: [T]; 2: [E,B]; 3: [T,E,B].  phase/map components likewise [T] / [Q,U] / [T,Q,U].
+static int stage_alm2phase(pixsht_plan* P, int ncomp, const double2* const* alm, int nm, const int* d_m_list, double2* phase,
+                           long long stride_c, long long stride_m, cudaStream_t st)
+{
+    if (ncomp == 1 || ncomp == 3) {
+        LegParams L = leg_params(P, 0, P->R0, nm, d_m_list, phase, stride_c, stride_m);
+        L.alm_in0 = alm[0];
+        launch_synth<0>(P, P->R0, L, st);
+    }
+    if (ncomp >= 2) {
+        const int c0 = ncomp == 3 ? 1 : 0;
+        LegParams L = leg_params(P, 2, P->R2, nm, d_m_list, phase + (long long)c0 * stride_c, stride_c, stride_m);
+        L.alm_in0 = alm[c0]; L.alm_in1 = alm[c0 + 1];
+        launch_synth<2>(P, P->R2, L, st);
+    }
+    CU(cudaGetLastError());
+    return PIXSHT_OK;
+}
+
+static int stage_phase2alm(pixsht_plan* P, int ncomp, double2* phase, long long stride_c, long long stride_m, int nm,
+                           const int* d_m_list, double2* const* alm, cudaStream_t st)
+{
+    if (ncomp == 1 || ncomp == 3) {
+        LegParams L = leg_params(P, 0, P->R0, nm, d_m_list, phase, stride_c, stride_m);
+        L.alm_out0 = alm[0];
+        launch_anal<0>(P, P->R0, L, st);
+    }
+    if (ncomp >= 2) {
+        const int c0 = ncomp == 3 ? 1 : 0;
+        LegParams L = leg_params(P, 2, P->R2, nm, d_m_list, phase + (long long)c0 * stride_c, stride_c, stride_m);
+        L.alm_out0 = alm[c0]; L.alm_out1 = alm[c0 + 1];
+        launch_anal<2>(P, P->R2, L, st);
+    }
+    CU(cudaGetLastError());
+    return PIXSHT_OK;
+}
+
+static FftParams fft_params(pixsht_plan* P, int ncomp, double2* phase, long long stride_c, long long stride_m, const int* d_m_row,
+                            int ring_begin, int ring_count, void* const* maps)
+{
+    FftParams F;
+    memset(&F, 0, sizeof(F));
+    F.nphi = P->nphi; F.n = P->nfft; F.nfac = P->nfac;
+    for (int i = 0; i < P->nfac; ++i) F.fac[i] = P->fac[i];
+    F.tw = P->d_tw.p; F.phi0tw = P->d_phi0tw.p; F.wgt = P->d_wgt.p; F.mmax = P->mmax; F.m_row = d_m_row;
+    F.phase = phase; F.stride_c = stride_c; F.stride_m = stride_m;
+    F.ring_begin = ring_begin; F.ring_count = ring_count;
+    F.nx = P->nx; F.ny = P->ny; F.flipx = P->flipx; F.flipy = P->flipy;
+    for (int c = 0; c < ncomp; ++c) F.maps[c] = maps[c];
+    return F;
+}
+
+static int stage_fft(pixsht_plan* P, int dir, int ncomp, double2* phase, long long stride_c, long long stride_m, const int* d_m_row,
+                     int ring_begin, int ring_count, void* const* maps, cudaStream_t st)
+{
+    if (ring_count <= 0) return PIXSHT_OK;
+    FftParams F = fft_params(P, ncomp, phase, stride_c, stride_m, d_m_row, ring_begin, ring_count, maps);
+    dim3 grid(ring_count, ncomp);
+    if (P->dtype == PIXSHT_F64) {
+        if (dir == PIXSHT_ALM2MAP) PIXSHT_LAUNCH(fft_phase2map<double>, grid, P->fft_threads, P->fft_smem, st, F);
+        else PIXSHT_LAUNCH(fft_map2phase<double>, grid, P->fft_threads, P->fft_smem, st, F);
+    } else {
+        if (dir == PIXSHT_ALM2MAP) PIXSHT_LAUNCH(fft_phase2map<float>, grid, P->fft_threads, P->fft_smem, st, F);
+        else PIXSHT_LAUNCH(fft_map2phase<float>, grid, P->fft_threads, P->fft_smem, st, F);
+    }
+    P->launches++;
+    CU(cudaGetLastError());
+    return PIXSHT_OK;
+}
+
+static int ensure_phase(pixsht_plan* P, int ncomp)
+{
+    if (P->phase_ncomp >= ncomp) return PIXSHT_OK;
+    if (P->d_phase.alloc((size_t)ncomp * (P->mmax + 1) * P->nrings)) return fail(PIXSHT_ERR_NOMEM, "phase buffer allocation failed");
+    P->phase_ncomp = ncomp;
+    return PIXSHT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pixsht_execute
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int pixsht_execute(pixsht_plan* P, int direction, int ncomp, void* const* alms, void* const* maps, int location)
+{
+    if (!P || !alms || !maps) return fail(PIXSHT_ERR_ARG, "null argument");
+    if (direction != PIXSHT_MAP2ALM && direction != PIXSHT_ALM2MAP) return fail(PIXSHT_ERR_ARG, "bad direction");
+    if (ncomp < 1 || ncomp > 3) return fail(PIXSHT_ERR_ARG, "SHTs require 1 <= ncomp <= 3, for I, QU, and IQU.");
+    if (location != PIXSHT_HOST && location != PIXSHT_DEVICE) return fail(PIXSHT_ERR_ARG, "bad location");
+    for (int c = 0; c < ncomp; ++c) if (!alms[c] || !maps[c]) return fail(PIXSHT_ERR_ARG, "null component pointer");
+    std::lock_guard<std::mutex> lock(P->mu);
+    int rc = check_device(P->device); if (rc) return rc;
+    const auto t_begin = std::chrono::steady_clock::now();
+    cudaStream_t st = P->stream;
+    const bool f32 = P->dtype == PIXSHT_F32;
+    const size_t esz = f32 ? 4 : 8;
+    const size_t map_bytes = (size_t)P->nx * P->ny * esz, alm_bytes = (size_t)P->nalm * 2 * esz;
+    P->launches = 0;
+    rc = ensure_phase(P, ncomp); if (rc) return rc;
+
+    void* dmap[3] = {nullptr, nullptr, nullptr};
+    void* dalm[3] = {nullptr, nullptr, nullptr};     // boundary dtype
+    double2* dalm64[3] = {nullptr, nullptr, nullptr}; // what the Legendre kernels see
+    for (int c = 0; c < ncomp; ++c) {
+        if (location == PIXSHT_HOST) {
+            if (P->d_map[c].n < map_bytes && P->d_map[c].alloc(map_bytes)) return fail(PIXSHT_ERR_NOMEM, "map staging allocation failed");
+            if (P->d_alm[c].n < alm_bytes && P->d_alm[c].alloc(alm_bytes)) return fail(PIXSHT_ERR_NOMEM, "alm staging allocation failed");
+            dmap[c] = P->d_map[c].p; dalm[c] = P->d_alm[c].p;
+        } else { dmap[c] = maps[c]; dalm[c] = alms[c]; }
+        if (f32) {
+            if (P->d_alm64[c].n < (size_t)P->nalm && P->d_alm64[c].alloc(P->nalm)) return fail(PIXSHT_ERR_NOMEM, "alm work buffer allocation failed");
+            dalm64[c] = P->d_alm64[c].p;
+        } else dalm64[c] = reinterpret_cast<double2*>(dalm[c]);
+    }
+    const long long stride_m = P->nrings, stride_c = (long long)(P->mmax + 1) * P->nrings;
+    const int cvt_grid = P->sm_count > 0 ? P->sm_count * 8 : 256;
+
+    CU(cudaEventRecord(P->ev[0], st));
+    if (direction == PIXSHT_ALM2MAP) {
+        if (location == PIXSHT_HOST)
+            for (int c = 0; c < ncomp; ++c) CU(cudaMemcpyAsync(dalm[c], alms[c], alm_bytes, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(P->ev[1], st));
+        if (f32)
+            for (int c = 0; c < ncomp; ++c) {
+                PIXSHT_LAUNCH(k_cvt_f32_to_f64, cvt_grid, 256, 0, st, (const float*)dalm[c], (double*)dalm64[c], 2 * P->nalm);
+                P->launches++;
+            }
+        rc = stage_alm2phase(P, ncomp, dalm64, P->mmax + 1, nullptr, P->d_phase.p, stride_c, stride_m, st); if (rc) return rc;
+        CU(cudaEventRecord(P->ev[2], st));
+        rc = stage_fft(P, PIXSHT_ALM2MAP, ncomp, P->d_phase.p, stride_c, stride_m, nullptr, 0, P->nrings, dmap, st); if (rc) return rc;
+        CU(cudaEventRecord(P->ev[3], st));
+        if (location == PIXSHT_HOST)
+            for (int c = 0; c < ncomp; ++c) CU(cudaMemcpyAsync(maps[c], dmap[c], map_bytes, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(P->ev[4], st));
+    } else {
+        if (location == PIXSHT_HOST)
+            for (int c = 0; c < ncomp; ++c) CU(cudaMemcpyAsync(dmap[c], maps[c], map_bytes, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(P->ev[1], st));
+        rc = stage_fft(P, PIXSHT_MAP2ALM, ncomp, P->d_phase.p, stride_c, stride_m, nullptr, 0, P->nrings, dmap, st); if (rc) return rc;
+        CU(cudaEventRecord(P->ev[2], st));
+        for (int c = 0; c < ncomp; ++c) CU(cudaMemsetAsync(dalm64[c], 0, (size_t)P->nalm * sizeof(double2), st));
+        rc = stage_phase2alm(P, ncomp, P->d_phase.p, stride_c, stride_m, P->mmax + 1, nullptr, dalm64, st); if (rc) return rc;
+        if (f32)
+            for (int c = 0; c < ncomp; ++c) {
+                PIXSHT_LAUNCH(k_cvt_f64_to_f32, cvt_grid, 256, 0, st, (const double*)dalm64[c], (float*)dalm[c], 2 * P->nalm);
+                P->launches++;
+            }
+        CU(cudaEventRecord(P->ev[3], st));
+        if (location == PIXSHT_HOST)
+            for (int c = 0; c < ncomp; ++c) CU(cudaMemcpyAsync(alms[c], dalm[c], alm_bytes, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(P->ev[4], st));
+    }
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    float ms[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&ms[i], P->ev[i], P->ev[i + 1]));
+    for (auto& t : P->timings) t = 0;
+    P->timings[0] = ms[0];
+    if (direction == PIXSHT_ALM2MAP) { P->timings[1] = ms[1]; P->timings[2] = ms[2]; }
+    else { P->timings[2] = ms[1]; P->timings[1] = ms[2]; }
+    P->timings[3] = ms[3];
+    P->timings[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    return PIXSHT_OK;
+}
+
+extern "C" int pixsht_get_timings(const pixsht_plan* P, double ms[8])
+{
+    if (!P || !ms) return fail(PIXSHT_ERR_ARG, "null argument");
+    for (int i = 0; i < 8; ++i) ms[i] = P->timings[i];
+    return PIXSHT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stage API (multi-GPU pipeline)
+// ---------------------------------------------------------------------------------------------------------------
+static int stage_common(pixsht_plan* P, int ncomp)
+{
+    if (!P) return fail(PIXSHT_ERR_ARG, "null plan");
+    if (ncomp < 1 || ncomp > 3) return fail(PIXSHT_ERR_ARG, "SHTs require 1 <= ncomp <= 3, for I, QU, and IQU.");
+    if (P->dtype != PIXSHT_F64) return fail(PIXSHT_ERR_UNSUPPORTED, "the stage API works on Float64 plans");
+    return check_device(P->device);
+}
+
+extern "C" int pixsht_stage_alm2phase(pixsht_plan* P, int ncomp, const void* const* d_alms, int nm, const int32_t* d_m_list,
+                                      void* d_phase, void* stream)
+{
+    int rc = stage_common(P, ncomp); if (rc) return rc;
+    if (!d_alms || !d_phase || nm < 0 || nm > P->mmax + 1) return fail(PIXSHT_ERR_ARG, "bad argument");
+    if (nm == 0) return PIXSHT_OK;
+    const double2* alm[3] = {nullptr, nullptr, nullptr};
+    for (int c = 0; c < ncomp; ++c) alm[c] = (const double2*)d_alms[c];
+    return stage_alm2phase(P, ncomp, alm, nm, d_m_list, (double2*)d_phase, (long long)nm * P->nrings, P->nrings, (cudaStream_t)stream);
+}
+
+extern "C" int pixsht_stage_phase2alm(pixsht_plan* P, int ncomp, const void* d_phase, int nm, const int32_t* d_m_list,
+                                      void* const* d_alms, void* stream)
+{
+    int rc = stage_common(P, ncomp); if (rc) return rc;
+    if (!d_alms || !d_phase || nm < 0 || nm > P->mmax + 1) return fail(PIXSHT_ERR_ARG, "bad argument");
+    if (nm == 0) return PIXSHT_OK;
+    double2* alm[3] = {nullptr, nullptr, nullptr};
+    for (int c = 0; c < ncomp; ++c) alm[c] = (double2*)d_alms[c];
+    return stage_phase2alm(P, ncomp, (double2*)d_phase, (long long)nm * P->nrings, P->nrings, nm, d_m_list, alm, (cudaStream_t)stream);
+}
+
+extern "C" int pixsht_stage_phase2map(pixsht_plan* P, int ncomp, const void* d_phase, const int32_t* d_m_row, int ring_begin,
+                                      int ring_count, void* const* d_maps, void* stream)
+{
+    int rc = stage_common(P, ncomp); if (rc) return rc;
+    if (!d_maps || !d_phase || ring_begin < 0 || ring_count < 0 || ring_begin + ring_count > P->nrings) return fail(PIXSHT_ERR_ARG, "bad argument");
+    return stage_fft(P, PIXSHT_ALM2MAP, ncomp, (double2*)d_phase, (long long)(P->mmax + 1) * ring_count, ring_count, d_m_row,
+                     ring_begin, ring_count, d_maps, (cudaStream_t)stream);
+}
+
+extern "C" int pixsht_stage_map2phase(pixsht_plan* P, int ncomp, const void* const* d_maps, const int32_t* d_m_row, int ring_begin,
+                                      int ring_count, void* d_phase, void* stream)
+{
+    int rc = stage_common(P, ncomp); if (rc) return rc;
+    if (!d_maps || !d_phase || ring_begin < 0 || ring_count < 0 || ring_begin + ring_count > P->nrings) return fail(PIXSHT_ERR_ARG, "bad argument");
+    return stage_fft(P, PIXSHT_MAP2ALM, ncomp, (double2*)d_phase, (long long)(P->mmax + 1) * ring_count, ring_count, d_m_row,
+                     ring_begin, ring_count, (void* const*)d_maps, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// introspection
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int pixsht_plan_info(const pixsht_plan* P, int32_t info[16])
+{
+    if (!P || !info) return fail(PIXSHT_ERR_ARG, "null argument");
+    for (int i = 0; i < 16; ++i) info[i] = 0;
+    info[0] = P->nphi; info[1] = P->nrings; info[2] = P->lmax; info[3] = P->mmax; info[4] = P->dtype; info[5] = P->device;
+    info[6] = P->npairs; info[7] = P->sm_count; info[8] = P->nfft; info[9] = P->launches; info[10] = P->R0; info[11] = P->R2;
+    return PIXSHT_OK;
+}
+
+extern "C" int pixsht_plan_weights(const pixsht_plan* P, double* weights, double* theta)
+{
+    if (!P) return fail(PIXSHT_ERR_ARG, "null argument");
+    if (weights) memcpy(weights, P->h_wgt.data(), sizeof(double) * P->nrings);
+    if (theta) memcpy(theta, P->h_theta.data(), sizeof(double) * P->nrings);
+    return PIXSHT_OK;
+}
+
+extern "C" const char* pixsht_last_error(void) { return g_err.c_str(); }
+extern "C" const char* pixsht_version(void)
+{
+#ifdef PIXSHT_EMU
+    return "pixsht 0.1 (HOST EMULATION BUILD - tests only)";
+#else
+    return "pixsht 0.1 (sm_100a)";
+#endif
+}
+extern "C" int pixsht_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int pixsht_measure_fma_peak(int device, double* fp64_tflops, double* fp32_tflops)
+{
+#ifdef PIXSHT_EMU
+    (void)device; (void)fp64_tflops; (void)fp32_tflops;
+    return fail(PIXSHT_ERR_UNSUPPORTED, "not available in the host emulation build");
+#else
+    int rc = check_device(device); if (rc) return rc;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    void* buf = nullptr;
+    CU(cudaMalloc(&buf, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    for (int pass = 0; pass < 2; ++pass) {
+        const int iters = pass == 0 ? 4096 : 16384;   // fp64, fp32
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            CU(cudaEventRecord(e0, 0));
+            if (pass == 0) k_fma_peak<double><<<blocks, threads>>>((double*)buf, iters, 1.0000001, 1e-9);
+            else k_fma_peak<float><<<blocks, threads>>>((float*)buf, iters, 1.0000001f, 1e-9f);
+            CU(cudaEventRecord(e1, 0));
+            CU(cudaEventSynchronize(e1));
+            float ms; CU(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+        const double tf = flops / ((double)best * 1e-3) / 1e12;
+        if (pass == 0) { if (fp64_tflops) *fp64_tflops = tf; }
+        else { if (fp32_tflops) *fp32_tflops = tf; }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+    CU(cudaGetLastError());
+    return PIXSHT_OK;
+#endif
+}

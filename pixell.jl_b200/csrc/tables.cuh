@@ -1,0 +1,80 @@
+// tables.cuh -- device-side precompute: quadrature weights, recurrence coefficient tables, FFT twiddles.
+// Replaces the per-call host setup of the reference (src/transforms.jl:44-46: FastTransforms CC weights; libsharp2's
+// per-m sharp_Ylmgen_prepare) by one-off kernels at plan creation.
+#pragma once
+#include "common.cuh"
+
+namespace pixsht {
+
+// Clenshaw-Curtis ring weights w_k = c_k * 2pi/nphi for band rings k = ring_first .. ring_first+nrings-1 of the
+// N-ring full-sky grid (closed form of SURVEY.md A.2; end points from the exact 1/(n^2-1+n%2)).
+__global__ void k_cc_weights(int N, int nphi, int ring_first, int nrings, double* __restrict__ w)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrings) return;
+    const int k = ring_first + i;
+    const int n = N - 1;
+    const double scale = 2.0 * 3.14159265358979323846 / (double)nphi;
+    if (N == 1) { w[i] = 2.0 * scale; return; }
+    if (k == 0 || k == n) { w[i] = scale / ((double)n * (double)n - 1.0 + (double)(n & 1)); return; }
+    // sum small terms first (q descending) for accuracy
+    double s = 0.0;
+    for (int q = n / 2; q >= 1; --q) {
+        const double b = (2 * q == n) ? 1.0 : 2.0;
+        const long long t = ((long long)2 * q * k) % (2LL * n);  // exact argument reduction of 2 q k pi / n
+        s += b / (4.0 * (double)q * (double)q - 1.0) * cospi((double)t / (double)n);
+    }
+    w[i] = (2.0 / (double)n) * (1.0 - s) * scale;
+}
+
+// A_l of lambda_{l+1} = A_l (x - mu_l) lambda_l - (A_l/A_{l-1}) lambda_{l-1}   (normalised d-functions)
+__device__ __forceinline__ double coefA(int l, int m, int s)
+{
+    const double l1 = (double)(l + 1);
+    const double num = (double)(2 * l + 1) * (double)(2 * l + 3);
+    const double den = ((l1 - (double)m) * (l1 + (double)m)) * ((l1 - (double)s) * (l1 + (double)s));
+    return l1 * sqrt(num / den);
+}
+
+// Per m (one thread each): alpha_l and gamma_l, l = l0..lmax, l0 = max(m, s), stored at alm_index(lmax, l, m).
+// lambda_l = gamma_l p_l with p_{l+1} = (alpha_l x + delta_l) p_l - p_{l-1}  (unit lower coefficient => 2 FMA per step):
+//   gamma_{l0} = gamma_{l0+1} = 1, gamma_{l+1} = (A_l/A_{l-1}) gamma_{l-1}, alpha_l = A_l gamma_l / gamma_{l+1}.
+__global__ void k_coef_tables(int lmax, int mmax, int s, double* __restrict__ alpha, double* __restrict__ gamma)
+{
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m > mmax) return;
+    const int l0 = m > s ? m : s;
+    const long long base = alm_index(lmax, 0, m);
+    for (int l = m; l < l0 && l <= lmax; ++l) { alpha[base + l] = 0.0; gamma[base + l] = 0.0; }
+    if (l0 > lmax) return;
+    double Aprev = coefA(l0, m, s);
+    double g_lm1 = 1.0, g_l = 1.0;  // gamma_{l-1}, gamma_l while stepping; start at l = l0+1
+    gamma[base + l0] = 1.0;
+    alpha[base + l0] = Aprev;       // gamma_{l0}/gamma_{l0+1} = 1
+    for (int l = l0 + 1; l <= lmax; ++l) {
+        const double A = coefA(l, m, s);
+        const double g_lp1 = (A / Aprev) * g_lm1;
+        gamma[base + l] = g_l;
+        alpha[base + l] = A * g_l / g_lp1;
+        g_lm1 = g_l; g_l = g_lp1; Aprev = A;
+    }
+}
+
+// tw[t] = exp(-2 pi i t / n), t = 0..n-1
+__global__ void k_twiddles(int n, double2* __restrict__ tw)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double s, c;
+    sincospi(2.0 * (double)t / (double)n, &s, &c);
+    tw[t] = make_double2(c, -s);
+}
+
+__global__ void k_inv_ll1(int lmax, double* __restrict__ v)
+{
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > lmax) return;
+    v[l] = l == 0 ? 0.0 : 2.0 / ((double)l * (double)(l + 1));
+}
+
+}  // namespace pixsht

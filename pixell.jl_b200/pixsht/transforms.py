@@ -1,0 +1,158 @@
+"""map2alm / alm2map with the reference's method table (src/transforms.jl:88-265), on top of the C ABI.
+
+The reference's per-call host work (create_sht_band copies, make_cc_geom_info, the un-flip slice copy) is replaced by
+a cached Plan per (geometry, lmax, mmax, dtype): the caller's array goes to the library untouched, flips and padding
+are index arithmetic in the FFT kernels.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import PixshtError, PixshtLib, get_lib, Geom, F64, F32, MAP2ALM, ALM2MAP, HOST, DEVICE  # noqa: F401
+from .enmap import Enmap, Alm
+from .geometry import sht_band, getlmax
+
+
+def _ptr_array(ptrs):
+    return (ctypes.c_void_p * len(ptrs))(*ptrs)
+
+
+class Plan:
+    """Owner of a pixsht_plan handle (include/pixsht.h)."""
+
+    def __init__(self, band, lmax, mmax=None, dtype=np.float64, device=0, lib=None):
+        self.lib = get_lib() if lib is None else lib
+        self.band, self.lmax, self.mmax = band, int(lmax), int(lmax if mmax is None else mmax)
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
+            raise TypeError("maps must be Float64 or Float32")
+        self.cdtype = np.dtype(np.complex128 if self.dtype == np.float64 else np.complex64)
+        g = Geom(band.nphi, band.nrings_total, band.ring_first, band.nrings, band.nx, int(band.flipx), int(band.flipy), 0,
+                 band.phi0)
+        h = ctypes.c_void_p()
+        self.lib.check(self.lib.lib.pixsht_plan_create(ctypes.byref(h), ctypes.byref(g), self.lmax, self.mmax,
+                                                       F64 if self.dtype == np.float64 else F32, device))
+        self.handle = h
+        self.nalm = int(self.lib.lib.pixsht_nalm(self.lmax, self.mmax))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.lib.pixsht_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def execute_ptrs(self, direction, alm_ptrs, map_ptrs, location=HOST):
+        n = len(alm_ptrs)
+        self.lib.check(self.lib.lib.pixsht_execute(self.handle, direction, n, _ptr_array(alm_ptrs), _ptr_array(map_ptrs),
+                                                   location))
+
+    def timings(self):
+        t = (ctypes.c_double * 8)()
+        self.lib.check(self.lib.lib.pixsht_get_timings(self.handle, t))
+        return dict(h2d=t[0], legendre=t[1], fft=t[2], d2h=t[3], total=t[4])
+
+    def info(self):
+        v = (ctypes.c_int32 * 16)()
+        self.lib.check(self.lib.lib.pixsht_plan_info(self.handle, v))
+        keys = ["nphi", "nrings", "lmax", "mmax", "dtype", "device", "npairs", "sm_count", "nfft", "launches", "R0", "R2"]
+        return dict(zip(keys, list(v)))
+
+    def weights(self):
+        w = np.empty(self.band.nrings)
+        th = np.empty(self.band.nrings)
+        self.lib.check(self.lib.lib.pixsht_plan_weights(self.handle, w.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                                        th.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+        return w, th
+
+    # ---- host-array front ends -------------------------------------------------------------------------------
+    def map2alm(self, maps):
+        """maps: list of (nx, ny) Fortran-ordered arrays of the plan dtype (1: T, 2: Q,U, 3: T,Q,U) -> list of alm vectors."""
+        maps = [self._as_map(m) for m in maps]
+        alms = [np.zeros(self.nalm, dtype=self.cdtype) for _ in maps]
+        self.execute_ptrs(MAP2ALM, [a.ctypes.data for a in alms], [m.ctypes.data for m in maps])
+        return alms
+
+    def alm2map(self, alms):
+        alms = [np.ascontiguousarray(a, dtype=self.cdtype) for a in alms]
+        for a in alms:
+            if a.shape != (self.nalm,):
+                raise ValueError("alm has %d entries, expected %d" % (a.size, self.nalm))
+        maps = [np.zeros((self.band.nx, self.band.nrings), dtype=self.dtype, order="F") for _ in alms]
+        self.execute_ptrs(ALM2MAP, [a.ctypes.data for a in alms], [m.ctypes.data for m in maps])
+        return maps
+
+    def _as_map(self, m):
+        m = np.asarray(m)
+        if m.shape != (self.band.nx, self.band.nrings):
+            raise ValueError("map has shape %s, expected %s" % (m.shape, (self.band.nx, self.band.nrings)))
+        if m.dtype != self.dtype or not m.flags.f_contiguous:
+            m = np.asfortranarray(m, dtype=self.dtype)
+        return m
+
+
+_PLANS = {}
+
+
+def _plan_for(shape, wcs, lmax, mmax, dtype, lib=None):
+    band = sht_band(tuple(shape[:2]), wcs)
+    lib = get_lib() if lib is None else lib
+    key = (id(lib), band, lmax, mmax, np.dtype(dtype).str)
+    p = _PLANS.get(key)
+    if p is None:
+        if len(_PLANS) >= 8:
+            _PLANS.pop(next(iter(_PLANS))).close()
+        p = _PLANS[key] = Plan(band, lmax, mmax, dtype=dtype, lib=lib)
+    return p
+
+
+def _compute_dtype(dt):
+    return np.float32 if np.dtype(dt) == np.float32 else np.float64
+
+
+def map2alm(m, lmax=None, mmax=None, lib=None):
+    """map2alm(::Enmap{T,2}) / (::NTuple{2}) / (::NTuple{3}) / (::Enmap{T,3})  (src/transforms.jl:88-165).
+
+    Returns an Alm (spin 0), or a tuple (E, B) / (T, E, B) of Alm -- the reference's return types."""
+    if isinstance(m, (tuple, list)):
+        maps = list(m)
+        if len(maps) not in (2, 3) or any(x.ndim != 2 for x in maps):
+            raise ValueError("tuples of 2 (Q,U) or 3 (I,Q,U) two-dimensional Enmaps are supported")
+        first = maps[0]
+        arrays = [x.data for x in maps]
+    else:
+        first = m
+        if m.ndim == 2:
+            arrays = [m.data]
+        else:
+            if m.shape[2] not in (1, 2, 3):
+                raise ValueError("SHTs require shape (nx,ny,ncomp) with 1 ≤ ncomp ≤ 3, for I, QU, and IQU.")
+            arrays = [m.data[:, :, c] for c in range(m.shape[2])]
+    if lmax is None:
+        lmax = getlmax(first.wcs)
+        mmax = lmax
+    mmax = lmax if mmax is None else mmax
+    plan = _plan_for(first.shape, first.wcs, lmax, mmax, _compute_dtype(first.dtype), lib)
+    alms = [Alm(lmax, mmax, a) for a in plan.map2alm(arrays)]
+    return alms[0] if len(alms) == 1 else tuple(alms)
+
+
+def alm2map(alm, shape, wcs, dtype=np.float64, lib=None):
+    """alm2map(::Alm, shape, wcs) -> Enmap;  (::NTuple{2,Alm}) -> list of 2 Enmaps;  (::NTuple{3,Alm}) / Vector -> tuple
+    (src/transforms.jl:206-265, return-type quirks of SURVEY.md F11 kept)."""
+    alms = [alm] if isinstance(alm, Alm) else list(alm)
+    if len(alms) not in (1, 2, 3):
+        raise ValueError("1, 2 or 3 Alm are supported")
+    lmax, mmax = alms[0].lmax, alms[0].mmax
+    plan = _plan_for(shape, wcs, lmax, mmax, dtype, lib)
+    maps = [Enmap(x, wcs) for x in plan.alm2map([a.alm for a in alms])]
+    if len(maps) == 1:
+        return maps[0]
+    if len(maps) == 2:
+        return maps
+    return tuple(maps)

@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- alm2map + map2alm wall time on the BASELINE.json configs (default: C4, full-sky CAR 1' IQU, lmax 10800, F64).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C1|C2|C3|C4] [--impl b200|reference]
+
+A step = one alm2map followed by one map2alm of the whole IQU (or T) set.  One JSON line is printed by rank 0:
+  value   : ms per step, inputs and outputs resident in HBM (device pointers through the C ABI / stage API)
+  e2e     : ms per step through the host-pointer C ABI call (pinned host buffers, H2D + D2H inside the timed region)
+  roofline: Legendre kernels (the dominant ones) against the measured FP64 FMA peak; roofline_fft against measured HBM
+  cpu_baseline: the oracle's double/OpenMP build ("port", not libsharp2) on a bounded sample, extrapolated linearly
+N > 1: launched by torchrun, one rank per GPU, m-sharded Legendre + NCCL all-to-all + ring-sharded FFT (strong scaling).
+--impl reference: times the CPU restatement of the reference path (oracle "d" build, all host threads); the real
+Pixell.jl/libsharp2 cannot run here (no Julia, no libsharp2: DESIGN.md).
+"""
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "pixell.jl_b200"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    "C1": dict(res_arcmin=60.0, lmax=180, ncomp=1, dtype="f64", desc="full-sky CAR 1deg (360x181) Float64 spin-0, lmax=180"),
+    "C2": dict(res_arcmin=4.0, lmax=2700, ncomp=1, dtype="f32", desc="full-sky CAR 4' (5400x2701) Float32 T-only, lmax=2700"),
+    "C3": dict(res_arcmin=2.0, lmax=5400, ncomp=3, dtype="f64", desc="full-sky CAR 2' (10800x5401) Float64 IQU, lmax=5400"),
+    "C4": dict(res_arcmin=1.0, lmax=10800, ncomp=3, dtype="f64", desc="full-sky CAR 1' (21600x10801) Float64 IQU, lmax=10800"),
+}
+METRIC = "alm2map+map2alm wall time"
+
+
+def algorithmic_flops(nalm, nrings, ncomp):
+    """per (l, m, ring pair) 4 FMA (spin 0), 12 (spin 2), 16 (IQU); 1 FMA = 2 flop; per direction."""
+    fma = {1: 4, 2: 12, 3: 16}[ncomp]
+    return 2.0 * fma * nalm * math.ceil(nrings / 2)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU baseline (oracle "d" build; test infrastructure used here ONLY as the timed baseline, never as the product)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_baseline(wl, target_s=12.0, maps=None, alms=None):
+    import pixsht
+    from oracle import get_oracle, cc_geometry, nalm as nalm_of
+    orc = get_oracle("d")
+    res = wl["res_arcmin"] * pixsht.arcminute
+    shape, wcs = pixsht.fullsky_geometry(res)
+    band = pixsht.sht_band(shape, wcs)
+    lmax, nc = wl["lmax"], wl["ncomp"]
+    theta, w = cc_geometry(band.nrings_total, band.nphi)
+    n = nalm_of(lmax)
+    rng = np.random.default_rng(4242)
+    if alms is None:
+        alms = [rng.standard_normal(n) + 1j * rng.standard_normal(n) for _ in range(nc)]
+    if maps is None:
+        maps = [rng.standard_normal((band.nrings, band.nphi)) for _ in range(nc)]
+    jobs = [(0, [0])] if nc == 1 else ([(2, [0, 1])] if nc == 2 else [(0, [0]), (2, [1, 2])])
+
+    def run_a2m(stride):
+        t0 = time.perf_counter()
+        for spin, idx in jobs:
+            orc.alm2map(np.stack([alms[i] for i in idx]), theta, band.phi0, band.nphi, lmax, spin=spin, ring_stride=stride, ring_offset=stride // 2)
+        return time.perf_counter() - t0
+
+    def run_m2a(stride):
+        t0 = time.perf_counter()
+        for spin, idx in jobs:
+            orc.map2alm(np.stack([maps[i] for i in idx]), theta, w, band.phi0, lmax, spin=spin, m_stride=stride, m_offset=stride // 3)
+        return time.perf_counter() - t0
+
+    nr, nm = band.nrings, lmax + 1
+    # calibrate on a very thin sample, then size the sample for ~target_s/2 per direction
+    s_r = max(1, nr // 2); t = run_a2m(s_r); per_ring = t / math.ceil((nr - s_r // 2) / s_r)
+    s_r = max(1, min(nr, int(nr * per_ring / (target_s / 2)) + 1)) if per_ring * nr > target_s / 2 else 1
+    t_a = run_a2m(s_r); n_r = len(range(s_r // 2, nr, s_r))
+    thr = orc.threads
+    s_m = max(1, nm // max(thr, 8)); t = run_m2a(s_m); per_m = t / len(range(s_m // 3, nm, s_m))
+    s_m = max(1, min(s_m, int(nm * per_m / (target_s / 2)) + 1)) if per_m * nm > target_s / 2 else 1
+    t_m = run_m2a(s_m); n_m = len(range(s_m // 3, nm, s_m))
+    full_ms = 1e3 * (t_a * nr / n_r + t_m * nm / n_m)
+    return {"value": full_ms, "unit": "ms", "cores": thr, "kind": "port",
+            "sample": "oracle double/OpenMP restatement (not libsharp2): alm2map on %d of %d rings in %.1f s + map2alm on %d of %d m in %.1f s, "
+                      "extrapolated linearly to the full transform" % (n_r, nr, t_a, n_m, nm, t_m)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def synth_alm_device(torch, nalm, lmax, seed, spin2, device, cdtype):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    a = torch.randn(nalm, 2, generator=g, device=device, dtype=torch.float64)
+    a[:lmax + 1, 1] = 0          # a_l0 real
+    if spin2:
+        a[0:2] = 0               # m = 0: l = 0, 1
+        a[lmax + 1:lmax + 2] = 0  # m = 1: l = 1
+    a = torch.view_as_complex(a)
+    return a.to(cdtype).contiguous()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "%s: %s" % (args.workload, wl["desc"]), "ncomp": wl["ncomp"], "lmax": wl["lmax"],
+              "step": "one alm2map + one map2alm", "l2": "inputs larger than L2 (map+alm+phase >> 126 MB)" if args.workload in ("C3", "C4") else
+              "inputs smaller than L2; 256 MB scratch written between timed steps"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        vals = []
+        base = None
+        for i in range(args.warmup + args.steps):
+            base = cpu_baseline(wl, target_s=8.0)
+            if i >= args.warmup:
+                vals.append(base["value"])
+        v = float(np.mean(vals))
+        base["value"] = v
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": v, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+                          "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": base,
+                          "e2e": {"value": v, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "note": "CPU restatement of the Pixell.jl/libsharp2 path (oracle double/OpenMP build); Julia and libsharp2 are "
+                                  "not available in this image, so the unmodified reference cannot be run"}))
+        return
+
+    import torch
+    import pixsht
+    from pixsht.transforms import Plan, get_lib, MAP2ALM, ALM2MAP, HOST, DEVICE
+    from pixsht.distributed import ShardedSHT
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    lib = get_lib()
+    res = wl["res_arcmin"] * pixsht.arcminute
+    shape, wcs = pixsht.fullsky_geometry(res)
+    band = pixsht.sht_band(shape, wcs)
+    lmax, nc = wl["lmax"], wl["ncomp"]
+    f64 = wl["dtype"] == "f64"
+    rdt, cdt = (torch.float64, torch.complex128) if f64 else (torch.float32, torch.complex64)
+    npdt = np.float64 if f64 else np.float32
+    esz = 8 if f64 else 4
+    seed0 = 1000 * int(args.workload[1])
+    stream = torch.cuda.current_stream(device)
+    l2_scratch = None if args.workload in ("C3", "C4") else torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)
+
+    def flush_l2():
+        if l2_scratch is not None:
+            l2_scratch.zero_()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def timed(fn, nwarm, nsteps):
+        for _ in range(nwarm):
+            fn(); flush_l2()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(nsteps):
+            fn(); flush_l2()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / nsteps
+
+    launches = 0
+    stage = {}
+    if world == 1:
+        plan = Plan(band, lmax, dtype=npdt)
+        lib.check(lib.lib.pixsht_plan_set_stream(plan.handle, ctypes.c_void_p(stream.cuda_stream), 1))
+        nalm = plan.nalm
+        d_alm = [synth_alm_device(torch, nalm, lmax, seed0 + c, c > 0, device, cdt) for c in range(nc)]
+        d_out = [torch.empty_like(a) for a in d_alm]
+        d_map = [torch.empty(band.nx * band.nrings, dtype=rdt, device=device) for _ in range(nc)]
+        acc = {"leg": 0.0, "fft": 0.0, "n": 0, "launches": 0}
+
+        def step_dev():
+            plan.execute_ptrs(ALM2MAP, [a.data_ptr() for a in d_alm], [m.data_ptr() for m in d_map], DEVICE)
+            t1 = plan.timings(); l1 = plan.info()["launches"]
+            plan.execute_ptrs(MAP2ALM, [a.data_ptr() for a in d_out], [m.data_ptr() for m in d_map], DEVICE)
+            t2 = plan.timings(); l2 = plan.info()["launches"]
+            acc["leg"] += t1["legendre"] + t2["legendre"]; acc["fft"] += t1["fft"] + t2["fft"]; acc["n"] += 1
+            acc["launches"] = l1 + l2
+
+        clk = ClockSampler(local_rank); clk.start()
+        for _ in range(args.warmup):
+            step_dev(); flush_l2()
+        acc.update(leg=0.0, fft=0.0, n=0)
+        ms_dev = timed(step_dev, 0, args.steps)
+        clocks = clk.stop()
+        leg_ms, fft_ms = acc["leg"] / acc["n"], acc["fft"] / acc["n"]
+        launches = acc["launches"] * args.steps
+        stage = {"legendre_ms": leg_ms, "fft_ms": fft_ms}
+        h2d = d2h = 0
+        e2e = None
+        host_maps = host_alms = None
+        if not args.no_e2e:
+            h_alm = [torch.empty(nalm, dtype=cdt).pin_memory() for _ in range(nc)]
+            h_out = [torch.empty(nalm, dtype=cdt).pin_memory() for _ in range(nc)]
+            h_map = [torch.empty(band.nx * band.nrings, dtype=rdt).pin_memory() for _ in range(nc)]
+            for h, d in zip(h_alm, d_alm):
+                h.copy_(d)
+            torch.cuda.synchronize(device)
+
+            def step_host():
+                plan.execute_ptrs(ALM2MAP, [a.data_ptr() for a in h_alm], [m.data_ptr() for m in h_map], HOST)
+                plan.execute_ptrs(MAP2ALM, [a.data_ptr() for a in h_out], [m.data_ptr() for m in h_map], HOST)
+
+            ms_e2e = timed(step_host, min(args.warmup, 3), args.steps)
+            h2d = sum(a.numel() * a.element_size() for a in h_alm) + sum(m.numel() * m.element_size() for m in h_map)
+            d2h = sum(m.numel() * m.element_size() for m in h_map) + sum(a.numel() * a.element_size() for a in h_out)
+            e2e = {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "api": "pixsht_execute(..., PIXSHT_HOST) on pinned host buffers"}
+            # sanity: device-resident and host paths agree
+            chk = float((h_out[0].to(device) - d_out[0]).abs().max().item())
+            e2e["host_vs_device_maxabs"] = chk
+            host_maps = [m.numpy().reshape(band.nrings, band.nx).astype(np.float64, copy=False) for m in h_map]
+            host_alms = [a.numpy().astype(np.complex128, copy=False) for a in h_alm]
+        nrings = band.nrings
+        plan_info = plan.info()
+    else:
+        if not f64:
+            raise SystemExit("multi-GPU runs are Float64 (C3/C4)")
+        sht = ShardedSHT(band, lmax, device=device)
+        nalm = sht.nalm
+        a, b = sht.map_rows()
+        d_alm = [synth_alm_device(torch, nalm, lmax, seed0 + c, c > 0, device, cdt) for c in range(nc)]
+        d_out = [torch.empty_like(x) for x in d_alm]
+        d_slab = [torch.empty((b - a) * band.nx, dtype=rdt, device=device) for _ in range(nc)]
+        acc = {"a2m": None, "m2a": None}
+
+        def step_dev():
+            sht.alm2map(d_alm, d_slab)
+            sht.map2alm(d_slab, d_out)
+
+        clk = ClockSampler(local_rank); clk.start()
+        ms_dev = timed(step_dev, args.warmup, args.steps)
+        clocks = clk.stop()
+        s1, s2 = sht.stage_ms("alm2map"), sht.stage_ms("map2alm")
+        leg_ms, fft_ms, a2a_ms = s1[0] + s2[2], s1[2] + s2[0], s1[1] + s2[1]
+        t = torch.tensor([leg_ms, fft_ms, a2a_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        leg_ms, fft_ms, a2a_ms = [float(x) for x in t.tolist()]
+        stage = {"legendre_ms": leg_ms, "fft_ms": fft_ms, "exchange_ms": a2a_ms}
+        launches = 8 * args.steps   # 2 Legendre + 1 FFT kernels per direction of our own per rank (+ torch pack/unpack copies)
+        e2e = None
+        if not args.no_e2e:
+            # each rank moves only what it owns: its alm columns (packed) and its rows of the map
+            cols = sht.alm_columns()
+            idx = torch.cat([torch.arange(s, e, device=device) for (s, e) in cols])
+            h_alm = [torch.empty(idx.numel(), dtype=cdt).pin_memory() for _ in range(nc)]
+            h_out = [torch.empty(idx.numel(), dtype=cdt).pin_memory() for _ in range(nc)]
+            h_slab = [torch.empty((b - a) * band.nx, dtype=rdt).pin_memory() for _ in range(nc)]
+            d_pack = [torch.empty(idx.numel(), dtype=cdt, device=device) for _ in range(nc)]
+            for h, d in zip(h_alm, d_alm):
+                h.copy_(d.index_select(0, idx))
+            torch.cuda.synchronize(device)
+
+            def step_host():
+                for c in range(nc):
+                    d_pack[c].copy_(h_alm[c], non_blocking=True)
+                    d_alm[c].index_copy_(0, idx, d_pack[c])
+                sht.alm2map(d_alm, d_slab)
+                for c in range(nc):
+                    h_slab[c].copy_(d_slab[c], non_blocking=True)
+                for c in range(nc):
+                    d_slab[c].copy_(h_slab[c], non_blocking=True)
+                sht.map2alm(d_slab, d_out)
+                for c in range(nc):
+                    torch.index_select(d_out[c], 0, idx, out=d_pack[c])
+                    h_out[c].copy_(d_pack[c], non_blocking=True)
+                torch.cuda.current_stream(device).synchronize()
+
+            ms_e2e = timed(step_host, min(args.warmup, 3), args.steps)
+            per_rank = (sum(x.numel() * x.element_size() for x in h_alm) + sum(x.numel() * x.element_size() for x in h_slab))
+            tb = torch.tensor([per_rank], device=device, dtype=torch.float64)
+            dist.all_reduce(tb)
+            h2d = d2h = int(tb.item())
+            e2e = {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "api": "pixsht.distributed.ShardedSHT with per-rank pinned host shards"}
+        nrings = band.nrings
+        plan_info = {"npairs": math.ceil(nrings / 2), "sm_count": None}
+        host_maps = host_alms = None
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier(); dist.destroy_process_group()
+        return
+
+    # ---- rooflines -----------------------------------------------------------------------------------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
+    fp64_peak, fp32_peak = lib.measure_fma_peak(local_rank)
+    flops = 2.0 * algorithmic_flops(nalm, nrings, nc)            # both directions, all ranks together
+    leg_tf = flops / world / (leg_ms * 1e-3) / 1e12             # per GPU
+    roofline = {"bound": "fp64_fma", "kernel": "leg_synth<0|2> + leg_anal<0|2> (Legendre stage, both directions)",
+                "achieved": leg_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": leg_tf / fp64_peak, "traffic": None,
+                "peak_source": "pixsht_measure_fma_peak: register-resident DFMA chain measured on this GPU in this run "
+                               "(datasheet FP64 vector peak 37 TFLOP/s); MEASURED_PEAKS.json has no FP64 figure",
+                "algorithmic_flop_per_step": flops, "note": "un-pruned, north/south-folded count of SURVEY.md 8(d); per GPU"}
+    fft_bytes = 2.0 * (nc * band.nx * nrings * esz + nc * (lmax + 1) * nrings * 16)
+    roofline_fft = {"bound": "hbm", "kernel": "fft_phase2map + fft_map2phase", "achieved": fft_bytes / world / (fft_ms * 1e-3) / 1e9,
+                    "peak": hbm_peak, "unit": "GB/s", "traffic": None, "peak_source": hbm_src}
+    roofline_fft["frac"] = roofline_fft["achieved"] / hbm_peak
+
+    line = {"metric": METRIC, "value": ms_dev, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": wl["dtype"], "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": launches,
+            "stages": stage, "roofline": roofline, "roofline_fft": roofline_fft, "fp32_fma_peak_tflops": fp32_peak,
+            "transforms_per_s": 2.0 * 1e3 / ms_dev, "plan": {k: plan_info.get(k) for k in ("npairs", "sm_count", "R0", "R2")}}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline(wl, maps=host_maps, alms=host_alms)
+        except Exception as ex:  # never lose the GPU numbers to a baseline problem
+            line["cpu_baseline"] = {"error": repr(ex)}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -67,12 +67,18 @@ void pixsht_plan_destroy(pixsht_plan *plan);
  * Outputs are overwritten (SHARP_ADD is never used by the reference). */
 int pixsht_execute(pixsht_plan *plan, int direction, int ncomp, void *const *alms, void *const *maps, int location);
 
+/* Run pixsht_execute on the caller's CUDA stream (cudaStream_t passed as void*; NULL is the legacy default stream) when
+ * use_caller_stream != 0, or go back to the plan's own stream.  The call still synchronises that stream before returning. */
+int pixsht_plan_set_stream(pixsht_plan *plan, void *stream, int use_caller_stream);
+
 /* per-stage device time (ms, CUDA events) of the last pixsht_execute on this plan:
  * [0] h2d copy, [1] Legendre stage, [2] FFT stage, [3] d2h copy, [4] whole call (host wall clock), [5..7] reserved */
 int pixsht_get_timings(const pixsht_plan *plan, double ms[8]);
 
 /* ---- stage API for the m-sharded multi-GPU pipeline (device pointers, asynchronous on `stream`) ------------ */
-/* phase buffers are complex double, element (c, row, ring) at ((c*nrows + row)*nrings_buf + ring).              */
+/* phase buffers are complex double, element (c, row, ring) at ((row*ncomp + c)*nrings_buf + ring): one row per m,
+ * components interleaved per row, so that the per-destination blocks of the all-to-all are contiguous row ranges.
+ * nrings_buf = plan nrings for the Legendre stages, ring_count for the FFT stages.                                */
 /* Legendre stage over the m values m_list[0..nm) (device array of int32, or NULL for m = 0..nm-1): row = position in m_list. */
 int pixsht_stage_alm2phase(pixsht_plan *plan, int ncomp, const void *const *d_alms, int nm, const int32_t *d_m_list,
                            void *d_phase, void *stream);

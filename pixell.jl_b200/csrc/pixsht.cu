@@ -68,7 +68,7 @@ struct pixsht_plan {
     DevBuf<double2> d_phase; int phase_ncomp = 0;
     DevBuf<unsigned char> d_map[3], d_alm[3];
     DevBuf<double2> d_alm64[3];
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double timings[8] = {0};
     int launches = 0;
@@ -253,7 +253,8 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     rc |= P->d_alpha2.alloc(P->nalm); rc |= P->d_gamma2.alloc(P->nalm);
     if (rc) return fail(PIXSHT_ERR_NOMEM, "device allocation of plan tables failed");
 
-    CU(cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&P->own_stream, cudaStreamNonBlocking));
+    P->stream = P->own_stream;
     for (auto& e : P->ev) CU(cudaEventCreate(&e));
 
     // ---- device-side precompute ----
@@ -363,7 +364,7 @@ extern "C" void pixsht_plan_destroy(pixsht_plan* P)
     P->d_tw.release(); P->d_phi0tw.release(); P->d_phase.release();
     for (int c = 0; c < 3; ++c) { P->d_map[c].release(); P->d_alm[c].release(); P->d_alm64[c].release(); }
     for (auto& e : P->ev) if (e) cudaEventDestroy(e);
-    if (P->stream) cudaStreamDestroy(P->stream);
+    if (P->own_stream) cudaStreamDestroy(P->own_stream);
     (void)cudaGetLastError();
     delete P;
 }
@@ -568,6 +569,14 @@ extern "C" int pixsht_execute(pixsht_plan* P, int direction, int ncomp, void* co
     return PIXSHT_OK;
 }
 
+extern "C" int pixsht_plan_set_stream(pixsht_plan* P, void* stream, int use_caller_stream)
+{
+    if (!P) return fail(PIXSHT_ERR_ARG, "null plan");
+    std::lock_guard<std::mutex> lock(P->mu);
+    P->stream = use_caller_stream ? (cudaStream_t)stream : P->own_stream;
+    return PIXSHT_OK;
+}
+
 extern "C" int pixsht_get_timings(const pixsht_plan* P, double ms[8])
 {
     if (!P || !ms) return fail(PIXSHT_ERR_ARG, "null argument");
@@ -594,7 +603,7 @@ extern "C" int pixsht_stage_alm2phase(pixsht_plan* P, int ncomp, const void* con
     if (nm == 0) return PIXSHT_OK;
     const double2* alm[3] = {nullptr, nullptr, nullptr};
     for (int c = 0; c < ncomp; ++c) alm[c] = (const double2*)d_alms[c];
-    return stage_alm2phase(P, ncomp, alm, nm, d_m_list, (double2*)d_phase, (long long)nm * P->nrings, P->nrings, (cudaStream_t)stream);
+    return stage_alm2phase(P, ncomp, alm, nm, d_m_list, (double2*)d_phase, P->nrings, (long long)ncomp * P->nrings, (cudaStream_t)stream);
 }
 
 extern "C" int pixsht_stage_phase2alm(pixsht_plan* P, int ncomp, const void* d_phase, int nm, const int32_t* d_m_list,
@@ -605,7 +614,7 @@ extern "C" int pixsht_stage_phase2alm(pixsht_plan* P, int ncomp, const void* d_p
     if (nm == 0) return PIXSHT_OK;
     double2* alm[3] = {nullptr, nullptr, nullptr};
     for (int c = 0; c < ncomp; ++c) alm[c] = (double2*)d_alms[c];
-    return stage_phase2alm(P, ncomp, (double2*)d_phase, (long long)nm * P->nrings, P->nrings, nm, d_m_list, alm, (cudaStream_t)stream);
+    return stage_phase2alm(P, ncomp, (double2*)d_phase, P->nrings, (long long)ncomp * P->nrings, nm, d_m_list, alm, (cudaStream_t)stream);
 }
 
 extern "C" int pixsht_stage_phase2map(pixsht_plan* P, int ncomp, const void* d_phase, const int32_t* d_m_row, int ring_begin,
@@ -613,7 +622,7 @@ extern "C" int pixsht_stage_phase2map(pixsht_plan* P, int ncomp, const void* d_p
 {
     int rc = stage_common(P, ncomp); if (rc) return rc;
     if (!d_maps || !d_phase || ring_begin < 0 || ring_count < 0 || ring_begin + ring_count > P->nrings) return fail(PIXSHT_ERR_ARG, "bad argument");
-    return stage_fft(P, PIXSHT_ALM2MAP, ncomp, (double2*)d_phase, (long long)(P->mmax + 1) * ring_count, ring_count, d_m_row,
+    return stage_fft(P, PIXSHT_ALM2MAP, ncomp, (double2*)d_phase, ring_count, (long long)ncomp * ring_count, d_m_row,
                      ring_begin, ring_count, d_maps, (cudaStream_t)stream);
 }
 
@@ -622,7 +631,7 @@ extern "C" int pixsht_stage_map2phase(pixsht_plan* P, int ncomp, const void* con
 {
     int rc = stage_common(P, ncomp); if (rc) return rc;
     if (!d_maps || !d_phase || ring_begin < 0 || ring_count < 0 || ring_begin + ring_count > P->nrings) return fail(PIXSHT_ERR_ARG, "bad argument");
-    return stage_fft(P, PIXSHT_MAP2ALM, ncomp, (double2*)d_phase, (long long)(P->mmax + 1) * ring_count, ring_count, d_m_row,
+    return stage_fft(P, PIXSHT_MAP2ALM, ncomp, (double2*)d_phase, ring_count, (long long)ncomp * ring_count, d_m_row,
                      ring_begin, ring_count, (void* const*)d_maps, (cudaStream_t)stream);
 }
 

@@ -24,7 +24,7 @@ class Geom(ctypes.Structure):
 
 
 # every symbol include/pixsht.h and include/pixsht_sharp_shim.h declare
-EXPORTS = ["pixsht_plan_create", "pixsht_plan_create_rings", "pixsht_plan_destroy", "pixsht_execute", "pixsht_get_timings",
+EXPORTS = ["pixsht_plan_create", "pixsht_plan_create_rings", "pixsht_plan_destroy", "pixsht_execute", "pixsht_get_timings", "pixsht_plan_set_stream",
            "pixsht_stage_alm2phase", "pixsht_stage_phase2alm", "pixsht_stage_phase2map", "pixsht_stage_map2phase",
            "pixsht_nalm", "pixsht_plan_info", "pixsht_plan_weights", "pixsht_last_error", "pixsht_version",
            "pixsht_device_count", "pixsht_measure_fma_peak",
@@ -50,6 +50,7 @@ class PixshtLib:
         L.pixsht_plan_destroy.argtypes = [vp]
         L.pixsht_plan_destroy.restype = None
         L.pixsht_execute.argtypes = [vp, i32, i32, pvp, pvp, i32]
+        L.pixsht_plan_set_stream.argtypes = [vp, vp, i32]
         L.pixsht_get_timings.argtypes = [vp, ctypes.POINTER(dbl)]
         L.pixsht_stage_alm2phase.argtypes = [vp, i32, pvp, i32, vp, vp, vp]
         L.pixsht_stage_phase2alm.argtypes = [vp, i32, vp, i32, vp, pvp, vp]

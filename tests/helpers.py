@@ -46,9 +46,14 @@ def band_copy(m):
 
 
 def band_to_map(band, b):
-    """Inverse of band_copy for alm2map results (src/transforms.jl:220-225): (ncomp, nrings, nphi) -> (nx, ny, ncomp)."""
+    """Inverse of band_copy for alm2map results: (ncomp, nrings, nphi) -> (nx, ny, ncomp).
+
+    The reference's alm2map (src/transforms.jl:206-225) pads the UNflipped band, so its phi0 is the RA of the virtual
+    column `fullringsize` and it reads the last nx band columns back in reverse; here the band follows the map2alm
+    convention of ShtBand (phi0 = RA of the flipped map's first column, padding at the end), so map column c is band
+    column nx-1-c.  Both address the same (theta, phi) per pixel; for full-sky maps they are the same indices."""
     a = band.transpose(2, 1, 0)  # (nphi, nrings, ncomp)
-    xs = slice(b.nphi - 1, b.nphi - b.nx - 1 if b.nphi - b.nx - 1 >= 0 else None, -1) if b.flipx else slice(0, b.nx)
+    xs = slice(b.nx - 1, None, -1) if b.flipx else slice(0, b.nx)
     ys = slice(None, None, -1) if b.flipy else slice(None)
     return np.asfortranarray(a[xs, ys, :])
 

@@ -75,3 +75,35 @@ def test_emu_alm2map_vs_oracle(emu, spin):
     out = [out] if nc == 1 else out
     for c in range(nc):
         assert rel_rms(out[c].data, ref[:, :, c]) < 1e-12
+
+
+# ---- the small GPU parity cases, replayed on the emulation build (logic check of the test bodies and the kernels) ----
+@pytest.fixture()
+def emu_default(emu, monkeypatch):
+    from pixsht import _lib, transforms
+    monkeypatch.setattr(_lib, "_DEFAULT", emu)
+    transforms._PLANS.clear()
+    yield emu
+    transforms._PLANS.clear()
+
+
+def test_emu_replay_golden_cases(emu_default):
+    import test_gpu_parity as g
+    g.test_golden_spin0_fullsky_sliced_box()
+    g.test_golden_spin2_stack_tuple_iqu()
+    g.test_bad_ncomp_is_an_error_not_a_crash()
+
+
+def test_emu_replay_partial_sky_and_flips(emu_default):
+    import test_gpu_parity as g
+    g.test_partial_sky_band_and_unflipped_geometry()
+
+
+def test_emu_replay_sharp_shim(emu_default):
+    import test_gpu_parity as g
+    g.test_sharp_shim_runs_the_reference_call_sequence()
+
+
+def test_emu_c1_config(emu_default):
+    import test_gpu_parity as g
+    g.test_c1_spin0_f64_both_directions_and_roundtrip()

@@ -23,8 +23,7 @@ constexpr int ACT_LOG2 = SEEK_THR_LOG2 - SEEK_QUANT;  // -90
 constexpr unsigned SEEK_THR_EXPBITS = (unsigned)(1023 + SEEK_THR_LOG2) << 20;
 constexpr int E_DEAD = 1;  // marks a ring slot that never contributes (padding / pruned / zero seed)
 
-constexpr int LEG_NT = 128;   // threads per Legendre block
-constexpr int LEG_LC = 256;   // l values staged in shared memory per chunk
+constexpr int LEG_NT = 32;    // threads per Legendre CTA: one warp = one independent work unit (no block barriers)
 
 // ---- double-double helpers (used only for seeds: O(1) per (m, ring)) -----------------------------------------
 struct dd { double hi, lo; };
@@ -48,6 +47,45 @@ __host__ __device__ __forceinline__ dd dd_add(dd a, dd b)
     s.lo += a.lo + b.lo;
     return s;
 }
+
+// ---- warp-private asynchronous staging: TMA bulk copy global -> shared, completion on an mbarrier ------------------
+#ifndef PIXSHT_EMU
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// lane-0 side: announce `bytes` and start the bulk copy that will complete on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy reads of dst are ordered before the async write
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PIXSHT_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PIXSHT_DONE_%=;\n"
+        "bra PIXSHT_WAIT_%=;\n"
+        "PIXSHT_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+#else
+inline void mbar_init(unsigned long long*, unsigned) {}
+inline void mbar_init_fence() {}
+inline void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) { memcpy(dst, src, bytes); }
+inline void mbar_wait(unsigned long long*, unsigned) { __syncwarp(); }   // emulation: lane 0's memcpy happens-before the readers
+#endif
 
 // triangular m-major alm index (Healpix.Alm / make_triangular_alm_info(lmax, mmax, 1))
 __host__ __device__ __forceinline__ long long alm_index(int lmax, int l, int m)

@@ -1,15 +1,20 @@
 // legendre.cuh -- the Legendre stage (alm <-> phase), hand-written for sm_100a.  This is where ~all the time goes
 // ("libsharp2 sharp_execute internals, stage B").  FP64 FMA bound; nothing here is a tensor-core shape.
 //
-// Work decomposition: one CTA = (one m) x (a chunk of LEG_NT*R north/south ring pairs); one thread = R ring pairs of
-// one m (pairs lane, lane+32, ... of its warp's contiguous block, so phase I/O is coalesced along the ring index).
+// Work decomposition: one CTA = one warp = one independent work unit = (one m) x (32*R contiguous north/south ring
+// pairs); lane i owns pairs base + i + 32 j, j < R (coalesced phase I/O, neighbouring rings => coherent seek/active
+// state across the warp).  There is no block-level barrier anywhere: ncu (profiles/r01) showed `barrier` as the top
+// stall when four warps with different amounts of work shared a CTA and a staging buffer.
+//
 // For each pair the scaled functions p_l = lambda_lm(theta)/gamma_l are generated on the fly by
 //     p_{l+1} = (alpha_l x + delta_l) p_l - p_{l-1}                       (2 FP64 ops per l and function)
-// with per-(l,m) uniform coefficients staged in shared memory, and
+// The per-(l,m) uniform operands (alpha, delta and, for synthesis, the pre-scaled alm) are fixed-size records in
+// global memory; each warp streams its m-column of records through a private two-stage shared-memory ring with TMA bulk
+// copies (cp.async.bulk, completion on an mbarrier), so staging overlaps the arithmetic and costs no register.
 //   synthesis: per-ring register accumulators  sum_l p_l * (gamma_l a_lm)   (2 FMA per l, spin 0; 8 for spin 2),
 //              north = even + odd, south = even - odd  (equatorial symmetry);
 //   analysis : per-l partial sums over the thread's R rings, a warp-private shared-memory transpose-reduction
-//              every G (16 / 8) steps, then one atomicAdd per (l, m, CTA).
+//              every G (16 / 8) steps, then one atomicAdd per (l, m, warp).
 // Dynamic range: p carries an exponent e (multiple of 64, <= 0); while e < 0 the ring is "seeking" (recurrence only,
 // 2 ops per l) and contributes nothing; see common.cuh.  Rings that can never matter for this m are pruned.
 #pragma once
@@ -17,33 +22,57 @@
 
 namespace pixsht {
 
-constexpr int LEG_LCA = 128;  // analysis: l values per chunk
-struct __align__(16) red4 { double x, y, z, w; };
-template <int SPIN> struct RedT { typedef double2 type; static constexpr int G = 16; };   // G: l-steps per warp-level reduction group
-template <> struct RedT<2> { typedef red4 type; static constexpr int G = 8; };
-template <int SPIN> constexpr size_t leg_anal_smem()
-{
-    return sizeof(typename RedT<SPIN>::type) * ((size_t)(LEG_NT / 32) * RedT<SPIN>::G * 33 + (size_t)(LEG_NT / 32) * LEG_LCA) + 2 * sizeof(double) * LEG_LCA;
-}
+// records streamed by the synthesis kernels (written per call by k_prep_synth):
+//   spin 0: { alpha, 0, gamma*Re a, gamma*Im a }                                  4 doubles
+//   spin 2: { alpha, delta, G+re, G+im, G-re, G-im },  G+- = -gamma (E +- iB)/2   6 doubles
+// the analysis kernels stream the static (alpha, delta) table (2 doubles per l).
+template <int SPIN> struct SynthRec { static constexpr int ND = (SPIN == 0) ? 4 : 6; static constexpr int STEPS = (SPIN == 0) ? 128 : 64; };
+constexpr int ANAL_STEPS = 128;
+template <int SPIN> struct RedT { static constexpr int G = (SPIN == 0) ? 16 : 8; static constexpr int NV = (SPIN == 0) ? 1 : 2; };   // G: l-steps per reduction group; NV: double2 values per l
 
 struct LegParams {
     int lmax, mmax;
     int nm;                 // number of m values handled by this launch
     const int* m_list;      // device; nullptr => m = row index
-    int npairs, nchunks;    // ring pairs; chunks of LEG_NT*R pairs per m
-    const double* x;        // [npairs] cos(theta) of the pair's northern member (|x| as stored; may be <0 for lone south rings)
+    int npairs, nchunks;    // ring pairs; chunks of 32*R pairs per m
+    const double* x;        // [npairs] cos(theta) of the pair's northern member
     const double* lsh_hi; const double* lsh_lo;   // log2 sin(theta/2), double-double
     const double* lch_hi; const double* lch_lo;   // log2 cos(theta/2)
     const int* ringN; const int* ringS;           // band ring index of the north/south member, -1 if absent
     const double* mlim;     // [npairs] prune: the pair is skipped for m > mlim
     const double* lgpref_hi; const double* lgpref_lo;   // [mmax+1] log2 of the seed prefactor for this spin family
-    const double* alpha; const double* gamma;     // [nalm] recurrence tables of this spin family
-    const double* inv_ll1;  // [lmax+1] 2/(l(l+1))
-    const double2* alm_in0; const double2* alm_in1;     // synthesis input  (T | E,B)
+    const double2* ad;      // [nalm] (alpha, delta) table of this spin family
+    const double* gamma;    // [nalm]
+    const double* rec;      // synthesis: [nalm * SynthRec::ND] records
     double2* alm_out0; double2* alm_out1;               // analysis output  (T | E,B), pre-zeroed, accumulated atomically
     double2* phase;         // element (c,row,ring) at c*stride_c + row*stride_m + ring
     long long stride_c, stride_m;
 };
+
+// ---- pre-scaling pass: alm -> records (element-wise over the alm index; ~1 ms at lmax = 10800) ----------------------
+template <int SPIN>
+__global__ void k_prep_synth(long long nalm, int lmax, const double2* __restrict__ ad, const double* __restrict__ gamma,
+                             const double2* __restrict__ a0, const double2* __restrict__ a1, double* __restrict__ rec)
+{
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (; k < nalm; k += step) {
+        const double2 c = ad[k];
+        const double g = gamma[k];
+        double2* r = reinterpret_cast<double2*>(rec + k * SynthRec<SPIN>::ND);
+        if (SPIN == 0) {
+            const double2 a = a0[k];
+            r[0] = make_double2(c.x, 0.0);
+            r[1] = make_double2(g * a.x, (k <= lmax) ? 0.0 : g * a.y);   // k <= lmax  <=>  m == 0: a_l0 is real
+        } else {
+            const double2 E = a0[k], B = a1[k];
+            const double h = -0.5 * g;
+            r[0] = c;
+            r[1] = make_double2(h * (E.x - B.y), h * (E.y + B.x));
+            r[SPIN != 0 ? 2 : 0] = make_double2(h * (E.x + B.y), h * (E.y - B.x));
+        }
+    }
+}
 
 // ---- seeds -------------------------------------------------------------------------------------------------
 // value = sign * 2^(lg) with lg = lgpref[m] + a*log2 cos(theta/2) + b*log2 sin(theta/2), returned as (k, frac) with
@@ -176,30 +205,39 @@ __device__ __forceinline__ void ring_flags(const RingState<SPIN, R>& S, bool& an
     any_act = __any_sync(0xffffffffu, a);
 }
 
-// stage alpha / delta for l = l0+c0 .. l0+c0+LEG_LC-1 (zeros beyond lmax)
-template <int SPIN>
-__device__ __forceinline__ void stage_coef(const LegParams& P, int m, int l0, int c0, double* sA, double* sD)
-{
-    const long long base = alm_index(P.lmax, 0, m);
-    for (int i = threadIdx.x; i < LEG_LC; i += LEG_NT) {
-        const int l = l0 + c0 + i;
-        double a = 0.0, d = 0.0;
-        if (l <= P.lmax) {
-            a = P.alpha[base + l];
-            if (SPIN != 0) d = a * (double)m * P.inv_ll1[l];   // delta^+ = -alpha mu^+ = alpha * 2m/(l(l+1))
+// ---- warp-private record stream: two-stage shared ring filled by TMA bulk copies ----------------------------------
+template <int ND, int STEPS>
+struct RecStream {
+    const double* src;      // first record of this warp's column
+    int nrec;               // records in the column
+    double* buf;            // [2][STEPS*ND] in shared memory
+    unsigned long long* bar;  // [2]
+    __device__ __forceinline__ void issue(int chunk, int lane) const
+    {
+        if (lane == 0) {
+            const int first = chunk * STEPS;
+            int n = nrec - first; if (n > STEPS) n = STEPS;
+            bulk_g2s(buf + (size_t)(chunk & 1) * STEPS * ND, src + (size_t)first * ND, (unsigned)(n * ND * sizeof(double)), &bar[chunk & 1]);
         }
-        sA[i] = a;
-        if (SPIN != 0) sD[i] = d;
     }
-}
+    __device__ __forceinline__ const double* wait(int chunk) const
+    {
+        mbar_wait(&bar[chunk & 1], (unsigned)((chunk >> 1) & 1));
+        return buf + (size_t)(chunk & 1) * STEPS * ND;
+    }
+};
 
 // =============================================================================================================
 // synthesis: alm -> phase
 // =============================================================================================================
+// MODE 0: every ring of the warp is still seeking (recurrence + check only); 1: mixed (masked accumulate + check);
+// MODE 2: every live ring is active (no masks, no checks)
 template <int SPIN, int R, int MODE, int PAR>
-__device__ __forceinline__ void synth_step(RingState<SPIN, R>& S, double (&acc)[(SPIN == 0 ? 4 : 8)][R], double alpha, double delta,
-                                           double2 g0, double2 g1)
+__device__ __forceinline__ void synth_step(RingState<SPIN, R>& S, double (&acc)[(SPIN == 0 ? 4 : 8)][R], const double* rec)
 {
+    const double2 c = *reinterpret_cast<const double2*>(rec);
+    const double2 g0 = *reinterpret_cast<const double2*>(rec + 2);
+    const double2 g1 = *reinterpret_cast<const double2*>(rec + (SPIN == 0 ? 2 : 4));
 #pragma unroll
     for (int j = 0; j < R; ++j) {
         if (MODE != 0) {
@@ -211,9 +249,9 @@ __device__ __forceinline__ void synth_step(RingState<SPIN, R>& S, double (&acc)[
                 acc[2 * PAR + 1][j] = fma(p0, g0.y, acc[2 * PAR + 1][j]);
             } else {
                 // north: S+ += p+ G+, S- += p- G-;  south: T+ += sgn p- G+, T- += sgn p+ G-  (sgn alternates with l)
+                constexpr int A4 = (SPIN == 0 ? 0 : 4);   // keeps indices in range in the (dead) SPIN == 0 instantiation
                 acc[0][j] = fma(p0, g0.x, acc[0][j]);
                 acc[1][j] = fma(p0, g0.y, acc[1][j]);
-                constexpr int A4 = (SPIN == 0 ? 0 : 4);   // keeps indices in range in the (dead) SPIN == 0 instantiation
                 acc[2][j] = fma(p1, g1.x, acc[2][j]);
                 acc[3][j] = fma(p1, g1.y, acc[3][j]);
                 if (PAR == 0) {
@@ -229,7 +267,7 @@ __device__ __forceinline__ void synth_step(RingState<SPIN, R>& S, double (&acc)[
                 }
             }
         }
-        rec_step<SPIN, R, (MODE != 2)>(S, j, alpha, delta);
+        rec_step<SPIN, R, (MODE != 2)>(S, j, c.x, c.y);
     }
 }
 
@@ -237,15 +275,15 @@ template <int SPIN, int R>
 __global__ void __launch_bounds__(LEG_NT) leg_synth(const LegParams P)
 {
     constexpr int NACC = (SPIN == 0) ? 4 : 8;
-    __shared__ double sA[LEG_LC];
-    __shared__ double sD[LEG_LC];
-    __shared__ double2 sG0[LEG_LC];
-    __shared__ double2 sG1[LEG_LC];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int row = blockIdx.x / P.nchunks, chunk = blockIdx.x % P.nchunks;
+    constexpr int ND = SynthRec<SPIN>::ND, STEPS = SynthRec<SPIN>::STEPS;
+    __shared__ __align__(16) double sbuf[2 * STEPS * ND];
+    __shared__ __align__(8) unsigned long long sbar[2];
+    const int lane = threadIdx.x;
+    const int row = blockIdx.x / P.nchunks;
+    const int chunk = P.nchunks - 1 - (int)(blockIdx.x % P.nchunks);   // equator-side (longest) units first
     const int m = P.m_list ? P.m_list[row] : row;
     const int l0 = (SPIN == 0) ? m : (m > 2 ? m : 2);
-    const int pair0 = chunk * (LEG_NT * R) + warp * (32 * R);
+    const int pair0 = chunk * (32 * R);
 
     RingState<SPIN, R> S;
     init_rings<SPIN, R>(P, m, pair0, lane, S);
@@ -257,56 +295,44 @@ __global__ void __launch_bounds__(LEG_NT) leg_synth(const LegParams P)
 
     bool any_seek, any_act;
     ring_flags<SPIN, R>(S, any_seek, any_act);
-    const bool warp_live = any_seek || any_act;
     const int nl = P.lmax - l0 + 1;
-    const int block_live = __syncthreads_or(warp_live ? 1 : 0);
 
-    if (block_live && nl > 0) {
-        const long long abase = alm_index(P.lmax, 0, m);
-        for (int c0 = 0; c0 < nl; c0 += LEG_LC) {
-            stage_coef<SPIN>(P, m, l0, c0, sA, sD);
-            for (int i = tid; i < LEG_LC; i += LEG_NT) {
-                const int l = l0 + c0 + i;
-                double2 g0 = make_double2(0.0, 0.0), g1 = make_double2(0.0, 0.0);
-                if (l <= P.lmax) {
-                    const double g = P.gamma[abase + l];
-                    if (SPIN == 0) {
-                        const double2 a = P.alm_in0[abase + l];
-                        g0 = make_double2(g * a.x, (m == 0) ? 0.0 : g * a.y);
-                    } else {
-                        // G+- = -gamma (E +- iB)/2
-                        const double2 E = P.alm_in0[abase + l], B = P.alm_in1[abase + l];
-                        const double h = -0.5 * g;
-                        g0 = make_double2(h * (E.x - B.y), h * (E.y + B.x));
-                        g1 = make_double2(h * (E.x + B.y), h * (E.y - B.x));
+    if ((any_seek || any_act) && nl > 0) {
+        if (lane == 0) { mbar_init(&sbar[0], 1); mbar_init(&sbar[1], 1); mbar_init_fence(); }
+        __syncwarp();
+        RecStream<ND, STEPS> rs;
+        rs.src = P.rec + (size_t)(alm_index(P.lmax, 0, m) + l0) * ND; rs.nrec = nl; rs.buf = sbuf; rs.bar = sbar;
+        const int nchunk = (nl + STEPS - 1) / STEPS;
+        rs.issue(0, lane);
+        for (int c = 0; c < nchunk; ++c) {
+            if (c + 1 < nchunk) rs.issue(c + 1, lane);
+            const double* rec = rs.wait(c);
+            int cnt = nl - c * STEPS; if (cnt > STEPS) cnt = STEPS;
+            int i = 0;
+            // STEPS is even, so local step i has the parity of (l - l0)
+            while (i + 2 <= cnt) {
+                if (!any_seek) {
+#pragma unroll 2
+                    for (; i + 2 <= cnt; i += 2) {
+                        synth_step<SPIN, R, 2, 0>(S, acc, rec + (size_t)i * ND);
+                        synth_step<SPIN, R, 2, 1>(S, acc, rec + (size_t)(i + 1) * ND);
                     }
-                }
-                sG0[i] = g0;
-                if (SPIN != 0) sG1[i] = g1;
-            }
-            __syncthreads();
-            if (warp_live) {
-                int cnt = nl - c0; if (cnt > LEG_LC) cnt = LEG_LC;
-                // steps are taken in (even, odd) pairs; LEG_LC is even and the staged arrays are zero-padded
-                for (int i = 0; i < cnt; i += 2) {
-                    const double a0 = sA[i], a1 = sA[i + 1];
-                    const double d0 = (SPIN != 0) ? sD[i] : 0.0, d1 = (SPIN != 0) ? sD[i + 1] : 0.0;
-                    if (!any_seek) {
-                        synth_step<SPIN, R, 2, 0>(S, acc, a0, d0, sG0[i], (SPIN != 0) ? sG1[i] : sG0[i]);
-                        synth_step<SPIN, R, 2, 1>(S, acc, a1, d1, sG0[i + 1], (SPIN != 0) ? sG1[i + 1] : sG0[i + 1]);
+                } else {
+                    if (!any_act) {
+                        synth_step<SPIN, R, 0, 0>(S, acc, rec + (size_t)i * ND);
+                        synth_step<SPIN, R, 0, 1>(S, acc, rec + (size_t)(i + 1) * ND);
                     } else {
-                        if (!any_act) {
-                            synth_step<SPIN, R, 0, 0>(S, acc, a0, d0, sG0[i], sG0[i]);
-                            synth_step<SPIN, R, 0, 1>(S, acc, a1, d1, sG0[i], sG0[i]);
-                        } else {
-                            synth_step<SPIN, R, 1, 0>(S, acc, a0, d0, sG0[i], (SPIN != 0) ? sG1[i] : sG0[i]);
-                            synth_step<SPIN, R, 1, 1>(S, acc, a1, d1, sG0[i + 1], (SPIN != 0) ? sG1[i + 1] : sG0[i + 1]);
-                        }
-                        ring_flags<SPIN, R>(S, any_seek, any_act);
+                        synth_step<SPIN, R, 1, 0>(S, acc, rec + (size_t)i * ND);
+                        synth_step<SPIN, R, 1, 1>(S, acc, rec + (size_t)(i + 1) * ND);
                     }
+                    ring_flags<SPIN, R>(S, any_seek, any_act);
+                    i += 2;
                 }
             }
-            __syncthreads();
+            if (i < cnt) {   // odd tail: the very last l of the column (even parity)
+                if (any_act) synth_step<SPIN, R, 1, 0>(S, acc, rec + (size_t)i * ND);
+            }
+            __syncwarp();   // every lane is done with this stage before it is refilled
         }
     }
 
@@ -324,11 +350,11 @@ __global__ void __launch_bounds__(LEG_NT) leg_synth(const LegParams P)
         } else {
             // q = S+ + S-, u = -i (S+ - S-);  south: base sign (-1)^(l0+m) times the alternating sums
             const double bs = ((l0 + m) & 1) ? -1.0 : 1.0;
+            constexpr int A4 = (SPIN == 0 ? 0 : 4);
             if (rN >= 0) {
                 ph[rN] = make_double2(acc[0][j] + acc[2][j], acc[1][j] + acc[3][j]);
                 ph[P.stride_c + rN] = make_double2(acc[1][j] - acc[3][j], -(acc[0][j] - acc[2][j]));
             }
-            constexpr int A4 = (SPIN == 0 ? 0 : 4);
             if (rS >= 0) {
                 ph[rS] = make_double2(bs * (acc[A4 + 0][j] + acc[A4 + 2][j]), bs * (acc[A4 + 1][j] + acc[A4 + 3][j]));
                 ph[P.stride_c + rS] = make_double2(bs * (acc[A4 + 1][j] - acc[A4 + 3][j]), -bs * (acc[A4 + 0][j] - acc[A4 + 2][j]));
@@ -341,9 +367,10 @@ __global__ void __launch_bounds__(LEG_NT) leg_synth(const LegParams P)
 // analysis: (weighted) phase -> alm
 // =============================================================================================================
 template <int SPIN, int R, int MODE, int PAR>
-__device__ __forceinline__ void anal_step(RingState<SPIN, R>& S, const double (&X)[(SPIN == 0 ? 4 : 8)][R], double alpha, double delta,
+__device__ __forceinline__ void anal_step(RingState<SPIN, R>& S, const double (&X)[(SPIN == 0 ? 4 : 8)][R], const double* rec,
                                           double (&part)[(SPIN == 0 ? 2 : 4)])
 {
+    const double2 c = *reinterpret_cast<const double2*>(rec);
 #pragma unroll
     for (int j = 0; j < R; ++j) {
         if (MODE != 0) {
@@ -356,9 +383,9 @@ __device__ __forceinline__ void anal_step(RingState<SPIN, R>& S, const double (&
                 part[1] = fma(p0, X[2 * PAR + 1][j], part[1]);
             } else {
                 // a+ += p+ Y+_N + sgn p- Y+_S ;  a- += p- Y-_N + sgn p+ Y-_S   (Y_S pre-multiplied by the base sign)
+                constexpr int NXX = (SPIN == 0 ? 4 : 8), NPP = (SPIN == 0 ? 2 : 4);
                 part[0] = fma(p0, X[0][j], part[0]);
                 part[1] = fma(p0, X[1][j], part[1]);
-                constexpr int NXX = (SPIN == 0 ? 4 : 8), NPP = (SPIN == 0 ? 2 : 4);
                 part[NPP - 2] = fma(p1, X[NXX - 4][j], part[NPP - 2]);
                 part[NPP - 1] = fma(p1, X[NXX - 3][j], part[NPP - 1]);
                 if (PAR == 0) {
@@ -374,7 +401,7 @@ __device__ __forceinline__ void anal_step(RingState<SPIN, R>& S, const double (&
                 }
             }
         }
-        rec_step<SPIN, R, (MODE != 2)>(S, j, alpha, delta);
+        rec_step<SPIN, R, (MODE != 2)>(S, j, c.x, c.y);
     }
 }
 
@@ -383,21 +410,17 @@ __global__ void __launch_bounds__(LEG_NT) leg_anal(const LegParams P)
 {
     constexpr int NX = (SPIN == 0) ? 4 : 8;
     constexpr int NPART = (SPIN == 0) ? 2 : 4;
-    constexpr int NW = LEG_NT / 32;
-    constexpr int G = RedT<SPIN>::G;
-    typedef typename RedT<SPIN>::type red_t;
-    PIXSHT_DYN_SMEM(smem_raw);
-    red_t* red = reinterpret_cast<red_t*>(smem_raw);              // [NW][G][33]
-    red_t* outw = red + (size_t)NW * G * 33;                      // [NW][LEG_LCA]
-    double* sA = reinterpret_cast<double*>(outw + (size_t)NW * LEG_LCA);   // [LEG_LCA]
-    double* sD = sA + LEG_LCA;                                    // [LEG_LCA]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int row = blockIdx.x / P.nchunks, chunk = blockIdx.x % P.nchunks;
+    constexpr int G = RedT<SPIN>::G, NV = RedT<SPIN>::NV;
+    constexpr int STEPS = ANAL_STEPS;
+    __shared__ __align__(16) double sbuf[2 * STEPS * 2];
+    __shared__ __align__(16) double2 red[NV * G * 33];
+    __shared__ __align__(8) unsigned long long sbar[2];
+    const int lane = threadIdx.x;
+    const int row = blockIdx.x / P.nchunks;
+    const int chunk = P.nchunks - 1 - (int)(blockIdx.x % P.nchunks);
     const int m = P.m_list ? P.m_list[row] : row;
     const int l0 = (SPIN == 0) ? m : (m > 2 ? m : 2);
-    const int pair0 = chunk * (LEG_NT * R) + warp * (32 * R);
-    red_t* wred = red + (size_t)warp * G * 33;
-    red_t* wout = outw + (size_t)warp * LEG_LCA;
+    const int pair0 = chunk * (32 * R);
 
     RingState<SPIN, R> S;
     init_rings<SPIN, R>(P, m, pair0, lane, S);
@@ -429,117 +452,95 @@ __global__ void __launch_bounds__(LEG_NT) leg_anal(const LegParams P)
 
     bool any_seek, any_act;
     ring_flags<SPIN, R>(S, any_seek, any_act);
-    const bool warp_live = any_seek || any_act;
     const int nl = P.lmax - l0 + 1;
-    const int block_live = __syncthreads_or(warp_live ? 1 : 0);
-    if (!block_live || nl <= 0) return;   // whole CTA: nothing to add (outputs are pre-zeroed)
+    if (!(any_seek || any_act) || nl <= 0) return;   // nothing to add (outputs are pre-zeroed)
 
+    if (lane == 0) { mbar_init(&sbar[0], 1); mbar_init(&sbar[1], 1); mbar_init_fence(); }
+    __syncwarp();
     const long long abase = alm_index(P.lmax, 0, m);
-    for (int c0 = 0; c0 < nl; c0 += LEG_LCA) {
-        // stage alpha / delta (zeros beyond lmax) and clear this warp's chunk accumulators
-        for (int i = tid; i < LEG_LCA; i += LEG_NT) {
-            const int l = l0 + c0 + i;
-            double a = 0.0, d = 0.0;
-            if (l <= P.lmax) {
-                a = P.alpha[abase + l];
-                if (SPIN != 0) d = a * (double)m * P.inv_ll1[l];
-            }
-            sA[i] = a; sD[i] = d;
-        }
-        {
-            red_t z; memset(&z, 0, sizeof(z));
-            for (int i = lane; i < LEG_LCA; i += 32) wout[i] = z;
-        }
-        __syncthreads();
-        int cnt = nl - c0; if (cnt > LEG_LCA) cnt = LEG_LCA;
-        if (warp_live) {
-            for (int g0 = 0; g0 < cnt; g0 += G) {
-                int wrote_from = G;   // first step of this group whose partials were written
+    RecStream<2, STEPS> rs;
+    rs.src = reinterpret_cast<const double*>(P.ad + abase + l0); rs.nrec = nl; rs.buf = sbuf; rs.bar = sbar;
+    const int nchunk = (nl + STEPS - 1) / STEPS;
+    rs.issue(0, lane);
+    for (int c = 0; c < nchunk; ++c) {
+        if (c + 1 < nchunk) rs.issue(c + 1, lane);
+        const double* rec = rs.wait(c);
+        int cnt = nl - c * STEPS; if (cnt > STEPS) cnt = STEPS;
+        for (int g0 = 0; g0 < cnt; g0 += G) {
+            int gcnt = cnt - g0; if (gcnt > G) gcnt = G;
+            int wrote_from = G;   // first step of this group whose partials were written
 #pragma unroll 1
-                for (int s = 0; s < G; s += 2) {
-                    const int i = g0 + s;
-                    const double a0 = sA[i], a1 = sA[i + 1];
-                    const double d0 = sD[i], d1 = sD[i + 1];
-                    double part0[NPART], part1[NPART];
+            for (int s = 0; s < gcnt; s += 2) {
+                const double* r0 = rec + (size_t)(g0 + s) * 2;
+                const bool two = (s + 1 < gcnt);
+                double part0[NPART], part1[NPART];
 #pragma unroll
-                    for (int k = 0; k < NPART; ++k) { part0[k] = 0.0; part1[k] = 0.0; }
-                    if (!any_act) {
-                        anal_step<SPIN, R, 0, 0>(S, X, a0, d0, part0);
-                        anal_step<SPIN, R, 0, 1>(S, X, a1, d1, part1);
-                        ring_flags<SPIN, R>(S, any_seek, any_act);
-                        if (any_act) wrote_from = s + 2;
-                        continue;
-                    }
-                    if (any_seek) {
-                        anal_step<SPIN, R, 1, 0>(S, X, a0, d0, part0);
-                        anal_step<SPIN, R, 1, 1>(S, X, a1, d1, part1);
-                        ring_flags<SPIN, R>(S, any_seek, any_act);
-                    } else {
-                        anal_step<SPIN, R, 2, 0>(S, X, a0, d0, part0);
-                        anal_step<SPIN, R, 2, 1>(S, X, a1, d1, part1);
-                    }
-                    if (wrote_from == G) wrote_from = s;
-                    red_t v0, v1;
-                    memcpy(&v0, part0, sizeof(red_t)); memcpy(&v1, part1, sizeof(red_t));
-                    wred[s * 33 + lane] = v0;
-                    wred[(s + 1) * 33 + lane] = v1;
+                for (int k = 0; k < NPART; ++k) { part0[k] = 0.0; part1[k] = 0.0; }
+                if (!any_act) {
+                    anal_step<SPIN, R, 0, 0>(S, X, r0, part0);
+                    if (two) anal_step<SPIN, R, 0, 1>(S, X, r0 + 2, part1);
+                    ring_flags<SPIN, R>(S, any_seek, any_act);
+                    continue;
                 }
-                if (wrote_from < G) {
-                    __syncwarp();
-                    // transpose-reduce: lane -> (step lq = lane % G, source slice = lane / G of 32/G slices)
-                    constexpr int NSL = 32 / G, SL = 32 / NSL;   // slices, sources per slice (= G)
-                    const int lq = lane % G, slice = lane / G;
-                    double t[NPART];
+                if (any_seek) {
+                    anal_step<SPIN, R, 1, 0>(S, X, r0, part0);
+                    if (two) anal_step<SPIN, R, 1, 1>(S, X, r0 + 2, part1);
+                    ring_flags<SPIN, R>(S, any_seek, any_act);
+                } else {
+                    anal_step<SPIN, R, 2, 0>(S, X, r0, part0);
+                    if (two) anal_step<SPIN, R, 2, 1>(S, X, r0 + 2, part1);
+                }
+                if (wrote_from == G) wrote_from = s;
 #pragma unroll
-                    for (int k = 0; k < NPART; ++k) t[k] = 0.0;
-                    if (lq >= wrote_from) {
+                for (int v = 0; v < NV; ++v) {
+                    red[(v * G + s) * 33 + lane] = make_double2(part0[2 * v], part0[2 * v + 1]);
+                    red[(v * G + s + 1) * 33 + lane] = make_double2(part1[2 * v], part1[2 * v + 1]);
+                }
+            }
+            if (wrote_from < G) {
+                __syncwarp();
+                // transpose-reduce: lane -> (step lq = lane % G, source slice = lane / G of 32/G slices)
+                constexpr int NSL = 32 / G, SL = 32 / NSL;
+                const int lq = lane % G, slice = lane / G;
+                double t[NPART];
+#pragma unroll
+                for (int k = 0; k < NPART; ++k) t[k] = 0.0;
+                const bool mine = (lq >= wrote_from) && (lq < gcnt);
+                if (mine) {
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
 #pragma unroll 4
                         for (int k = 0; k < SL; ++k) {
-                            const red_t v = wred[lq * 33 + slice * SL + k];
-                            const double* vd = reinterpret_cast<const double*>(&v);
-#pragma unroll
-                            for (int q = 0; q < NPART; ++q) t[q] += vd[q];
+                            const double2 q = red[(v * G + lq) * 33 + slice * SL + k];
+                            t[2 * v] += q.x; t[2 * v + 1] += q.y;
                         }
                     }
-#pragma unroll
-                    for (int off = G; off < 32; off <<= 1)
-#pragma unroll
-                        for (int q = 0; q < NPART; ++q) t[q] += __shfl_xor_sync(0xffffffffu, t[q], off);
-                    if (slice == 0 && lq >= wrote_from) {
-                        red_t o; memcpy(&o, t, sizeof(red_t));
-                        wout[g0 + lq] = o;
-                    }
-                    __syncwarp();
                 }
+#pragma unroll
+                for (int off = G; off < 32; off <<= 1)
+#pragma unroll
+                    for (int q = 0; q < NPART; ++q) t[q] += __shfl_xor_sync(0xffffffffu, t[q], off);
+                if (slice == 0 && mine) {
+                    const long long k = abase + l0 + c * STEPS + g0 + lq;
+                    const double g = P.gamma[k];
+                    if (SPIN == 0) {
+                        if (t[0] != 0.0) atomicAdd(&P.alm_out0[k].x, g * t[0]);
+                        if (t[1] != 0.0 && m != 0) atomicAdd(&P.alm_out0[k].y, g * t[1]);
+                    } else {
+                        // E = -(a+ + a-)/2 ; B = i (a+ - a-)/2
+                        const double h = 0.5 * g;
+                        const double er = -h * (t[0] + t[NPART - 2]), ei = -h * (t[1] + t[NPART - 1]);
+                        const double br = -h * (t[1] - t[NPART - 1]), bi = h * (t[0] - t[NPART - 2]);
+                        if (er != 0.0) atomicAdd(&P.alm_out0[k].x, er);
+                        if (ei != 0.0 && m != 0) atomicAdd(&P.alm_out0[k].y, ei);
+                        if (br != 0.0) atomicAdd(&P.alm_out1[k].x, br);
+                        if (bi != 0.0 && m != 0) atomicAdd(&P.alm_out1[k].y, bi);
+                    }
+                }
+                __syncwarp();
             }
         }
-        __syncthreads();
-        // combine the warps, scale by gamma_l, accumulate into the global alm
-        for (int i = tid; i < cnt; i += LEG_NT) {
-            const int l = l0 + c0 + i;
-            double t[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                const double* v = reinterpret_cast<const double*>(&outw[(size_t)w * LEG_LCA + i]);
-#pragma unroll
-                for (int k = 0; k < NPART; ++k) t[k] += v[k];
-            }
-            const double g = P.gamma[abase + l];
-            if (SPIN == 0) {
-                if (t[0] != 0.0) atomicAdd(&P.alm_out0[abase + l].x, g * t[0]);
-                if (t[1] != 0.0 && m != 0) atomicAdd(&P.alm_out0[abase + l].y, g * t[1]);
-            } else {
-                // E = -(a+ + a-)/2 ; B = i (a+ - a-)/2
-                const double h = 0.5 * g;
-                const double er = -h * (t[0] + t[2]), ei = -h * (t[1] + t[3]);
-                const double br = -h * (t[1] - t[3]), bi = h * (t[0] - t[2]);
-                if (er != 0.0) atomicAdd(&P.alm_out0[abase + l].x, er);
-                if (ei != 0.0 && m != 0) atomicAdd(&P.alm_out0[abase + l].y, ei);
-                if (br != 0.0) atomicAdd(&P.alm_out1[abase + l].x, br);
-                if (bi != 0.0 && m != 0) atomicAdd(&P.alm_out1[abase + l].y, bi);
-            }
-        }
-        __syncthreads();
+        __syncwarp();   // every lane is done with this stage before it is refilled
     }
 }
 

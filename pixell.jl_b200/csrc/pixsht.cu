@@ -59,10 +59,12 @@ struct pixsht_plan {
     // geometry (host copies kept for introspection)
     std::vector<double> h_theta, h_wgt;
     // device tables
-    DevBuf<double> d_x, d_lsh_hi, d_lsh_lo, d_lch_hi, d_lch_lo, d_mlim, d_wgt, d_inv_ll1;
+    DevBuf<double> d_x, d_lsh_hi, d_lsh_lo, d_lch_hi, d_lch_lo, d_mlim, d_wgt;
     DevBuf<int> d_ringN, d_ringS;
     DevBuf<double> d_lg0_hi, d_lg0_lo, d_lg2_hi, d_lg2_lo;
-    DevBuf<double> d_alpha0, d_gamma0, d_alpha2, d_gamma2;
+    DevBuf<double2> d_ad0, d_ad2;          // (alpha, delta) per (l,m)
+    DevBuf<double> d_gamma0, d_gamma2;
+    DevBuf<double> d_rec0, d_rec2;         // synthesis records, written per call by k_prep_synth
     DevBuf<double2> d_tw, d_phi0tw;
     // work buffers (grown on demand)
     DevBuf<double2> d_phase; int phase_ncomp = 0;
@@ -151,8 +153,8 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     P->nalm = pixsht_nalm(lmax, mmax);
     P->h_theta = theta;
     {
-        int v = env_int("PIXSHT_R0", 4); P->R0 = (v == 1 || v == 2 || v == 4) ? v : 4;
-        v = env_int("PIXSHT_R2", 2); P->R2 = (v == 1 || v == 2 || v == 4) ? v : 2;
+        int v = env_int("PIXSHT_R0", 4); P->R0 = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4;
+        v = env_int("PIXSHT_R2", 4); P->R2 = (v == 1 || v == 2 || v == 4) ? v : 4;
     }
 
     // ---- north/south pairing (equatorial symmetry): pair rings whose cos(theta) are opposite ----
@@ -248,9 +250,9 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     rc |= P->d_ringN.upload(ringN); rc |= P->d_ringS.upload(ringS);
     rc |= P->d_lg0_hi.upload(lg0_hi); rc |= P->d_lg0_lo.upload(lg0_lo); rc |= P->d_lg2_hi.upload(lg2_hi); rc |= P->d_lg2_lo.upload(lg2_lo);
     rc |= P->d_phi0tw.upload(ph0);
-    rc |= P->d_wgt.alloc(nr); rc |= P->d_inv_ll1.alloc(lmax + 1); rc |= P->d_tw.alloc(P->nphi);
-    rc |= P->d_alpha0.alloc(P->nalm); rc |= P->d_gamma0.alloc(P->nalm);
-    rc |= P->d_alpha2.alloc(P->nalm); rc |= P->d_gamma2.alloc(P->nalm);
+    rc |= P->d_wgt.alloc(nr); rc |= P->d_tw.alloc(P->nphi);
+    rc |= P->d_ad0.alloc(P->nalm); rc |= P->d_gamma0.alloc(P->nalm);
+    rc |= P->d_ad2.alloc(P->nalm); rc |= P->d_gamma2.alloc(P->nalm);
     if (rc) return fail(PIXSHT_ERR_NOMEM, "device allocation of plan tables failed");
 
     CU(cudaStreamCreateWithFlags(&P->own_stream, cudaStreamNonBlocking));
@@ -263,10 +265,9 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     } else {
         CU(cudaMemcpyAsync(P->d_wgt.p, wgt_or_empty.data(), sizeof(double) * nr, cudaMemcpyHostToDevice, P->stream));
     }
-    PIXSHT_LAUNCH(k_inv_ll1, (lmax + 128) / 128, 128, 0, P->stream, lmax, P->d_inv_ll1.p);
     PIXSHT_LAUNCH(k_twiddles, (P->nphi + 127) / 128, 128, 0, P->stream, P->nphi, P->d_tw.p);
-    PIXSHT_LAUNCH(k_coef_tables, (mmax + 64) / 64, 64, 0, P->stream, lmax, mmax, 0, P->d_alpha0.p, P->d_gamma0.p);
-    PIXSHT_LAUNCH(k_coef_tables, (mmax + 64) / 64, 64, 0, P->stream, lmax, mmax, 2, P->d_alpha2.p, P->d_gamma2.p);
+    PIXSHT_LAUNCH(k_coef_tables, (mmax + 64) / 64, 64, 0, P->stream, lmax, mmax, 0, P->d_ad0.p, P->d_gamma0.p);
+    PIXSHT_LAUNCH(k_coef_tables, (mmax + 64) / 64, 64, 0, P->stream, lmax, mmax, 2, P->d_ad2.p, P->d_gamma2.p);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(P->stream));
     P->h_wgt.resize(nr);
@@ -281,12 +282,6 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
         CU(cudaFuncSetAttribute(fft_phase2map<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
         CU(cudaFuncSetAttribute(fft_map2phase<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
     }
-    CU(cudaFuncSetAttribute(leg_anal<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leg_anal_smem<0>()));
-    CU(cudaFuncSetAttribute(leg_anal<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leg_anal_smem<0>()));
-    CU(cudaFuncSetAttribute(leg_anal<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leg_anal_smem<0>()));
-    CU(cudaFuncSetAttribute(leg_anal<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leg_anal_smem<2>()));
-    CU(cudaFuncSetAttribute(leg_anal<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leg_anal_smem<2>()));
-    CU(cudaFuncSetAttribute(leg_anal<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leg_anal_smem<2>()));
 #endif
     return PIXSHT_OK;
 }
@@ -358,9 +353,9 @@ extern "C" void pixsht_plan_destroy(pixsht_plan* P)
     // may run from a GC finalizer thread, possibly after the CUDA context is gone: every call below tolerates failure
     (void)cudaSetDevice(P->device);
     P->d_x.release(); P->d_lsh_hi.release(); P->d_lsh_lo.release(); P->d_lch_hi.release(); P->d_lch_lo.release();
-    P->d_mlim.release(); P->d_wgt.release(); P->d_inv_ll1.release(); P->d_ringN.release(); P->d_ringS.release();
+    P->d_mlim.release(); P->d_wgt.release(); P->d_ringN.release(); P->d_ringS.release();
     P->d_lg0_hi.release(); P->d_lg0_lo.release(); P->d_lg2_hi.release(); P->d_lg2_lo.release();
-    P->d_alpha0.release(); P->d_gamma0.release(); P->d_alpha2.release(); P->d_gamma2.release();
+    P->d_ad0.release(); P->d_gamma0.release(); P->d_ad2.release(); P->d_gamma2.release(); P->d_rec0.release(); P->d_rec2.release();
     P->d_tw.release(); P->d_phi0tw.release(); P->d_phase.release();
     for (int c = 0; c < 3; ++c) { P->d_map[c].release(); P->d_alm[c].release(); P->d_alm64[c].release(); }
     for (auto& e : P->ev) if (e) cudaEventDestroy(e);
@@ -378,12 +373,11 @@ static LegParams leg_params(pixsht_plan* P, int spin, int R, int nm, const int* 
     LegParams L;
     memset(&L, 0, sizeof(L));
     L.lmax = P->lmax; L.mmax = P->mmax; L.nm = nm; L.m_list = d_m_list;
-    L.npairs = P->npairs; L.nchunks = (P->npairs + LEG_NT * R - 1) / (LEG_NT * R);
+    L.npairs = P->npairs; L.nchunks = (P->npairs + 32 * R - 1) / (32 * R);
     L.x = P->d_x.p; L.lsh_hi = P->d_lsh_hi.p; L.lsh_lo = P->d_lsh_lo.p; L.lch_hi = P->d_lch_hi.p; L.lch_lo = P->d_lch_lo.p;
     L.ringN = P->d_ringN.p; L.ringS = P->d_ringS.p; L.mlim = P->d_mlim.p;
-    if (spin == 0) { L.lgpref_hi = P->d_lg0_hi.p; L.lgpref_lo = P->d_lg0_lo.p; L.alpha = P->d_alpha0.p; L.gamma = P->d_gamma0.p; }
-    else { L.lgpref_hi = P->d_lg2_hi.p; L.lgpref_lo = P->d_lg2_lo.p; L.alpha = P->d_alpha2.p; L.gamma = P->d_gamma2.p; }
-    L.inv_ll1 = P->d_inv_ll1.p;
+    if (spin == 0) { L.lgpref_hi = P->d_lg0_hi.p; L.lgpref_lo = P->d_lg0_lo.p; L.ad = P->d_ad0.p; L.gamma = P->d_gamma0.p; L.rec = P->d_rec0.p; }
+    else { L.lgpref_hi = P->d_lg2_hi.p; L.lgpref_lo = P->d_lg2_lo.p; L.ad = P->d_ad2.p; L.gamma = P->d_gamma2.p; L.rec = P->d_rec2.p; }
     L.phase = phase; L.stride_c = stride_c; L.stride_m = stride_m;
     return L;
 }
@@ -392,7 +386,7 @@ template <int SPIN>
 static void launch_synth(pixsht_plan* P, int R, const LegParams& L, cudaStream_t st)
 {
     const int grid = L.nm * L.nchunks;
-    void (*k)(const LegParams) = (R == 1) ? leg_synth<SPIN, 1> : (R == 2 ? leg_synth<SPIN, 2> : leg_synth<SPIN, 4>);
+    void (*k)(const LegParams) = (R == 1) ? leg_synth<SPIN, 1> : (R == 2 ? leg_synth<SPIN, 2> : (R == 8 && SPIN == 0 ? leg_synth<0, 8> : leg_synth<SPIN, 4>));
     PIXSHT_LAUNCH(k, grid, LEG_NT, 0, st, L);
     P->launches++;
 }
@@ -400,9 +394,8 @@ template <int SPIN>
 static void launch_anal(pixsht_plan* P, int R, const LegParams& L, cudaStream_t st)
 {
     const int grid = L.nm * L.nchunks;
-    const size_t sm = leg_anal_smem<SPIN>();
-    void (*k)(const LegParams) = (R == 1) ? leg_anal<SPIN, 1> : (R == 2 ? leg_anal<SPIN, 2> : leg_anal<SPIN, 4>);
-    PIXSHT_LAUNCH(k, grid, LEG_NT, sm, st, L);
+    void (*k)(const LegParams) = (R == 1) ? leg_anal<SPIN, 1> : (R == 2 ? leg_anal<SPIN, 2> : (R == 8 && SPIN == 0 ? leg_anal<0, 8> : leg_anal<SPIN, 4>));
+    PIXSHT_LAUNCH(k, grid, LEG_NT, 0, st, L);
     P->launches++;
 }
 
@@ -410,15 +403,20 @@ static void launch_anal(pixsht_plan* P, int R, const LegParams& L, cudaStream_t 
 static int stage_alm2phase(pixsht_plan* P, int ncomp, const double2* const* alm, int nm, const int* d_m_list, double2* phase,
                            long long stride_c, long long stride_m, cudaStream_t st)
 {
+    const int prep_grid = P->sm_count > 0 ? P->sm_count * 8 : 256;
     if (ncomp == 1 || ncomp == 3) {
+        if (P->d_rec0.n < (size_t)P->nalm * 4 && P->d_rec0.alloc((size_t)P->nalm * 4)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
+        PIXSHT_LAUNCH(k_prep_synth<0>, prep_grid, 256, 0, st, P->nalm, P->lmax, P->d_ad0.p, P->d_gamma0.p, alm[0], alm[0], P->d_rec0.p);
+        P->launches++;
         LegParams L = leg_params(P, 0, P->R0, nm, d_m_list, phase, stride_c, stride_m);
-        L.alm_in0 = alm[0];
         launch_synth<0>(P, P->R0, L, st);
     }
     if (ncomp >= 2) {
         const int c0 = ncomp == 3 ? 1 : 0;
+        if (P->d_rec2.n < (size_t)P->nalm * 6 && P->d_rec2.alloc((size_t)P->nalm * 6)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
+        PIXSHT_LAUNCH(k_prep_synth<2>, prep_grid, 256, 0, st, P->nalm, P->lmax, P->d_ad2.p, P->d_gamma2.p, alm[c0], alm[c0 + 1], P->d_rec2.p);
+        P->launches++;
         LegParams L = leg_params(P, 2, P->R2, nm, d_m_list, phase + (long long)c0 * stride_c, stride_c, stride_m);
-        L.alm_in0 = alm[c0]; L.alm_in1 = alm[c0 + 1];
         launch_synth<2>(P, P->R2, L, st);
     }
     CU(cudaGetLastError());

@@ -36,26 +36,29 @@ __device__ __forceinline__ double coefA(int l, int m, int s)
     return l1 * sqrt(num / den);
 }
 
-// Per m (one thread each): alpha_l and gamma_l, l = l0..lmax, l0 = max(m, s), stored at alm_index(lmax, l, m).
+// Per m (one thread each): (alpha_l, delta_l) and gamma_l, l = l0..lmax, l0 = max(m, s), stored at alm_index(lmax, l, m).
 // lambda_l = gamma_l p_l with p_{l+1} = (alpha_l x + delta_l) p_l - p_{l-1}  (unit lower coefficient => 2 FMA per step):
-//   gamma_{l0} = gamma_{l0+1} = 1, gamma_{l+1} = (A_l/A_{l-1}) gamma_{l-1}, alpha_l = A_l gamma_l / gamma_{l+1}.
-__global__ void k_coef_tables(int lmax, int mmax, int s, double* __restrict__ alpha, double* __restrict__ gamma)
+//   gamma_{l0} = gamma_{l0+1} = 1, gamma_{l+1} = (A_l/A_{l-1}) gamma_{l-1}, alpha_l = A_l gamma_l / gamma_{l+1},
+//   delta_l = -alpha_l mu_l with mu_l = -m s/(l(l+1)) for d^l_{-m,s}  (the s = -2 sequence uses -delta_l).
+__global__ void k_coef_tables(int lmax, int mmax, int s, double2* __restrict__ ad, double* __restrict__ gamma)
 {
     int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m > mmax) return;
     const int l0 = m > s ? m : s;
     const long long base = alm_index(lmax, 0, m);
-    for (int l = m; l < l0 && l <= lmax; ++l) { alpha[base + l] = 0.0; gamma[base + l] = 0.0; }
+    for (int l = m; l < l0 && l <= lmax; ++l) { ad[base + l] = make_double2(0.0, 0.0); gamma[base + l] = 0.0; }
     if (l0 > lmax) return;
+    const double ms = (double)m * (double)s;
     double Aprev = coefA(l0, m, s);
     double g_lm1 = 1.0, g_l = 1.0;  // gamma_{l-1}, gamma_l while stepping; start at l = l0+1
     gamma[base + l0] = 1.0;
-    alpha[base + l0] = Aprev;       // gamma_{l0}/gamma_{l0+1} = 1
+    ad[base + l0] = make_double2(Aprev, l0 > 0 ? Aprev * ms / ((double)l0 * (double)(l0 + 1)) : 0.0);   // gamma_{l0}/gamma_{l0+1} = 1
     for (int l = l0 + 1; l <= lmax; ++l) {
         const double A = coefA(l, m, s);
         const double g_lp1 = (A / Aprev) * g_lm1;
+        const double a = A * g_l / g_lp1;
         gamma[base + l] = g_l;
-        alpha[base + l] = A * g_l / g_lp1;
+        ad[base + l] = make_double2(a, a * ms / ((double)l * (double)(l + 1)));
         g_lm1 = g_l; g_l = g_lp1; Aprev = A;
     }
 }
@@ -68,13 +71,6 @@ __global__ void k_twiddles(int n, double2* __restrict__ tw)
     double s, c;
     sincospi(2.0 * (double)t / (double)n, &s, &c);
     tw[t] = make_double2(c, -s);
-}
-
-__global__ void k_inv_ll1(int lmax, double* __restrict__ v)
-{
-    int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l > lmax) return;
-    v[l] = l == 0 ? 0.0 : 2.0 / ((double)l * (double)(l + 1));
 }
 
 }  // namespace pixsht

@@ -29,7 +29,7 @@
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __grid_constant__
-#define __align__(x) alignas(x)
+#define __align__(x) __attribute__((aligned(x)))
 
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct uint3_ { unsigned x, y, z; };

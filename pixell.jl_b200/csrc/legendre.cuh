@@ -2,9 +2,9 @@
 // ("libsharp2 sharp_execute internals, stage B").  FP64 FMA bound; nothing here is a tensor-core shape.
 //
 // Work decomposition: one CTA = one warp = one independent work unit = (one m) x (32*R contiguous north/south ring
-// pairs); lane i owns pairs base + i + 32 j, j < R (coalesced phase I/O, neighbouring rings => coherent seek/active
-// state across the warp).  There is no block-level barrier anywhere: ncu (profiles/r01) showed `barrier` as the top
-// stall when four warps with different amounts of work shared a CTA and a staging buffer.
+// pairs); lane i owns pairs base + i + 32 j, j < R (coalesced phase I/O, neighbouring rings => the rings of a warp
+// become active within a few per cent of the l range of each other).  There is no block-level barrier anywhere: ncu
+// (profiles/r01) showed `barrier` as the top stall when four warps with different amounts of work shared a CTA.
 //
 // For each pair the scaled functions p_l = lambda_lm(theta)/gamma_l are generated on the fly by
 //     p_{l+1} = (alpha_l x + delta_l) p_l - p_{l-1}                       (2 FP64 ops per l and function)
@@ -15,8 +15,14 @@
 //              north = even + odd, south = even - odd  (equatorial symmetry);
 //   analysis : per-l partial sums over the thread's R rings, a warp-private shared-memory transpose-reduction
 //              every G (16 / 8) steps, then one atomicAdd per (l, m, warp).
-// Dynamic range: p carries an exponent e (multiple of 64, <= 0); while e < 0 the ring is "seeking" (recurrence only,
-// 2 ops per l) and contributes nothing; see common.cuh.  Rings that can never matter for this m are pruned.
+//
+// Dynamic range (DESIGN.md "activation table"): lambda_lm(theta) ~ sin^m(theta) underflows FP64 by thousands of
+// decades near the poles.  The scaled-exponent "seek" from l = m up to the first l where the function reaches 2^-90
+// depends only on the plan (m, theta), not on the data, so it runs ONCE at plan creation (k_seek_table): for every
+// (m, ring pair) it stores l_act and the recurrence state (p, p_{l-1}) there, or L_NEVER when the pair never matters
+// for l <= lmax.  The transform kernels start each ring at its l_act in plain FP64: no exponents, no rescale checks,
+// no seeding arithmetic in the hot loops.  A warp runs "mixed" steps (per-ring predicate l >= l_act) from the earliest
+// l_act of its rings to the latest, then branch-free full steps to lmax.
 #pragma once
 #include "common.cuh"
 
@@ -29,6 +35,7 @@ namespace pixsht {
 template <int SPIN> struct SynthRec { static constexpr int ND = (SPIN == 0) ? 4 : 6; static constexpr int STEPS = (SPIN == 0) ? 128 : 64; };
 constexpr int ANAL_STEPS = 128;
 template <int SPIN> struct RedT { static constexpr int G = (SPIN == 0) ? 16 : 8; static constexpr int NV = (SPIN == 0) ? 1 : 2; };   // G: l-steps per reduction group; NV: double2 values per l
+constexpr int L_NEVER = 0x3fffffff;
 
 struct LegParams {
     int lmax, mmax;
@@ -36,17 +43,27 @@ struct LegParams {
     const int* m_list;      // device; nullptr => m = row index
     int npairs, nchunks;    // ring pairs; chunks of 32*R pairs per m
     const double* x;        // [npairs] cos(theta) of the pair's northern member
-    const double* lsh_hi; const double* lsh_lo;   // log2 sin(theta/2), double-double
-    const double* lch_hi; const double* lch_lo;   // log2 cos(theta/2)
     const int* ringN; const int* ringS;           // band ring index of the north/south member, -1 if absent
-    const double* mlim;     // [npairs] prune: the pair is skipped for m > mlim
-    const double* lgpref_hi; const double* lgpref_lo;   // [mmax+1] log2 of the seed prefactor for this spin family
+    const int* lact;        // [(mmax+1) * npairs] first l at which the pair contributes, L_NEVER if none
+    const double* st;       // [(mmax+1) * npairs * NS] state at l_act: spin 0 (p, p_prev); spin 2 (p+, p-, p+_prev, p-_prev)
     const double2* ad;      // [nalm] (alpha, delta) table of this spin family
     const double* gamma;    // [nalm]
     const double* rec;      // synthesis: [nalm * SynthRec::ND] records
     double2* alm_out0; double2* alm_out1;               // analysis output  (T | E,B), pre-zeroed, accumulated atomically
     double2* phase;         // element (c,row,ring) at c*stride_c + row*stride_m + ring
     long long stride_c, stride_m;
+};
+
+// plan-time inputs of the activation table
+struct SeekParams {
+    int lmax, mmax, npairs;
+    const double* x;
+    const double* lsh_hi; const double* lsh_lo;   // log2 sin(theta/2), double-double
+    const double* lch_hi; const double* lch_lo;   // log2 cos(theta/2)
+    const double* mlim;     // [npairs] prune: the pair is skipped for m > mlim
+    const double* lgpref_hi; const double* lgpref_lo;   // [mmax+1] log2 of the seed prefactor for this spin family
+    const double2* ad;
+    int* lact; double* st;
 };
 
 // ---- pre-scaling pass: alm -> records (element-wise over the alm index; ~1 ms at lmax = 10800) ----------------------
@@ -74,12 +91,12 @@ __global__ void k_prep_synth(long long nalm, int lmax, const double2* __restrict
     }
 }
 
-// ---- seeds -------------------------------------------------------------------------------------------------
+// ---- seeds (plan time only) --------------------------------------------------------------------------------
 // value = sign * 2^(lg) with lg = lgpref[m] + a*log2 cos(theta/2) + b*log2 sin(theta/2), returned as (k, frac) with
 // lg = k + frac, k integer-valued.  zero => the seed vanishes (pole).
 struct LogVal { double k, frac; bool zero; };
 
-__device__ __forceinline__ LogVal seed_log(const LegParams& P, int m, int pair, int a, int b)
+__device__ __forceinline__ LogVal seed_log(const SeekParams& P, int m, int pair, int a, int b)
 {
     LogVal r; r.zero = false; r.k = 0; r.frac = 0;
     dd acc; acc.hi = P.lgpref_hi[m]; acc.lo = P.lgpref_lo[m];
@@ -114,71 +131,133 @@ __device__ __forceinline__ double seed_value(const LogVal& v, int e, double sign
     return sign * ldexp(exp2(v.frac), (int)d);
 }
 
-template <int SPIN, int R>
-struct RingState {
-    double x[R];
-    double p[(SPIN == 0 ? 1 : 2)][R];
-    double pp[(SPIN == 0 ? 1 : 2)][R];
-    int e[R];
-};
-
-template <int SPIN, int R>
-__device__ __forceinline__ void init_rings(const LegParams& P, int m, int pair0, int lane, RingState<SPIN, R>& S)
-{
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-        const int pair = pair0 + j * 32 + lane;
-        S.x[j] = 0.0; S.e[j] = E_DEAD;
-        S.p[0][j] = 0.0; S.pp[0][j] = 0.0;
-        if (SPIN != 0) { S.p[SPIN != 0][j] = 0.0; S.pp[SPIN != 0][j] = 0.0; }
-        if (pair < P.npairs && (double)m <= P.mlim[pair]) {
-            S.x[j] = P.x[pair];
-            const double sgn = (m & 1) ? -1.0 : 1.0;
-            if (SPIN == 0) {
-                // lambda_mm = (-1)^m N_m sin^m(theta), sin(theta) = 2 sin(theta/2) cos(theta/2): the factor 2^m is in lgpref
-                LogVal v = seed_log(P, m, pair, m, m);
-                if (!v.zero) {
-                    const int e = seed_exponent(v.k);
-                    S.p[0][j] = seed_value(v, e, sgn);
-                    S.e[j] = e;
-                }
-            } else {
-                // l0 = max(m,2):  lambda^+ ~ cos^{|m-2|} sin^{m+2},  lambda^- ~ cos^{m+2} sin^{|m-2|}  (half angles)
-                const int am = m >= 2 ? m - 2 : 2 - m;
-                LogVal vp = seed_log(P, m, pair, am, m + 2);
-                LogVal vm = seed_log(P, m, pair, m + 2, am);
-                const double sp = sgn, sm = (m >= 2) ? sgn : 1.0;
-                if (!(vp.zero && vm.zero)) {
-                    double kmax = vp.zero ? vm.k : (vm.zero ? vp.k : fmax(vp.k, vm.k));
-                    const int e = seed_exponent(kmax);
-                    S.p[0][j] = seed_value(vp, e, sp);
-                    S.p[SPIN != 0][j] = seed_value(vm, e, sm);
-                    S.e[j] = e;
-                }
-            }
-        }
-    }
-}
-
 __device__ __forceinline__ bool over_thr(double v)
 {
     return ((unsigned)__double2hiint(v) & 0x7ff00000u) >= SEEK_THR_EXPBITS;
 }
 
-// one recurrence step for ring slot j (+ rescale check when CHECK)
-template <int SPIN, int R, bool CHECK>
+// One thread per (m, ring pair): seed at l0 = max(m, |s|) as mantissa * 2^e (e a multiple of 64, <= 0), run the
+// recurrence with rescaling until e reaches 0 (the function has grown to >= 2^-90) and record l and the state there.
+template <int SPIN>
+__global__ void __launch_bounds__(128) k_seek_table(const SeekParams P)
+{
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = blockIdx.y;
+    if (pair >= P.npairs) return;
+    const int l0 = (SPIN == 0) ? m : (m > 2 ? m : 2);
+    double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;   // p: value at l, q: value at l-1  (0: lambda / lambda+, 1: lambda-)
+    int e = E_DEAD;
+    if ((double)m <= P.mlim[pair] && l0 <= P.lmax) {
+        const double sgn = (m & 1) ? -1.0 : 1.0;
+        if (SPIN == 0) {
+            // lambda_mm = (-1)^m N_m sin^m(theta), sin(theta) = 2 sin(theta/2) cos(theta/2): the factor 2^m is in lgpref
+            LogVal v = seed_log(P, m, pair, m, m);
+            if (!v.zero) { e = seed_exponent(v.k); p0 = seed_value(v, e, sgn); }
+        } else {
+            // l0 = max(m,2):  lambda^+ ~ cos^{|m-2|} sin^{m+2},  lambda^- ~ cos^{m+2} sin^{|m-2|}  (half angles)
+            const int am = m >= 2 ? m - 2 : 2 - m;
+            LogVal vp = seed_log(P, m, pair, am, m + 2);
+            LogVal vm = seed_log(P, m, pair, m + 2, am);
+            const double sp = sgn, sm = (m >= 2) ? sgn : 1.0;
+            if (!(vp.zero && vm.zero)) {
+                const double kmax = vp.zero ? vm.k : (vm.zero ? vp.k : fmax(vp.k, vm.k));
+                e = seed_exponent(kmax);
+                p0 = seed_value(vp, e, sp);
+                p1 = seed_value(vm, e, sm);
+            }
+        }
+    }
+    int l = l0;
+    if (e < 0) {
+        const double x = P.x[pair];
+        const double2* ad = P.ad + alm_index(P.lmax, 0, m);
+        const double sc = 5.421010862427522e-20;  // 2^-64
+        while (e < 0 && l <= P.lmax) {
+            const double2 c = ad[l];
+            if (SPIN == 0) {
+                const double pn = fma(c.x * x, p0, -q0);
+                q0 = p0; p0 = pn;
+                if (over_thr(pn)) { p0 *= sc; q0 *= sc; e += SEEK_QUANT; }
+            } else {
+                const double pn = fma(fma(c.x, x, c.y), p0, -q0);
+                const double mn = fma(fma(c.x, x, -c.y), p1, -q1);
+                q0 = p0; p0 = pn; q1 = p1; p1 = mn;
+                if (over_thr(pn) || over_thr(mn)) { p0 *= sc; q0 *= sc; p1 *= sc; q1 *= sc; e += SEEK_QUANT; }
+            }
+            ++l;
+        }
+    }
+    const size_t k = (size_t)m * P.npairs + pair;
+    const bool live = (e == 0) && (l <= P.lmax);
+    P.lact[k] = live ? l : L_NEVER;
+    if (SPIN == 0) reinterpret_cast<double2*>(P.st)[k] = live ? make_double2(p0, q0) : make_double2(0.0, 0.0);
+    else {
+        double2* o = reinterpret_cast<double2*>(P.st) + 2 * k;
+        o[0] = live ? make_double2(p0, p1) : make_double2(0.0, 0.0);
+        o[SPIN != 0] = live ? make_double2(q0, q1) : make_double2(0.0, 0.0);
+    }
+}
+
+// ---- per-thread ring state of the transform kernels ------------------------------------------------------------
+template <int SPIN, int R>
+struct RingState {
+    double x[R];
+    double p[(SPIN == 0 ? 1 : 2)][R];
+    double pp[(SPIN == 0 ? 1 : 2)][R];
+    int la[R];
+};
+
+__device__ __forceinline__ int warp_min(int v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { const int o = __shfl_xor_sync(0xffffffffu, v, off); v = o < v ? o : v; }
+    return v;
+}
+__device__ __forceinline__ int warp_max(int v)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { const int o = __shfl_xor_sync(0xffffffffu, v, off); v = o > v ? o : v; }
+    return v;
+}
+
+// loads the activation state of the warp's rings; lmin / lmaxact = earliest / latest l_act over the live rings of the warp
+template <int SPIN, int R>
+__device__ __forceinline__ void load_rings(const LegParams& P, int m, int pair0, int lane, RingState<SPIN, R>& S, int& lmin, int& lmaxact)
+{
+    int mn = L_NEVER, mx = -1;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const int pair = pair0 + j * 32 + lane;
+        S.x[j] = 0.0; S.la[j] = L_NEVER;
+        S.p[0][j] = 0.0; S.pp[0][j] = 0.0;
+        if (SPIN != 0) { S.p[SPIN != 0][j] = 0.0; S.pp[SPIN != 0][j] = 0.0; }
+        if (pair < P.npairs) {
+            const size_t k = (size_t)m * P.npairs + pair;
+            const int la = P.lact[k];
+            if (la <= P.lmax) {
+                S.la[j] = la; S.x[j] = P.x[pair];
+                if (SPIN == 0) {
+                    const double2 v = reinterpret_cast<const double2*>(P.st)[k];
+                    S.p[0][j] = v.x; S.pp[0][j] = v.y;
+                } else {
+                    const double2 v = reinterpret_cast<const double2*>(P.st)[2 * k], w = reinterpret_cast<const double2*>(P.st)[2 * k + 1];
+                    S.p[0][j] = v.x; S.p[SPIN != 0][j] = v.y; S.pp[0][j] = w.x; S.pp[SPIN != 0][j] = w.y;
+                }
+                mn = la < mn ? la : mn; mx = la > mx ? la : mx;
+            }
+        }
+    }
+    lmin = warp_min(mn); lmaxact = warp_max(mx);
+}
+
+// one recurrence step for ring slot j
+template <int SPIN, int R>
 __device__ __forceinline__ void rec_step(RingState<SPIN, R>& S, int j, double alpha, double delta)
 {
     if (SPIN == 0) {
         const double u = alpha * S.x[j];
         const double pn = fma(u, S.p[0][j], -S.pp[0][j]);
         S.pp[0][j] = S.p[0][j]; S.p[0][j] = pn;
-        if (CHECK) {
-            if (S.e[j] < 0 && over_thr(pn)) {
-                const double sc = 5.421010862427522e-20;  // 2^-64
-                S.p[0][j] *= sc; S.pp[0][j] *= sc; S.e[j] += SEEK_QUANT;
-            }
-        }
     } else {
         const double up = fma(alpha, S.x[j], delta);
         const double um = fma(alpha, S.x[j], -delta);
@@ -186,23 +265,7 @@ __device__ __forceinline__ void rec_step(RingState<SPIN, R>& S, int j, double al
         const double mn = fma(um, S.p[SPIN != 0][j], -S.pp[SPIN != 0][j]);
         S.pp[0][j] = S.p[0][j]; S.p[0][j] = pn;
         S.pp[SPIN != 0][j] = S.p[SPIN != 0][j]; S.p[SPIN != 0][j] = mn;
-        if (CHECK) {
-            if (S.e[j] < 0 && (over_thr(pn) || over_thr(mn))) {
-                const double sc = 5.421010862427522e-20;
-                S.p[0][j] *= sc; S.pp[0][j] *= sc; S.p[SPIN != 0][j] *= sc; S.pp[SPIN != 0][j] *= sc; S.e[j] += SEEK_QUANT;
-            }
-        }
     }
-}
-
-template <int SPIN, int R>
-__device__ __forceinline__ void ring_flags(const RingState<SPIN, R>& S, bool& any_seek, bool& any_act)
-{
-    bool s = false, a = false;
-#pragma unroll
-    for (int j = 0; j < R; ++j) { s |= (S.e[j] < 0); a |= (S.e[j] == 0); }
-    any_seek = __any_sync(0xffffffffu, s);
-    any_act = __any_sync(0xffffffffu, a);
 }
 
 // ---- warp-private record stream: two-stage shared ring filled by TMA bulk copies ----------------------------------
@@ -230,20 +293,18 @@ struct RecStream {
 // =============================================================================================================
 // synthesis: alm -> phase
 // =============================================================================================================
-// MODE 0: every ring of the warp is still seeking (recurrence + check only); 1: mixed (masked accumulate + check);
-// MODE 2: every live ring is active (no masks, no checks)
-template <int SPIN, int R, int MODE, int PAR>
-__device__ __forceinline__ void synth_step(RingState<SPIN, R>& S, double (&acc)[(SPIN == 0 ? 4 : 8)][R], const double* rec)
+// MIXED: per-ring predicate l >= l_act (some rings of the warp have not started yet); otherwise branch-free
+template <int SPIN, int R, bool MIXED, int PAR>
+__device__ __forceinline__ void synth_step(RingState<SPIN, R>& S, double (&acc)[(SPIN == 0 ? 4 : 8)][R], const double* rec, int l)
 {
     const double2 c = *reinterpret_cast<const double2*>(rec);
     const double2 g0 = *reinterpret_cast<const double2*>(rec + 2);
     const double2 g1 = *reinterpret_cast<const double2*>(rec + (SPIN == 0 ? 2 : 4));
 #pragma unroll
     for (int j = 0; j < R; ++j) {
-        if (MODE != 0) {
-            double p0 = S.p[0][j];
-            double p1 = S.p[SPIN != 0][j];
-            if (MODE == 1) { if (S.e[j] != 0) { p0 = 0.0; p1 = 0.0; } }
+        if (!MIXED || l >= S.la[j]) {
+            const double p0 = S.p[0][j];
+            const double p1 = S.p[SPIN != 0][j];
             if (SPIN == 0) {
                 acc[2 * PAR + 0][j] = fma(p0, g0.x, acc[2 * PAR + 0][j]);
                 acc[2 * PAR + 1][j] = fma(p0, g0.y, acc[2 * PAR + 1][j]);
@@ -266,8 +327,8 @@ __device__ __forceinline__ void synth_step(RingState<SPIN, R>& S, double (&acc)[
                     acc[A4 + 3][j] = fma(-p0, g1.y, acc[A4 + 3][j]);
                 }
             }
+            rec_step<SPIN, R>(S, j, c.x, c.y);
         }
-        rec_step<SPIN, R, (MODE != 2)>(S, j, c.x, c.y);
     }
 }
 
@@ -286,52 +347,45 @@ __global__ void __launch_bounds__(LEG_NT) leg_synth(const LegParams P)
     const int pair0 = chunk * (32 * R);
 
     RingState<SPIN, R> S;
-    init_rings<SPIN, R>(P, m, pair0, lane, S);
+    int lmin, lmaxact;
+    load_rings<SPIN, R>(P, m, pair0, lane, S, lmin, lmaxact);
     double acc[NACC][R];
 #pragma unroll
     for (int a = 0; a < NACC; ++a)
 #pragma unroll
         for (int j = 0; j < R; ++j) acc[a][j] = 0.0;
 
-    bool any_seek, any_act;
-    ring_flags<SPIN, R>(S, any_seek, any_act);
-    const int nl = P.lmax - l0 + 1;
-
-    if ((any_seek || any_act) && nl > 0) {
+    if (lmin <= P.lmax) {
+        // local step t <-> l = lstart + t; lstart keeps the parity of l0 so that step parity = parity of (l - l0)
+        const int lstart = l0 + ((lmin - l0) & ~1);
+        const int nl = P.lmax - lstart + 1;
+        const int nmixed = (lmaxact - lstart + 1) & ~1;   // steps [0, nmixed) need the per-ring predicate
         if (lane == 0) { mbar_init(&sbar[0], 1); mbar_init(&sbar[1], 1); mbar_init_fence(); }
         __syncwarp();
         RecStream<ND, STEPS> rs;
-        rs.src = P.rec + (size_t)(alm_index(P.lmax, 0, m) + l0) * ND; rs.nrec = nl; rs.buf = sbuf; rs.bar = sbar;
+        rs.src = P.rec + (size_t)(alm_index(P.lmax, 0, m) + lstart) * ND; rs.nrec = nl; rs.buf = sbuf; rs.bar = sbar;
         const int nchunk = (nl + STEPS - 1) / STEPS;
         rs.issue(0, lane);
         for (int c = 0; c < nchunk; ++c) {
             if (c + 1 < nchunk) rs.issue(c + 1, lane);
             const double* rec = rs.wait(c);
-            int cnt = nl - c * STEPS; if (cnt > STEPS) cnt = STEPS;
+            const int t0 = c * STEPS;
+            int cnt = nl - t0; if (cnt > STEPS) cnt = STEPS;
+            int na = nmixed - t0; if (na > cnt) na = cnt;
             int i = 0;
-            // STEPS is even, so local step i has the parity of (l - l0)
-            while (i + 2 <= cnt) {
-                if (!any_seek) {
+            // STEPS and nmixed are even, so local step i has the parity of (l - l0)
+#pragma unroll 1
+            for (; i + 2 <= na; i += 2) {
+                synth_step<SPIN, R, true, 0>(S, acc, rec + (size_t)i * ND, lstart + t0 + i);
+                synth_step<SPIN, R, true, 1>(S, acc, rec + (size_t)(i + 1) * ND, lstart + t0 + i + 1);
+            }
+            if (i < na) { synth_step<SPIN, R, true, 0>(S, acc, rec + (size_t)i * ND, lstart + t0 + i); ++i; }   // odd tail at lmax
 #pragma unroll 2
-                    for (; i + 2 <= cnt; i += 2) {
-                        synth_step<SPIN, R, 2, 0>(S, acc, rec + (size_t)i * ND);
-                        synth_step<SPIN, R, 2, 1>(S, acc, rec + (size_t)(i + 1) * ND);
-                    }
-                } else {
-                    if (!any_act) {
-                        synth_step<SPIN, R, 0, 0>(S, acc, rec + (size_t)i * ND);
-                        synth_step<SPIN, R, 0, 1>(S, acc, rec + (size_t)(i + 1) * ND);
-                    } else {
-                        synth_step<SPIN, R, 1, 0>(S, acc, rec + (size_t)i * ND);
-                        synth_step<SPIN, R, 1, 1>(S, acc, rec + (size_t)(i + 1) * ND);
-                    }
-                    ring_flags<SPIN, R>(S, any_seek, any_act);
-                    i += 2;
-                }
+            for (; i + 2 <= cnt; i += 2) {
+                synth_step<SPIN, R, false, 0>(S, acc, rec + (size_t)i * ND, 0);
+                synth_step<SPIN, R, false, 1>(S, acc, rec + (size_t)(i + 1) * ND, 0);
             }
-            if (i < cnt) {   // odd tail: the very last l of the column (even parity)
-                if (any_act) synth_step<SPIN, R, 1, 0>(S, acc, rec + (size_t)i * ND);
-            }
+            if (i < cnt) synth_step<SPIN, R, false, 0>(S, acc, rec + (size_t)i * ND, 0);   // odd tail: the very last l of the column
             __syncwarp();   // every lane is done with this stage before it is refilled
         }
     }
@@ -366,17 +420,16 @@ __global__ void __launch_bounds__(LEG_NT) leg_synth(const LegParams P)
 // =============================================================================================================
 // analysis: (weighted) phase -> alm
 // =============================================================================================================
-template <int SPIN, int R, int MODE, int PAR>
+template <int SPIN, int R, bool MIXED, int PAR>
 __device__ __forceinline__ void anal_step(RingState<SPIN, R>& S, const double (&X)[(SPIN == 0 ? 4 : 8)][R], const double* rec,
-                                          double (&part)[(SPIN == 0 ? 2 : 4)])
+                                          double (&part)[(SPIN == 0 ? 2 : 4)], int l)
 {
     const double2 c = *reinterpret_cast<const double2*>(rec);
 #pragma unroll
     for (int j = 0; j < R; ++j) {
-        if (MODE != 0) {
-            double p0 = S.p[0][j];
-            double p1 = S.p[SPIN != 0][j];
-            if (MODE == 1) { if (S.e[j] != 0) { p0 = 0.0; p1 = 0.0; } }
+        if (!MIXED || l >= S.la[j]) {
+            const double p0 = S.p[0][j];
+            const double p1 = S.p[SPIN != 0][j];
             if (SPIN == 0) {
                 // even (l-m): X_N + X_S ; odd: X_N - X_S
                 part[0] = fma(p0, X[2 * PAR + 0][j], part[0]);
@@ -400,8 +453,8 @@ __device__ __forceinline__ void anal_step(RingState<SPIN, R>& S, const double (&
                     part[NPP - 1] = fma(-p0, X[NXX - 1][j], part[NPP - 1]);
                 }
             }
+            rec_step<SPIN, R>(S, j, c.x, c.y);
         }
-        rec_step<SPIN, R, (MODE != 2)>(S, j, c.x, c.y);
     }
 }
 
@@ -423,7 +476,9 @@ __global__ void __launch_bounds__(LEG_NT) leg_anal(const LegParams P)
     const int pair0 = chunk * (32 * R);
 
     RingState<SPIN, R> S;
-    init_rings<SPIN, R>(P, m, pair0, lane, S);
+    int lmin, lmaxact;
+    load_rings<SPIN, R>(P, m, pair0, lane, S, lmin, lmaxact);
+    if (lmin > P.lmax) return;   // nothing to add (outputs are pre-zeroed)
 
     // folded inputs
     double X[NX][R];
@@ -433,7 +488,7 @@ __global__ void __launch_bounds__(LEG_NT) leg_anal(const LegParams P)
     for (int j = 0; j < R; ++j) {
         const int pair = pair0 + j * 32 + lane;
         double2 qN = make_double2(0.0, 0.0), qS = qN, uN = qN, uS = qN;
-        if (pair < P.npairs && S.e[j] != E_DEAD) {
+        if (S.la[j] != L_NEVER) {
             const int rN = P.ringN[pair], rS = P.ringS[pair];
             if (rN >= 0) { qN = ph[rN]; if (SPIN != 0) uN = ph[P.stride_c + rN]; }
             if (rS >= 0) { qS = ph[rS]; if (SPIN != 0) uS = ph[P.stride_c + rS]; }
@@ -450,16 +505,14 @@ __global__ void __launch_bounds__(LEG_NT) leg_anal(const LegParams P)
         }
     }
 
-    bool any_seek, any_act;
-    ring_flags<SPIN, R>(S, any_seek, any_act);
-    const int nl = P.lmax - l0 + 1;
-    if (!(any_seek || any_act) || nl <= 0) return;   // nothing to add (outputs are pre-zeroed)
-
+    const int lstart = l0 + ((lmin - l0) & ~1);
+    const int nl = P.lmax - lstart + 1;
+    const int nmixed = (lmaxact - lstart + 1) & ~1;
     if (lane == 0) { mbar_init(&sbar[0], 1); mbar_init(&sbar[1], 1); mbar_init_fence(); }
     __syncwarp();
     const long long abase = alm_index(P.lmax, 0, m);
     RecStream<2, STEPS> rs;
-    rs.src = reinterpret_cast<const double*>(P.ad + abase + l0); rs.nrec = nl; rs.buf = sbuf; rs.bar = sbar;
+    rs.src = reinterpret_cast<const double*>(P.ad + abase + lstart); rs.nrec = nl; rs.buf = sbuf; rs.bar = sbar;
     const int nchunk = (nl + STEPS - 1) / STEPS;
     rs.issue(0, lane);
     for (int c = 0; c < nchunk; ++c) {
@@ -468,60 +521,68 @@ __global__ void __launch_bounds__(LEG_NT) leg_anal(const LegParams P)
         int cnt = nl - c * STEPS; if (cnt > STEPS) cnt = STEPS;
         for (int g0 = 0; g0 < cnt; g0 += G) {
             int gcnt = cnt - g0; if (gcnt > G) gcnt = G;
-            int wrote_from = G;   // first step of this group whose partials were written
+            const int t0 = c * STEPS + g0;
+            if (t0 >= nmixed && gcnt == G) {
+                // fast path: every live ring is active for the whole group -> straight-line code
+#pragma unroll
+                for (int s = 0; s < G; s += 2) {
+                    const double* r0 = rec + (size_t)(g0 + s) * 2;
+                    double part0[NPART], part1[NPART];
+#pragma unroll
+                    for (int k = 0; k < NPART; ++k) { part0[k] = 0.0; part1[k] = 0.0; }
+                    anal_step<SPIN, R, false, 0>(S, X, r0, part0, 0);
+                    anal_step<SPIN, R, false, 1>(S, X, r0 + 2, part1, 0);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        red[(v * G + s) * 33 + lane] = make_double2(part0[2 * v], part0[2 * v + 1]);
+                        red[(v * G + s + 1) * 33 + lane] = make_double2(part1[2 * v], part1[2 * v + 1]);
+                    }
+                }
+            } else {
 #pragma unroll 1
-            for (int s = 0; s < gcnt; s += 2) {
-                const double* r0 = rec + (size_t)(g0 + s) * 2;
-                const bool two = (s + 1 < gcnt);
-                double part0[NPART], part1[NPART];
+                for (int s = 0; s < gcnt; s += 2) {
+                    const double* r0 = rec + (size_t)(g0 + s) * 2;
+                    double part0[NPART], part1[NPART];
 #pragma unroll
-                for (int k = 0; k < NPART; ++k) { part0[k] = 0.0; part1[k] = 0.0; }
-                if (!any_act) {
-                    anal_step<SPIN, R, 0, 0>(S, X, r0, part0);
-                    if (two) anal_step<SPIN, R, 0, 1>(S, X, r0 + 2, part1);
-                    ring_flags<SPIN, R>(S, any_seek, any_act);
-                    continue;
-                }
-                if (any_seek) {
-                    anal_step<SPIN, R, 1, 0>(S, X, r0, part0);
-                    if (two) anal_step<SPIN, R, 1, 1>(S, X, r0 + 2, part1);
-                    ring_flags<SPIN, R>(S, any_seek, any_act);
-                } else {
-                    anal_step<SPIN, R, 2, 0>(S, X, r0, part0);
-                    if (two) anal_step<SPIN, R, 2, 1>(S, X, r0 + 2, part1);
-                }
-                if (wrote_from == G) wrote_from = s;
+                    for (int k = 0; k < NPART; ++k) { part0[k] = 0.0; part1[k] = 0.0; }
+                    anal_step<SPIN, R, true, 0>(S, X, r0, part0, lstart + t0 + s);
+                    if (s + 1 < gcnt) anal_step<SPIN, R, true, 1>(S, X, r0 + 2, part1, lstart + t0 + s + 1);
 #pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    red[(v * G + s) * 33 + lane] = make_double2(part0[2 * v], part0[2 * v + 1]);
-                    red[(v * G + s + 1) * 33 + lane] = make_double2(part1[2 * v], part1[2 * v + 1]);
+                    for (int v = 0; v < NV; ++v) {
+                        red[(v * G + s) * 33 + lane] = make_double2(part0[2 * v], part0[2 * v + 1]);
+                        red[(v * G + s + 1) * 33 + lane] = make_double2(part1[2 * v], part1[2 * v + 1]);
+                    }
                 }
             }
-            if (wrote_from < G) {
-                __syncwarp();
-                // transpose-reduce: lane -> (step lq = lane % G, source slice = lane / G of 32/G slices)
+            __syncwarp();
+            // transpose-reduce: lane -> (step lq = lane % G, source slice = lane / G of 32/G slices)
+            {
                 constexpr int NSL = 32 / G, SL = 32 / NSL;
                 const int lq = lane % G, slice = lane / G;
-                double t[NPART];
+                double t[NPART], t2[NPART];
 #pragma unroll
-                for (int k = 0; k < NPART; ++k) t[k] = 0.0;
-                const bool mine = (lq >= wrote_from) && (lq < gcnt);
+                for (int k = 0; k < NPART; ++k) { t[k] = 0.0; t2[k] = 0.0; }
+                const bool mine = lq < gcnt;
                 if (mine) {
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
-#pragma unroll 4
-                        for (int k = 0; k < SL; ++k) {
+#pragma unroll
+                        for (int k = 0; k < SL; k += 2) {
                             const double2 q = red[(v * G + lq) * 33 + slice * SL + k];
+                            const double2 q2 = red[(v * G + lq) * 33 + slice * SL + k + 1];
                             t[2 * v] += q.x; t[2 * v + 1] += q.y;
+                            t2[2 * v] += q2.x; t2[2 * v + 1] += q2.y;
                         }
                     }
                 }
+#pragma unroll
+                for (int k = 0; k < NPART; ++k) t[k] += t2[k];
 #pragma unroll
                 for (int off = G; off < 32; off <<= 1)
 #pragma unroll
                     for (int q = 0; q < NPART; ++q) t[q] += __shfl_xor_sync(0xffffffffu, t[q], off);
                 if (slice == 0 && mine) {
-                    const long long k = abase + l0 + c * STEPS + g0 + lq;
+                    const long long k = abase + lstart + t0 + lq;
                     const double g = P.gamma[k];
                     if (SPIN == 0) {
                         if (t[0] != 0.0) atomicAdd(&P.alm_out0[k].x, g * t[0]);

@@ -65,6 +65,9 @@ struct pixsht_plan {
     DevBuf<double2> d_ad0, d_ad2;          // (alpha, delta) per (l,m)
     DevBuf<double> d_gamma0, d_gamma2;
     DevBuf<double> d_rec0, d_rec2;         // synthesis records, written per call by k_prep_synth
+    DevBuf<int> d_lact0, d_lact2;          // activation table: first contributing l per (m, ring pair), built lazily per spin family
+    DevBuf<double> d_st0, d_st2;           // recurrence state at l_act
+    bool have_seek0 = false, have_seek2 = false;
     DevBuf<double2> d_tw, d_phi0tw;
     // work buffers (grown on demand)
     DevBuf<double2> d_phase; int phase_ncomp = 0;
@@ -357,6 +360,7 @@ extern "C" void pixsht_plan_destroy(pixsht_plan* P)
     P->d_lg0_hi.release(); P->d_lg0_lo.release(); P->d_lg2_hi.release(); P->d_lg2_lo.release();
     P->d_ad0.release(); P->d_gamma0.release(); P->d_ad2.release(); P->d_gamma2.release(); P->d_rec0.release(); P->d_rec2.release();
     P->d_tw.release(); P->d_phi0tw.release(); P->d_phase.release();
+    P->d_lact0.release(); P->d_lact2.release(); P->d_st0.release(); P->d_st2.release();
     for (int c = 0; c < 3; ++c) { P->d_map[c].release(); P->d_alm[c].release(); P->d_alm64[c].release(); }
     for (auto& e : P->ev) if (e) cudaEventDestroy(e);
     if (P->own_stream) cudaStreamDestroy(P->own_stream);
@@ -367,6 +371,30 @@ extern "C" void pixsht_plan_destroy(pixsht_plan* P)
 // ---------------------------------------------------------------------------------------------------------------
 // stage launches
 // ---------------------------------------------------------------------------------------------------------------
+// The activation table of one spin family (legendre.cuh, k_seek_table): built on first use, kept for the plan's lifetime.
+static int ensure_seek(pixsht_plan* P, int spin, cudaStream_t st)
+{
+    bool& have = spin == 0 ? P->have_seek0 : P->have_seek2;
+    if (have) return PIXSHT_OK;
+    DevBuf<int>& lact = spin == 0 ? P->d_lact0 : P->d_lact2;
+    DevBuf<double>& stt = spin == 0 ? P->d_st0 : P->d_st2;
+    const size_t n = (size_t)(P->mmax + 1) * P->npairs;
+    if (lact.alloc(n) || stt.alloc(n * (spin == 0 ? 2 : 4))) return fail(PIXSHT_ERR_NOMEM, "activation table allocation failed");
+    SeekParams K;
+    memset(&K, 0, sizeof(K));
+    K.lmax = P->lmax; K.mmax = P->mmax; K.npairs = P->npairs; K.x = P->d_x.p;
+    K.lsh_hi = P->d_lsh_hi.p; K.lsh_lo = P->d_lsh_lo.p; K.lch_hi = P->d_lch_hi.p; K.lch_lo = P->d_lch_lo.p; K.mlim = P->d_mlim.p;
+    if (spin == 0) { K.lgpref_hi = P->d_lg0_hi.p; K.lgpref_lo = P->d_lg0_lo.p; K.ad = P->d_ad0.p; }
+    else { K.lgpref_hi = P->d_lg2_hi.p; K.lgpref_lo = P->d_lg2_lo.p; K.ad = P->d_ad2.p; }
+    K.lact = lact.p; K.st = stt.p;
+    dim3 grid((P->npairs + 127) / 128, P->mmax + 1);
+    if (spin == 0) PIXSHT_LAUNCH(k_seek_table<0>, grid, 128, 0, st, K);
+    else PIXSHT_LAUNCH(k_seek_table<2>, grid, 128, 0, st, K);
+    CU(cudaGetLastError());
+    have = true;
+    return PIXSHT_OK;
+}
+
 static LegParams leg_params(pixsht_plan* P, int spin, int R, int nm, const int* d_m_list, double2* phase, long long stride_c,
                             long long stride_m)
 {
@@ -374,10 +402,9 @@ static LegParams leg_params(pixsht_plan* P, int spin, int R, int nm, const int* 
     memset(&L, 0, sizeof(L));
     L.lmax = P->lmax; L.mmax = P->mmax; L.nm = nm; L.m_list = d_m_list;
     L.npairs = P->npairs; L.nchunks = (P->npairs + 32 * R - 1) / (32 * R);
-    L.x = P->d_x.p; L.lsh_hi = P->d_lsh_hi.p; L.lsh_lo = P->d_lsh_lo.p; L.lch_hi = P->d_lch_hi.p; L.lch_lo = P->d_lch_lo.p;
-    L.ringN = P->d_ringN.p; L.ringS = P->d_ringS.p; L.mlim = P->d_mlim.p;
-    if (spin == 0) { L.lgpref_hi = P->d_lg0_hi.p; L.lgpref_lo = P->d_lg0_lo.p; L.ad = P->d_ad0.p; L.gamma = P->d_gamma0.p; L.rec = P->d_rec0.p; }
-    else { L.lgpref_hi = P->d_lg2_hi.p; L.lgpref_lo = P->d_lg2_lo.p; L.ad = P->d_ad2.p; L.gamma = P->d_gamma2.p; L.rec = P->d_rec2.p; }
+    L.x = P->d_x.p; L.ringN = P->d_ringN.p; L.ringS = P->d_ringS.p;
+    if (spin == 0) { L.lact = P->d_lact0.p; L.st = P->d_st0.p; L.ad = P->d_ad0.p; L.gamma = P->d_gamma0.p; L.rec = P->d_rec0.p; }
+    else { L.lact = P->d_lact2.p; L.st = P->d_st2.p; L.ad = P->d_ad2.p; L.gamma = P->d_gamma2.p; L.rec = P->d_rec2.p; }
     L.phase = phase; L.stride_c = stride_c; L.stride_m = stride_m;
     return L;
 }
@@ -405,6 +432,7 @@ static int stage_alm2phase(pixsht_plan* P, int ncomp, const double2* const* alm,
 {
     const int prep_grid = P->sm_count > 0 ? P->sm_count * 8 : 256;
     if (ncomp == 1 || ncomp == 3) {
+        { int rc = ensure_seek(P, 0, st); if (rc) return rc; }
         if (P->d_rec0.n < (size_t)P->nalm * 4 && P->d_rec0.alloc((size_t)P->nalm * 4)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
         PIXSHT_LAUNCH(k_prep_synth<0>, prep_grid, 256, 0, st, P->nalm, P->lmax, P->d_ad0.p, P->d_gamma0.p, alm[0], alm[0], P->d_rec0.p);
         P->launches++;
@@ -413,6 +441,7 @@ static int stage_alm2phase(pixsht_plan* P, int ncomp, const double2* const* alm,
     }
     if (ncomp >= 2) {
         const int c0 = ncomp == 3 ? 1 : 0;
+        { int rc = ensure_seek(P, 2, st); if (rc) return rc; }
         if (P->d_rec2.n < (size_t)P->nalm * 6 && P->d_rec2.alloc((size_t)P->nalm * 6)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
         PIXSHT_LAUNCH(k_prep_synth<2>, prep_grid, 256, 0, st, P->nalm, P->lmax, P->d_ad2.p, P->d_gamma2.p, alm[c0], alm[c0 + 1], P->d_rec2.p);
         P->launches++;
@@ -427,12 +456,14 @@ static int stage_phase2alm(pixsht_plan* P, int ncomp, double2* phase, long long 
                            const int* d_m_list, double2* const* alm, cudaStream_t st)
 {
     if (ncomp == 1 || ncomp == 3) {
+        { int rc = ensure_seek(P, 0, st); if (rc) return rc; }
         LegParams L = leg_params(P, 0, P->R0, nm, d_m_list, phase, stride_c, stride_m);
         L.alm_out0 = alm[0];
         launch_anal<0>(P, P->R0, L, st);
     }
     if (ncomp >= 2) {
         const int c0 = ncomp == 3 ? 1 : 0;
+        { int rc = ensure_seek(P, 2, st); if (rc) return rc; }
         LegParams L = leg_params(P, 2, P->R2, nm, d_m_list, phase + (long long)c0 * stride_c, stride_c, stride_m);
         L.alm_out0 = alm[c0]; L.alm_out1 = alm[c0 + 1];
         launch_anal<2>(P, P->R2, L, st);

@@ -111,6 +111,7 @@ static inline double __shfl_xor_sync(unsigned, double v, int lanemask)
     memcpy(&v, &u, 8);
     return v;
 }
+static inline int __shfl_xor_sync(unsigned, int v, int lanemask) { return (int)(uint32_t)emu_xchg((uint64_t)(uint32_t)v, emu_lane() ^ lanemask); }
 static inline int __shfl_sync(unsigned, int v, int src) { return (int)emu_xchg((uint64_t)(uint32_t)v, src); }
 static inline double atomicAdd(double* addr, double v)
 {

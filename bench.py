@@ -388,7 +388,7 @@ def main():
             "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": wl["dtype"], "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": launches,
             "stages": stage, "roofline": roofline, "roofline_fft": roofline_fft, "fp32_fma_peak_tflops": fp32_peak,
-            "transforms_per_s": 2.0 * 1e3 / ms_dev, "plan": {k: plan_info.get(k) for k in ("npairs", "sm_count", "R0", "R2")}}
+            "transforms_per_s": 2.0 * 1e3 / ms_dev, "plan": {k: plan_info.get(k) for k in ("npairs", "sm_count", "R0", "R2", "R0a", "R2a")}}
     if e2e is not None:
         line["e2e"] = e2e
     if world == 1 and not args.no_cpu_baseline:

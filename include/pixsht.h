@@ -95,7 +95,8 @@ int pixsht_stage_map2phase(pixsht_plan *plan, int ncomp, const void *const *d_ma
 int64_t pixsht_nalm(int lmax, int mmax);
 int pixsht_plan_info(const pixsht_plan *plan, int32_t info[16]);
 /* info: [0] nphi [1] nrings [2] lmax [3] mmax [4] dtype [5] device [6] npairs (north/south folded ring pairs)
- *       [7] SM count [8] FFT length [9] kernels launched by the last execute [10..15] reserved */
+ *       [7] SM count [8] FFT length [9] kernels launched by the last execute [10..13] ring pairs per thread of the
+ *       spin-0 / spin-2 synthesis and spin-0 / spin-2 analysis kernels [14..15] reserved */
 int pixsht_plan_weights(const pixsht_plan *plan, double *weights /* nrings */, double *theta /* nrings */);
 const char *pixsht_last_error(void);
 const char *pixsht_version(void);

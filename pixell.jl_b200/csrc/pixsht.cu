@@ -52,7 +52,7 @@ struct pixsht_plan {
     double phi0 = 0;
     long long nalm = 0;
     int npairs = 0;
-    int R0 = 4, R2 = 2;           // ring pairs per thread in the spin-0 / spin-2 Legendre kernels
+    int R0 = 4, R2 = 4, R0a = 4, R2a = 4;   // ring pairs per thread in the spin-0 / spin-2 synthesis and analysis kernels
     // FFT
     int nfft = 0, nfac = 0, fac[FFT_MAXFAC] = {0}, fft_threads = 256;
     size_t fft_smem = 0;
@@ -156,8 +156,10 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     P->nalm = pixsht_nalm(lmax, mmax);
     P->h_theta = theta;
     {
-        int v = env_int("PIXSHT_R0", 4); P->R0 = (v == 1 || v == 2 || v == 4 || v == 8) ? v : 4;
-        v = env_int("PIXSHT_R2", 4); P->R2 = (v == 1 || v == 2 || v == 4) ? v : 4;
+        int v = env_int("PIXSHT_R0", 4); P->R0 = (v == 1 || v == 2 || v == 3 || v == 4 || v == 6 || v == 8) ? v : 4;
+        v = env_int("PIXSHT_R2", 2); P->R2 = (v == 1 || v == 2 || v == 3 || v == 4) ? v : 2;
+        v = env_int("PIXSHT_R0A", P->R0); P->R0a = (v == 1 || v == 2 || v == 3 || v == 4 || v == 6 || v == 8) ? v : 4;
+        v = env_int("PIXSHT_R2A", 4); P->R2a = (v == 1 || v == 2 || v == 3 || v == 4) ? v : 4;
     }
 
     // ---- north/south pairing (equatorial symmetry): pair rings whose cos(theta) are opposite ----
@@ -413,7 +415,8 @@ template <int SPIN>
 static void launch_synth(pixsht_plan* P, int R, const LegParams& L, cudaStream_t st)
 {
     const int grid = L.nm * L.nchunks;
-    void (*k)(const LegParams) = (R == 1) ? leg_synth<SPIN, 1> : (R == 2 ? leg_synth<SPIN, 2> : (R == 8 && SPIN == 0 ? leg_synth<0, 8> : leg_synth<SPIN, 4>));
+    void (*k)(const LegParams) = (R == 1) ? leg_synth<SPIN, 1> : (R == 2 ? leg_synth<SPIN, 2> : (R == 3 ? leg_synth<SPIN, 3> :
+                                 (R == 8 && SPIN == 0 ? leg_synth<0, 8> : (R == 6 && SPIN == 0 ? leg_synth<0, 6> : leg_synth<SPIN, 4>))));
     PIXSHT_LAUNCH(k, grid, LEG_NT, 0, st, L);
     P->launches++;
 }
@@ -421,7 +424,8 @@ template <int SPIN>
 static void launch_anal(pixsht_plan* P, int R, const LegParams& L, cudaStream_t st)
 {
     const int grid = L.nm * L.nchunks;
-    void (*k)(const LegParams) = (R == 1) ? leg_anal<SPIN, 1> : (R == 2 ? leg_anal<SPIN, 2> : (R == 8 && SPIN == 0 ? leg_anal<0, 8> : leg_anal<SPIN, 4>));
+    void (*k)(const LegParams) = (R == 1) ? leg_anal<SPIN, 1> : (R == 2 ? leg_anal<SPIN, 2> : (R == 3 ? leg_anal<SPIN, 3> :
+                                 (R == 8 && SPIN == 0 ? leg_anal<0, 8> : (R == 6 && SPIN == 0 ? leg_anal<0, 6> : leg_anal<SPIN, 4>))));
     PIXSHT_LAUNCH(k, grid, LEG_NT, 0, st, L);
     P->launches++;
 }
@@ -457,16 +461,16 @@ static int stage_phase2alm(pixsht_plan* P, int ncomp, double2* phase, long long 
 {
     if (ncomp == 1 || ncomp == 3) {
         { int rc = ensure_seek(P, 0, st); if (rc) return rc; }
-        LegParams L = leg_params(P, 0, P->R0, nm, d_m_list, phase, stride_c, stride_m);
+        LegParams L = leg_params(P, 0, P->R0a, nm, d_m_list, phase, stride_c, stride_m);
         L.alm_out0 = alm[0];
-        launch_anal<0>(P, P->R0, L, st);
+        launch_anal<0>(P, P->R0a, L, st);
     }
     if (ncomp >= 2) {
         const int c0 = ncomp == 3 ? 1 : 0;
         { int rc = ensure_seek(P, 2, st); if (rc) return rc; }
-        LegParams L = leg_params(P, 2, P->R2, nm, d_m_list, phase + (long long)c0 * stride_c, stride_c, stride_m);
+        LegParams L = leg_params(P, 2, P->R2a, nm, d_m_list, phase + (long long)c0 * stride_c, stride_c, stride_m);
         L.alm_out0 = alm[c0]; L.alm_out1 = alm[c0 + 1];
-        launch_anal<2>(P, P->R2, L, st);
+        launch_anal<2>(P, P->R2a, L, st);
     }
     CU(cudaGetLastError());
     return PIXSHT_OK;
@@ -672,7 +676,7 @@ extern "C" int pixsht_plan_info(const pixsht_plan* P, int32_t info[16])
     if (!P || !info) return fail(PIXSHT_ERR_ARG, "null argument");
     for (int i = 0; i < 16; ++i) info[i] = 0;
     info[0] = P->nphi; info[1] = P->nrings; info[2] = P->lmax; info[3] = P->mmax; info[4] = P->dtype; info[5] = P->device;
-    info[6] = P->npairs; info[7] = P->sm_count; info[8] = P->nfft; info[9] = P->launches; info[10] = P->R0; info[11] = P->R2;
+    info[6] = P->npairs; info[7] = P->sm_count; info[8] = P->nfft; info[9] = P->launches; info[10] = P->R0; info[11] = P->R2; info[12] = P->R0a; info[13] = P->R2a;
     return PIXSHT_OK;
 }
 

@@ -1,0 +1,164 @@
+# PixellB200.jl -- Julia host side of the B200 SHT engine: Pixell.jl's map2alm / alm2map method table
+# (src/transforms.jl:88-265 of simonsobs/Pixell.jl v0.2.9) on top of the C ABI of libpixsht.so (include/pixsht.h).
+#
+# NOT EXECUTED IN THE BUILD IMAGE (no Julia there, SURVEY.md F12); kept thin enough to be checked by inspection: every
+# method only (1) derives the ring geometry from the WCS exactly as the reference does, (2) `ccall`s one C function
+# with the caller's own arrays, (3) wraps the result in the reference's return type.  The Python mirror
+# pixell.jl_b200/pixsht/transforms.py is the same logic, and that one is exercised by the test-suite.
+#
+# Usage inside Pixell (see INTEGRATION.md): `include("PixellB200.jl"); using .PixellB200` after `using Pixell`; the
+# methods below are more specific than nothing in Pixell -- they REPLACE the libsharp-backed ones, so load this file
+# instead of src/transforms.jl, or call `PixellB200.map2alm` / `PixellB200.alm2map` explicitly.
+module PixellB200
+
+using Pixell: Enmap, getwcs, pix2sky, slice_geometry
+import Healpix: Alm
+
+const libpixsht = get(ENV, "PIXSHT_LIB", joinpath(@__DIR__, "..", "lib", "libpixsht.so"))
+
+const PIXSHT_F64, PIXSHT_F32 = Cint(0), Cint(1)
+const PIXSHT_MAP2ALM, PIXSHT_ALM2MAP = Cint(0), Cint(1)
+const PIXSHT_HOST = Cint(0)
+
+# mirrors `struct pixsht_geom` of include/pixsht.h (field order and widths matter)
+struct PixshtGeom
+    nphi::Int32
+    nrings_total::Int32
+    ring_first::Int32
+    nrings::Int32
+    nx::Int32
+    flipx::Int32
+    flipy::Int32
+    reserved::Int32
+    phi0::Float64
+end
+
+struct PixshtError <: Exception
+    code::Int
+    msg::String
+end
+Base.showerror(io::IO, e::PixshtError) = print(io, "pixsht error ", e.code, ": ", e.msg)
+
+last_error() = unsafe_string(ccall((:pixsht_last_error, libpixsht), Cstring, ()))
+check(rc::Integer) = rc == 0 ? nothing : throw(PixshtError(rc, last_error()))
+
+# ---- ring bookkeeping: the reference's own helpers (src/transforms.jl:3-30,85) do the work -----------------------
+import Pixell: fullringsize, fullringnum, getlmax, first_last_rings_in_fullsky, get_flip_slices
+
+"""Describe how an (nx, ny) map with `wcs` sits on the full-sky CC ring grid (pixsht_geom).  Same derivation as
+make_cc_geom_info (src/transforms.jl:33-46): flip slices -> sliced WCS -> ring sub-range and phi0.  The reference then
+flips/pads the map on the host (create_sht_band, :66-82); here the flips/padding are two flags and `nx`, applied inside
+the FFT kernels, so the caller's array is passed untouched."""
+function sht_geom(shape, wcs0)
+    fx, fy = get_flip_slices(shape, wcs0)
+    _, wcs = slice_geometry(shape, wcs0, fx, fy, shape[3:end])
+    subinds = first_last_rings_in_fullsky(shape, wcs)
+    @assert first(subinds) ≤ last(subinds)                 # vertical angle must be increasing (:38)
+    @assert length(subinds) == shape[2]
+    phi0 = pix2sky(shape, wcs, 1, 2)[1]                    # (:41)
+    PixshtGeom(fullringsize(wcs), fullringnum(wcs), first(subinds) - 1, shape[2], shape[1],
+               step(fx) < 0, step(fy) < 0, 0, phi0)
+end
+
+# ---- plans: one per (geometry, lmax, mmax, eltype); finalizer frees the device tables -------------------------------
+mutable struct Plan
+    ptr::Ptr{Cvoid}
+    nalm::Int
+end
+
+const PLANS = Dict{Any,Plan}()
+const PLAN_LOCK = ReentrantLock()
+
+function plan_for(shape, wcs, lmax::Int, mmax::Int, ::Type{T}) where {T<:Union{Float32,Float64}}
+    g = sht_geom(shape, wcs)
+    key = (g, lmax, mmax, T)
+    lock(PLAN_LOCK) do
+        get!(PLANS, key) do
+            out = Ref{Ptr{Cvoid}}(C_NULL)
+            check(ccall((:pixsht_plan_create, libpixsht), Cint,
+                        (Ref{Ptr{Cvoid}}, Ref{PixshtGeom}, Cint, Cint, Cint, Cint),
+                        out, g, lmax, mmax, T === Float64 ? PIXSHT_F64 : PIXSHT_F32, 0))
+            p = Plan(out[], Int(ccall((:pixsht_nalm, libpixsht), Int64, (Cint, Cint), lmax, mmax)))
+            finalizer(p) do q   # thread-safe in the library; tolerates a torn-down CUDA context
+                ccall((:pixsht_plan_destroy, libpixsht), Cvoid, (Ptr{Cvoid},), q.ptr)
+            end
+            p
+        end
+    end
+end
+
+function execute!(p::Plan, dir::Cint, alms::Vector{<:AbstractVector}, maps::Vector{<:AbstractArray})
+    ncomp = length(alms)
+    GC.@preserve alms maps begin
+        aptr = Ptr{Cvoid}[pointer(a) for a in alms]
+        mptr = Ptr{Cvoid}[pointer(m) for m in maps]
+        check(ccall((:pixsht_execute, libpixsht), Cint,
+                    (Ptr{Cvoid}, Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Cint),
+                    p.ptr, dir, ncomp, aptr, mptr, PIXSHT_HOST))
+    end
+end
+
+compute_type(::Type{Float32}) = Float32
+compute_type(::Type) = Float64            # the reference promotes everything to Float64 (src/transforms.jl:71)
+
+dense(m::AbstractArray{T}, ::Type{T}) where {T} = (m isa Array && true) ? m : Array(m)
+dense(m::AbstractArray, ::Type{T}) where {T} = Array{T}(m)
+
+# ---- map2alm: src/transforms.jl:88-165 -------------------------------------------------------------------------
+function _map2alm(maps::Vector, wcs, shape; lmax=nothing, mmax=lmax)
+    if isnothing(lmax)
+        lmax = getlmax(wcs); mmax = lmax
+    end
+    T = compute_type(eltype(maps[1]))
+    p = plan_for(shape, wcs, lmax, mmax, T)
+    planes = [dense(m, T) for m in maps]
+    alms = [zeros(Complex{T}, p.nalm) for _ in planes]
+    execute!(p, PIXSHT_MAP2ALM, alms, planes)
+    [Alm(lmax, mmax, ComplexF64.(a)) for a in alms]
+end
+
+map2alm(m::Enmap{T,2}; lmax=nothing, mmax=lmax) where {T} =
+    _map2alm([parent(m)], getwcs(m), size(m); lmax=lmax, mmax=mmax)[1]
+
+function map2alm(ms::NTuple{2,Enmap{T,2}}; lmax=nothing, mmax=lmax) where {T}
+    e, b = _map2alm([parent(ms[1]), parent(ms[2])], getwcs(ms[1]), size(ms[1]); lmax=lmax, mmax=mmax)
+    (e, b)
+end
+
+function map2alm(ms::NTuple{3,Enmap{T,2}}; lmax=nothing, mmax=lmax) where {T}
+    t, e, b = _map2alm([parent(m) for m in ms], getwcs(ms[1]), size(ms[1]); lmax=lmax, mmax=mmax)
+    (t, e, b)
+end
+
+function map2alm(m::Enmap{T,3}; lmax=nothing, mmax=lmax) where {T}
+    ncomp = size(m, 3)
+    1 <= ncomp <= 3 || throw(ArgumentError("SHTs require shape (nx,ny,ncomp) with 1 ≤ ncomp ≤ 3, for I, QU, and IQU."))
+    planes = [view(parent(m), :, :, c) for c in 1:ncomp]   # contiguous column-major planes: no copy for Array storage
+    out = _map2alm(planes, getwcs(m), size(m)[1:2]; lmax=lmax, mmax=mmax)
+    ncomp == 1 ? out[1] : Tuple(out)
+end
+
+# ---- alm2map: src/transforms.jl:206-265 (return types of SURVEY.md F11 preserved) -------------------------------------
+function _alm2map(alms::Vector{<:Alm}, shape, wcs)
+    lmax, mmax = alms[1].lmax, alms[1].mmax
+    p = plan_for(shape[1:2], wcs, lmax, mmax, Float64)
+    vecs = [ComplexF64.(a.alm) for a in alms]
+    maps = [zeros(Float64, shape[1], shape[2]) for _ in alms]
+    execute!(p, PIXSHT_ALM2MAP, vecs, maps)
+    [Enmap(m, wcs) for m in maps]
+end
+
+alm2map(alm::Alm, shape, wcs) = _alm2map([alm], shape, wcs)[1]
+alm2map(alms::NTuple{2,<:Alm}, shape, wcs) = _alm2map(collect(alms), shape, wcs)            # Vector of 2 Enmaps (:251)
+alm2map(alms::NTuple{3,<:Alm}, shape, wcs) = Tuple(_alm2map(collect(alms), shape, wcs))     # Tuple (:254-255)
+function alm2map(alms::Vector{<:Alm}, shape, wcs)
+    n = length(alms)
+    n == 1 && return alm2map(alms[1], shape, wcs)
+    n == 2 && return alm2map((alms[1], alms[2]), shape, wcs)
+    n == 3 && return alm2map((alms[1], alms[2], alms[3]), shape, wcs)
+    throw(ArgumentError("1, 2 or 3 Alm are supported"))
+end
+
+export map2alm, alm2map
+
+end # module

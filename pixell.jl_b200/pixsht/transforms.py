@@ -60,7 +60,7 @@ class Plan:
     def info(self):
         v = (ctypes.c_int32 * 16)()
         self.lib.check(self.lib.lib.pixsht_plan_info(self.handle, v))
-        keys = ["nphi", "nrings", "lmax", "mmax", "dtype", "device", "npairs", "sm_count", "nfft", "launches", "R0", "R2"]
+        keys = ["nphi", "nrings", "lmax", "mmax", "dtype", "device", "npairs", "sm_count", "nfft", "launches", "R0", "R2", "R0a", "R2a"]
         return dict(zip(keys, list(v)))
 
     def weights(self):

@@ -316,7 +316,9 @@ def main():
         t = torch.tensor([leg_ms, fft_ms, a2a_ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         leg_ms, fft_ms, a2a_ms = [float(x) for x in t.tolist()]
-        stage = {"legendre_ms": leg_ms, "fft_ms": fft_ms, "exchange_ms": a2a_ms}
+        stage = {"legendre_ms": leg_ms, "fft_ms": fft_ms, "exchange_ms": a2a_ms,
+                 "exchange": "fused: Legendre kernels load/store phase rows in the owning GPU's memory over NVLink; exchange_ms is the "
+                             "stage-ordering barrier (includes waiting for the slowest rank)"}
         launches = 8 * args.steps   # 2 Legendre + 1 FFT kernels per direction of our own per rank (+ torch pack/unpack copies)
         e2e = None
         if not args.no_e2e:
@@ -356,6 +358,7 @@ def main():
         nrings = band.nrings
         plan_info = {"npairs": math.ceil(nrings / 2), "sm_count": None}
         host_maps = host_alms = None
+        sht.close()
 
     if rank != 0:
         if dist is not None:

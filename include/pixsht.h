@@ -75,21 +75,32 @@ int pixsht_plan_set_stream(pixsht_plan *plan, void *stream, int use_caller_strea
  * [0] h2d copy, [1] Legendre stage, [2] FFT stage, [3] d2h copy, [4] whole call (host wall clock), [5..7] reserved */
 int pixsht_get_timings(const pixsht_plan *plan, double ms[8]);
 
-/* ---- stage API for the m-sharded multi-GPU pipeline (device pointers, asynchronous on `stream`) ------------ */
-/* phase buffers are complex double, element (c, row, ring) at ((row*ncomp + c)*nrings_buf + ring): one row per m,
- * components interleaved per row, so that the per-destination blocks of the all-to-all are contiguous row ranges.
- * nrings_buf = plan nrings for the Legendre stages, ring_count for the FFT stages.                                */
-/* Legendre stage over the m values m_list[0..nm) (device array of int32, or NULL for m = 0..nm-1): row = position in m_list. */
+/* ---- stage API for the m-sharded multi-GPU pipeline (device pointers, asynchronous on `stream`) ------------
+ * Phase rows: one contiguous row of MP = pixsht_phase_row_len(plan) complex doubles per (ring, component), element
+ * (ring_local, c, m) at ((ring_local*ncomp + c)*MP + m).  A rank's phase buffer holds the rows of ITS slab of rings for
+ * ALL m.  The Legendre stages, which run on a rank's own m values over all rings, reach every ring's row through a
+ * device array of nrings pointers (d_ring_ptrs[ring] -> element (ring, 0, 0)); rows of rings owned by another GPU are
+ * addresses inside that GPU's buffer (pixsht_shared_open), so the phase transpose of SURVEY.md 8(e) happens inside the
+ * Legendre kernels' own loads/stores over NVLink and there is no separate exchange pass. */
+int64_t pixsht_phase_row_len(const pixsht_plan *plan);
+/* Legendre stage over the m values m_list[0..nm) (device array of int32, or NULL for m = 0..nm-1). */
 int pixsht_stage_alm2phase(pixsht_plan *plan, int ncomp, const void *const *d_alms, int nm, const int32_t *d_m_list,
-                           void *d_phase, void *stream);
-int pixsht_stage_phase2alm(pixsht_plan *plan, int ncomp, const void *d_phase, int nm, const int32_t *d_m_list,
+                           void *const *d_ring_ptrs, void *stream);
+int pixsht_stage_phase2alm(pixsht_plan *plan, int ncomp, void *const *d_ring_ptrs, int nm, const int32_t *d_m_list,
                            void *const *d_alms, void *stream);
-/* FFT stage over band rings [ring_begin, ring_begin+ring_count): d_phase holds all m = 0..mmax for those rings,
- * row of m = d_m_row[m] (or m when NULL), ring index local to the range; d_maps are the full caller-layout maps. */
-int pixsht_stage_phase2map(pixsht_plan *plan, int ncomp, const void *d_phase, const int32_t *d_m_row, int ring_begin,
-                           int ring_count, void *const *d_maps, void *stream);
-int pixsht_stage_map2phase(pixsht_plan *plan, int ncomp, const void *const *d_maps, const int32_t *d_m_row, int ring_begin,
-                           int ring_count, void *d_phase, void *stream);
+/* FFT stage over band rings [ring_begin, ring_begin+ring_count): d_phase holds the rows of exactly those rings;
+ * d_maps are the full caller-layout maps (only the rows of those rings are touched). */
+int pixsht_stage_phase2map(pixsht_plan *plan, int ncomp, const void *d_phase, int ring_begin, int ring_count,
+                           void *const *d_maps, void *stream);
+int pixsht_stage_map2phase(pixsht_plan *plan, int ncomp, const void *const *d_maps, int ring_begin, int ring_count,
+                           void *d_phase, void *stream);
+/* Peer-visible device memory for the phase buffers (CUDA IPC between the one-process-per-GPU ranks of a node):
+ * alloc on the owner and export a 64-byte handle; open maps a peer's buffer into this process (peer access over
+ * NVLink is enabled lazily); close unmaps an opened buffer; free releases an owned one. */
+int pixsht_shared_alloc(int device, size_t bytes, void **dptr, unsigned char handle[64]);
+int pixsht_shared_open(int device, const unsigned char handle[64], void **dptr);
+int pixsht_shared_close(void *dptr);
+int pixsht_shared_free(void *dptr);
 
 /* ---- introspection -------------------------------------------------------------------------------------- */
 int64_t pixsht_nalm(int lmax, int mmax);

@@ -1,9 +1,19 @@
 // fft.cuh -- the ring-FFT stage (phase <-> map), hand-written for sm_100a.  HBM bound: one read of
-// the phase row set and one write of the ring (or the reverse) per ring.
+// the phase row and one write of the ring (or the reverse) per ring and component.
+//
+// Phase layout: element (ring, component, m) at ((ring_local * ncomp + c) * MP + m) -- one contiguous row of MP >= mmax+1
+// complex doubles per (ring, component), so every global access of this stage is a coalesced row access (the Legendre
+// kernels, which are FP64 bound and have the memory system idle, do the strided side of the transpose).
 //
 // One CTA transforms one ring of one component entirely in shared memory: the real ring of nphi samples is handled
-// as a complex FFT of length n = nphi/2 (even/odd packing) done in place as a mixed-radix decimation-in-time
-// transform (radices 4/2/3/5 + generic odd primes) on digit-reversed input.  Fused into the same kernel:
+// as a complex FFT of length n = nphi/2 (even/odd packing), in place, mixed radix (2/3/4/5 + generic odd primes <= 64):
+//   synthesis (phase -> map): natural-order input, decimation-in-frequency passes, digit-reversed output that is
+//                             un-permuted by the coalesced store;
+//   analysis  (map -> phase): digit-reversed scatter on load, decimation-in-time passes, natural-order output.
+// The two are exact transposes of each other, so one pass geometry and one permutation table serve both.  Odd radices
+// come first in the pass order: the small-stride passes then have odd strides (no shared-memory bank conflicts), and the
+// even radices run at strides >= 8 elements where consecutive threads touch consecutive addresses.
+// Fused into the same kernels:
 //   - the e^{+-i m phi0} rotation and the quadrature weight (libsharp2's ring helper),
 //   - m >= nphi/2 aliasing exactly as the direct sum prescribes (golden test at lmax = 3 nphi),
 //   - the band bookkeeping of create_sht_band (src/transforms.jl:66-82): x/y flips and zero padding of partial-sky
@@ -15,18 +25,21 @@ namespace pixsht {
 
 constexpr int FFT_MAXFAC = 24;
 constexpr int FFT_MAXRADIX = 64;
+constexpr int FFT_MAXTHREADS = 768;
 
 struct FftParams {
     int nphi, n;                // ring length, complex FFT length (nphi/2)
     int nfac;
-    int fac[FFT_MAXFAC];        // radices in pass order (pass t works on sub-transforms of length L_t = prod_{u<t} fac[u])
+    int fac[FFT_MAXFAC];        // radices in DIT pass order (pass t works on sub-transforms of length L_t = prod_{u<t} fac[u])
+    unsigned magic[FFT_MAXFAC]; // floor(2^32 / L_t) + 1: b / L_t == umulhi(b, magic) for b < 2^16
     const double2* tw;          // [nphi] exp(-2 pi i t / nphi)
     const double2* phi0tw;      // [mmax+1] exp(+i m phi0)
     const double* wgt;          // [nrings] quadrature weight per band ring
+    const unsigned short* perm; // [n] position of natural index j in the permuted buffer
     int mmax;
-    const int* m_row;           // phase row of m (nullptr: row = m)
-    double2* phase;             // element (c,row,ringlocal) at c*stride_c + row*stride_m + ringlocal
-    long long stride_c, stride_m;
+    double2* phase;             // this launch's rows: (ringlocal, c, m) at ((ringlocal*ncomp + c)*MP + m)
+    long long MP;
+    int ncomp;
     int ring_begin, ring_count; // band rings handled by this launch; ringlocal = ring - ring_begin
     int nx, ny, flipx, flipy;   // caller's map layout (column-major nx x ny), see pixsht_geom
     void* maps[3];
@@ -42,18 +55,19 @@ template <class T, int SIGN> __device__ __forceinline__ cpx<T> cmuli(cpx<T> a) {
 
 // exp(SIGN * 2 pi i t / nphi) from the forward table
 template <class T, int SIGN>
-__device__ __forceinline__ cpx<T> twid(const FftParams& P, long long t)
+__device__ __forceinline__ cpx<T> twid(const FftParams& P, int t)
 {
     const double2 w = P.tw[t];
     cpx<T> r; r.x = (T)w.x; r.y = (T)(SIGN < 0 ? w.y : -w.y);
     return r;
 }
 
-__device__ __forceinline__ int digit_reverse(const FftParams& P, int i)
+// host side: position of natural index i in the permuted buffer (mixed-radix digit reversal for the DIT pass order fac[])
+inline int fft_digit_reverse(const int* fac, int nfac, int n, int i)
 {
-    int pos = 0, L = P.n;
-    for (int t = P.nfac - 1; t >= 0; --t) {
-        const int q = P.fac[t];
+    int pos = 0, L = n;
+    for (int t = nfac - 1; t >= 0; --t) {
+        const int q = fac[t];
         L /= q;
         pos += (i % q) * L;
         i /= q;
@@ -61,96 +75,132 @@ __device__ __forceinline__ int digit_reverse(const FftParams& P, int i)
     return pos;
 }
 
-// in-place mixed-radix DIT passes over buf[0..n) (digit-reversed input, natural-order output). SIGN=-1 forward.
+// q-point DFT of a[0..q) in registers, SIGN = -1 forward / +1 inverse
 template <class T, int SIGN>
+__device__ __forceinline__ void dft2(cpx<T>* a) { const cpx<T> t = a[0]; a[0] = cadd(t, a[1]); a[1] = csub(t, a[1]); }
+template <class T, int SIGN>
+__device__ __forceinline__ void dft3(cpx<T>* a)
+{
+    const T c = (T)-0.5, s = (T)(SIGN * 0.86602540378443864676);
+    const cpx<T> sum = cadd(a[1], a[2]), dif = csub(a[1], a[2]);
+    cpx<T> m1; m1.x = a[0].x + c * sum.x; m1.y = a[0].y + c * sum.y;
+    cpx<T> m2; m2.x = -s * dif.y; m2.y = s * dif.x;      // i*s*dif
+    a[0] = cadd(a[0], sum); a[1] = cadd(m1, m2); a[2] = csub(m1, m2);
+}
+template <class T, int SIGN>
+__device__ __forceinline__ void dft4(cpx<T>* a)
+{
+    const cpx<T> s02 = cadd(a[0], a[2]), d02 = csub(a[0], a[2]), s13 = cadd(a[1], a[3]), d13 = cmuli<T, SIGN>(csub(a[1], a[3]));
+    a[0] = cadd(s02, s13); a[2] = csub(s02, s13);
+    a[1] = cadd(d02, d13); a[3] = csub(d02, d13);
+}
+template <class T, int SIGN>
+__device__ __forceinline__ void dft5(cpx<T>* a)
+{
+    const T c1 = (T)0.30901699437494742410, c2 = (T)-0.80901699437494742410;
+    const T s1 = (T)(SIGN * 0.95105651629515357212), s2 = (T)(SIGN * 0.58778525229247312917);
+    const cpx<T> p14 = cadd(a[1], a[4]), m14 = csub(a[1], a[4]), p23 = cadd(a[2], a[3]), m23 = csub(a[2], a[3]);
+    cpx<T> r1; r1.x = a[0].x + c1 * p14.x + c2 * p23.x; r1.y = a[0].y + c1 * p14.y + c2 * p23.y;
+    cpx<T> r2; r2.x = a[0].x + c2 * p14.x + c1 * p23.x; r2.y = a[0].y + c2 * p14.y + c1 * p23.y;
+    cpx<T> i1; i1.x = -(s1 * m14.y + s2 * m23.y); i1.y = s1 * m14.x + s2 * m23.x;   // i*(s1 m14 + s2 m23)
+    cpx<T> i2; i2.x = -(s2 * m14.y - s1 * m23.y); i2.y = s2 * m14.x - s1 * m23.x;   // i*(s2 m14 - s1 m23)
+    a[0].x = a[0].x + p14.x + p23.x; a[0].y = a[0].y + p14.y + p23.y;
+    a[1] = cadd(r1, i1); a[4] = csub(r1, i1);
+    a[2] = cadd(r2, i2); a[3] = csub(r2, i2);
+}
+
+// one butterfly of a radix-Q pass at element pointer e (stride L), twiddle exponent base tk = kk * tstep.
+// DIF == false: decimation in time (twiddle, then DFT);  DIF == true: the transpose (DFT, then twiddle).
+template <class T, int SIGN, int Q, bool DIF>
+__device__ __forceinline__ void butterfly(const FftParams& P, cpx<T>* e, int L, int tk)
+{
+    cpx<T> a[Q];
+#pragma unroll
+    for (int j = 0; j < Q; ++j) a[j] = e[(size_t)j * L];
+    cpx<T> w[5];
+    if (tk) {
+        w[1] = twid<T, SIGN>(P, tk);
+        if constexpr (Q > 2) w[2] = twid<T, SIGN>(P, 2 * tk);
+        if constexpr (Q > 3) w[3] = cmul(w[1], w[2]);
+        if constexpr (Q > 4) w[4] = cmul(w[2], w[2]);
+    }
+    if (!DIF && tk) {
+#pragma unroll
+        for (int j = 1; j < Q; ++j) a[j] = cmul(a[j], w[j]);
+    }
+    if constexpr (Q == 2) dft2<T, SIGN>(a);
+    else if constexpr (Q == 3) dft3<T, SIGN>(a);
+    else if constexpr (Q == 4) dft4<T, SIGN>(a);
+    else dft5<T, SIGN>(a);
+    if (DIF && tk) {
+#pragma unroll
+        for (int j = 1; j < Q; ++j) a[j] = cmul(a[j], w[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < Q; ++j) e[(size_t)j * L] = a[j];
+}
+
+// generic (odd prime) radix, O(q^2)
+template <class T, int SIGN, bool DIF>
+__device__ void butterfly_generic(const FftParams& P, cpx<T>* e, int q, int L, int tk)
+{
+    cpx<T> a[FFT_MAXRADIX];
+    for (int j = 0; j < q; ++j) {
+        cpx<T> v = e[(size_t)j * L];
+        if (!DIF && tk && j) v = cmul(v, twid<T, SIGN>(P, j * tk));
+        a[j] = v;
+    }
+    const int qstep = P.nphi / q;
+    for (int u = 0; u < q; ++u) {
+        cpx<T> s = a[0];
+        for (int j = 1; j < q; ++j) s = cadd(s, cmul(a[j], twid<T, SIGN>(P, ((j * u) % q) * qstep)));
+        if (DIF && tk && u) s = cmul(s, twid<T, SIGN>(P, u * tk));
+        e[(size_t)u * L] = s;
+    }
+}
+
+// in-place mixed-radix passes over buf[0..n).  DIF == false: digit-reversed input -> natural output (pass order 0..nfac-1);
+// DIF == true: natural input -> digit-reversed output (pass order nfac-1..0).  SIGN = -1 forward.
+template <class T, int SIGN, bool DIF>
 __device__ void fft_passes(const FftParams& P, cpx<T>* buf)
 {
     const int n = P.n;
     int L = 1;
-    for (int t = 0; t < P.nfac; ++t) {
+    if (DIF) L = n;
+    for (int tt = 0; tt < P.nfac; ++tt) {
+        const int t = DIF ? (P.nfac - 1 - tt) : tt;
         const int q = P.fac[t];
+        if (DIF) L /= q;
         const int nb = n / q;
-        const long long tstep = P.nphi / (q * L);   // W_{qL}^{a} = tw[a * tstep]
+        const int tstep = P.nphi / (q * L);   // W_{qL}^{a} = tw[a * tstep]
+        const unsigned magic = P.magic[t];
         for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-            const int kk = b % L, g = b / L;
+            const int g = (L == 1) ? b : (int)__umulhi((unsigned)b, magic);
+            const int kk = b - g * L;
             cpx<T>* e = buf + (size_t)g * q * L + kk;
-            if (q == 2) {
-                cpx<T> a0 = e[0], a1 = e[L];
-                if (kk) a1 = cmul(a1, twid<T, SIGN>(P, (long long)kk * tstep));
-                e[0] = cadd(a0, a1); e[L] = csub(a0, a1);
-            } else if (q == 4) {
-                cpx<T> a0 = e[0], a1 = e[L], a2 = e[2 * L], a3 = e[3 * L];
-                if (kk) {
-                    a1 = cmul(a1, twid<T, SIGN>(P, (long long)kk * tstep));
-                    a2 = cmul(a2, twid<T, SIGN>(P, 2LL * kk * tstep));
-                    a3 = cmul(a3, twid<T, SIGN>(P, 3LL * kk * tstep));
-                }
-                const cpx<T> s02 = cadd(a0, a2), d02 = csub(a0, a2), s13 = cadd(a1, a3), d13 = cmuli<T, SIGN>(csub(a1, a3));
-                e[0] = cadd(s02, s13); e[2 * L] = csub(s02, s13);
-                e[L] = cadd(d02, d13); e[3 * L] = csub(d02, d13);
-            } else if (q == 3) {
-                cpx<T> a0 = e[0], a1 = e[L], a2 = e[2 * L];
-                if (kk) {
-                    a1 = cmul(a1, twid<T, SIGN>(P, (long long)kk * tstep));
-                    a2 = cmul(a2, twid<T, SIGN>(P, 2LL * kk * tstep));
-                }
-                const T c = (T)-0.5, s = (T)(SIGN * 0.86602540378443864676);
-                const cpx<T> sum = cadd(a1, a2), dif = csub(a1, a2);
-                cpx<T> m1; m1.x = a0.x + c * sum.x; m1.y = a0.y + c * sum.y;
-                cpx<T> m2; m2.x = -s * dif.y; m2.y = s * dif.x;      // i*s*dif
-                e[0] = cadd(a0, sum); e[L] = cadd(m1, m2); e[2 * L] = csub(m1, m2);
-            } else if (q == 5) {
-                cpx<T> a0 = e[0], a1 = e[L], a2 = e[2 * L], a3 = e[3 * L], a4 = e[4 * L];
-                if (kk) {
-                    a1 = cmul(a1, twid<T, SIGN>(P, (long long)kk * tstep));
-                    a2 = cmul(a2, twid<T, SIGN>(P, 2LL * kk * tstep));
-                    a3 = cmul(a3, twid<T, SIGN>(P, 3LL * kk * tstep));
-                    a4 = cmul(a4, twid<T, SIGN>(P, 4LL * kk * tstep));
-                }
-                const T c1 = (T)0.30901699437494742410, c2 = (T)-0.80901699437494742410;
-                const T s1 = (T)(SIGN * 0.95105651629515357212), s2 = (T)(SIGN * 0.58778525229247312917);
-                const cpx<T> p14 = cadd(a1, a4), m14 = csub(a1, a4), p23 = cadd(a2, a3), m23 = csub(a2, a3);
-                cpx<T> r1; r1.x = a0.x + c1 * p14.x + c2 * p23.x; r1.y = a0.y + c1 * p14.y + c2 * p23.y;
-                cpx<T> r2; r2.x = a0.x + c2 * p14.x + c1 * p23.x; r2.y = a0.y + c2 * p14.y + c1 * p23.y;
-                cpx<T> i1; i1.x = -(s1 * m14.y + s2 * m23.y); i1.y = s1 * m14.x + s2 * m23.x;   // i*(s1 m14 + s2 m23)
-                cpx<T> i2; i2.x = -(s2 * m14.y - s1 * m23.y); i2.y = s2 * m14.x - s1 * m23.x;   // i*(s2 m14 - s1 m23)
-                e[0].x = a0.x + p14.x + p23.x; e[0].y = a0.y + p14.y + p23.y;
-                e[L] = cadd(r1, i1); e[4 * L] = csub(r1, i1);
-                e[2 * L] = cadd(r2, i2); e[3 * L] = csub(r2, i2);
-            } else {
-                // generic (odd prime) radix, O(q^2)
-                cpx<T> a[FFT_MAXRADIX];
-                for (int j = 0; j < q; ++j) {
-                    cpx<T> v = e[(size_t)j * L];
-                    if (kk && j) v = cmul(v, twid<T, SIGN>(P, (long long)j * kk * tstep));
-                    a[j] = v;
-                }
-                const long long qstep = P.nphi / q;
-                for (int u = 0; u < q; ++u) {
-                    cpx<T> s = a[0];
-                    for (int j = 1; j < q; ++j) s = cadd(s, cmul(a[j], twid<T, SIGN>(P, (long long)((j * u) % q) * qstep)));
-                    e[(size_t)u * L] = s;
-                }
-            }
+            const int tk = kk * tstep;
+            if (q == 4) butterfly<T, SIGN, 4, DIF>(P, e, L, tk);
+            else if (q == 3) butterfly<T, SIGN, 3, DIF>(P, e, L, tk);
+            else if (q == 5) butterfly<T, SIGN, 5, DIF>(P, e, L, tk);
+            else if (q == 2) butterfly<T, SIGN, 2, DIF>(P, e, L, tk);
+            else butterfly_generic<T, SIGN, DIF>(P, e, q, L, tk);
         }
-        L *= q;
+        if (!DIF) L *= q;
         __syncthreads();
     }
 }
 
-// aliased half-spectrum entry X[k], 0 <= k <= n, of ring `rl` (local index): sum over m == +-k (mod nphi) of the rotated phases
+// aliased half-spectrum entry X[k], 0 <= k <= n: sum over m == +-k (mod nphi) of the rotated phases (general mmax)
 template <class T>
-__device__ __forceinline__ cpx<T> load_X(const FftParams& P, const double2* ph, int k)
+__device__ __forceinline__ cpx<T> load_X(const FftParams& P, const double2* row, int k)
 {
     double sx = 0.0, sy = 0.0;
     for (int m = k; m <= P.mmax; m += P.nphi) {
-        const int row = P.m_row ? P.m_row[m] : m;
-        const double2 a = ph[(long long)row * P.stride_m], r = P.phi0tw[m];
+        const double2 a = row[m], r = P.phi0tw[m];
         sx += a.x * r.x - a.y * r.y; sy += a.x * r.y + a.y * r.x;
     }
     for (int m = P.nphi - k; m <= P.mmax; m += P.nphi) {
-        const int row = P.m_row ? P.m_row[m] : m;
-        const double2 a = ph[(long long)row * P.stride_m], r = P.phi0tw[m];
+        const double2 a = row[m], r = P.phi0tw[m];
         sx += a.x * r.x - a.y * r.y; sy -= a.x * r.y + a.y * r.x;
     }
     cpx<T> v; v.x = (T)sx; v.y = (T)sy;
@@ -159,41 +209,58 @@ __device__ __forceinline__ cpx<T> load_X(const FftParams& P, const double2* ph, 
 
 // phase -> map  (synthesis).  grid = (ring_count, ncomp)
 template <class T>
-__global__ void fft_phase2map(const FftParams P)
+__global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams P)
 {
     PIXSHT_DYN_SMEM(smem_raw);
-    cpx<T>* buf = reinterpret_cast<cpx<T>*>(smem_raw);
+    cpx<T>* buf = reinterpret_cast<cpx<T>*>(smem_raw);   // n + 1 entries
     const int rl = blockIdx.x, c = blockIdx.y, ring = P.ring_begin + rl;
     const int n = P.n;
-    const double2* ph = P.phase + (long long)c * P.stride_c + rl;
+    const double2* row = P.phase + ((long long)rl * P.ncomp + c) * P.MP;
 
-    // pre-processing: Z[k] = (X[k] + conj X[n-k]) + i (X[k] - conj X[n-k]) e^{+2 pi i k/nphi}, stored digit-reversed
+    // X[k], k = 0..n, natural order (coalesced row read)
+    if (P.mmax <= n) {
+        for (int k = threadIdx.x; k <= n; k += blockDim.x) {
+            cpx<T> v; v.x = (T)0; v.y = (T)0;
+            if (k <= P.mmax) {
+                const double2 a = row[k], r = P.phi0tw[k];
+                const double sx = a.x * r.x - a.y * r.y, sy = a.x * r.y + a.y * r.x;
+                if (k == n) { v.x = (T)(2.0 * sx); }          // m = nphi/2: the ring carries only the (doubled) real part
+                else { v.x = (T)sx; v.y = (T)sy; }
+            }
+            buf[k] = v;
+        }
+    } else {
+        for (int k = threadIdx.x; k <= n; k += blockDim.x) buf[k] = load_X<T>(P, row, k);
+    }
+    __syncthreads();
+
+    // pre-processing in place: Z[k] = (X[k] + conj X[n-k]) + i (X[k] - conj X[n-k]) e^{+2 pi i k/nphi}
     for (int k = threadIdx.x; k <= n / 2; k += blockDim.x) {
         if (k == 0) {
-            const cpx<T> x0 = load_X<T>(P, ph, 0), xn = load_X<T>(P, ph, n);
+            const cpx<T> x0 = buf[0], xn = buf[n];
             cpx<T> z; z.x = x0.x + xn.x; z.y = x0.x - xn.x;
-            buf[digit_reverse(P, 0)] = z;
+            buf[0] = z;
         } else {
-            const cpx<T> xa = load_X<T>(P, ph, k), xb = load_X<T>(P, ph, n - k);
+            const cpx<T> xa = buf[k], xb = buf[n - k];
             const cpx<T> wa = twid<T, +1>(P, k);
             const cpx<T> ea = cadd(xa, cconj(xb)), oa = cmul(csub(xa, cconj(xb)), wa);
-            buf[digit_reverse(P, k)] = cadd(ea, cmuli<T, +1>(oa));
             if (k != n - k) {
                 const cpx<T> wb = twid<T, +1>(P, n - k);
                 const cpx<T> eb = cadd(xb, cconj(xa)), ob = cmul(csub(xb, cconj(xa)), wb);
-                buf[digit_reverse(P, n - k)] = cadd(eb, cmuli<T, +1>(ob));
+                buf[n - k] = cadd(eb, cmuli<T, +1>(ob));
             }
+            buf[k] = cadd(ea, cmuli<T, +1>(oa));
         }
     }
     __syncthreads();
-    fft_passes<T, +1>(P, buf);
+    fft_passes<T, +1, true>(P, buf);
 
     // store x[2j] = Re z[j], x[2j+1] = Im z[j] into the caller's array (flips / partial rings by index arithmetic)
     T* out = reinterpret_cast<T*>(P.maps[c]);
     const int rowy = P.flipy ? (P.ny - 1 - ring) : ring;
     T* orow = out + (size_t)rowy * P.nx;
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        const cpx<T> z = buf[j];
+        const cpx<T> z = buf[P.perm[j]];
         const int i0 = 2 * j, i1 = 2 * j + 1;
         if (i0 < P.nx) orow[P.flipx ? (P.nx - 1 - i0) : i0] = z.x;
         if (i1 < P.nx) orow[P.flipx ? (P.nx - 1 - i1) : i1] = z.y;
@@ -202,7 +269,7 @@ __global__ void fft_phase2map(const FftParams P)
 
 // map -> weighted phase  (analysis).  grid = (ring_count, ncomp)
 template <class T>
-__global__ void fft_map2phase(const FftParams P)
+__global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams P)
 {
     PIXSHT_DYN_SMEM(smem_raw);
     cpx<T>* buf = reinterpret_cast<cpx<T>*>(smem_raw);   // n + 1 entries
@@ -216,10 +283,10 @@ __global__ void fft_map2phase(const FftParams P)
         cpx<T> z;
         z.x = (i0 < P.nx) ? irow[P.flipx ? (P.nx - 1 - i0) : i0] : (T)0;
         z.y = (i1 < P.nx) ? irow[P.flipx ? (P.nx - 1 - i1) : i1] : (T)0;
-        buf[digit_reverse(P, j)] = z;
+        buf[P.perm[j]] = z;
     }
     __syncthreads();
-    fft_passes<T, -1>(P, buf);
+    fft_passes<T, -1, false>(P, buf);
 
     // post-processing in place: F[k] = ((Z[k] + conj Z[n-k]) - i e^{-2 pi i k/N} (Z[k] - conj Z[n-k])) / 2,  k = 0..n
     for (int k = threadIdx.x; k <= n / 2; k += blockDim.x) {
@@ -243,16 +310,15 @@ __global__ void fft_map2phase(const FftParams P)
     }
     __syncthreads();
 
-    // phase_m = w * e^{-i m phi0} * F[m mod N]  (conjugate symmetric upper half)
+    // phase_m = w * e^{-i m phi0} * F[m mod N]  (conjugate symmetric upper half); coalesced row write
     const double w = P.wgt[ring];
-    double2* ph = P.phase + (long long)c * P.stride_c + rl;
+    double2* row = P.phase + ((long long)rl * P.ncomp + c) * P.MP;
     for (int m = threadIdx.x; m <= P.mmax; m += blockDim.x) {
-        const int kk = m % N;
+        const int kk = (m < N) ? m : (m % N);
         cpx<T> f = (kk <= n) ? buf[kk] : cconj(buf[N - kk]);
         const double2 r = P.phi0tw[m];
         const double fx = (double)f.x, fy = (double)f.y;
-        const int row = P.m_row ? P.m_row[m] : m;
-        ph[(long long)row * P.stride_m] = make_double2(w * (fx * r.x + fy * r.y), w * (fy * r.x - fx * r.y));
+        row[m] = make_double2(w * (fx * r.x + fy * r.y), w * (fy * r.x - fx * r.y));
     }
 }
 

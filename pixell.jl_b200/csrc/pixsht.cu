@@ -55,7 +55,9 @@ struct pixsht_plan {
     int R0 = 4, R2 = 4, R0a = 4, R2a = 4;   // ring pairs per thread in the spin-0 / spin-2 synthesis and analysis kernels
     // FFT
     int nfft = 0, nfac = 0, fac[FFT_MAXFAC] = {0}, fft_threads = 256;
+    unsigned fft_magic[FFT_MAXFAC] = {0};
     size_t fft_smem = 0;
+    long long MP = 0;             // phase row length (mmax+1 rounded up to a multiple of 8 complex = 128 B)
     // geometry (host copies kept for introspection)
     std::vector<double> h_theta, h_wgt;
     // device tables
@@ -69,6 +71,7 @@ struct pixsht_plan {
     DevBuf<double> d_st0, d_st2;           // recurrence state at l_act
     bool have_seek0 = false, have_seek2 = false;
     DevBuf<double2> d_tw, d_phi0tw;
+    DevBuf<unsigned short> d_perm;
     // work buffers (grown on demand)
     DevBuf<double2> d_phase; int phase_ncomp = 0;
     DevBuf<unsigned char> d_map[3], d_alm[3];
@@ -127,19 +130,23 @@ static void split_dd(long double v, double& hi, double& lo)
 static int factorize(int n, int* fac, int& nfac)
 {
     nfac = 0;
-    // pass order = order of fac[]; larger radices first keeps early passes cheap in twiddles
-    while (n % 4 == 0) { if (nfac >= FFT_MAXFAC) return 1; fac[nfac++] = 4; n /= 4; }
-    while (n % 2 == 0) { if (nfac >= FFT_MAXFAC) return 1; fac[nfac++] = 2; n /= 2; }
+    // pass order = order of fac[] (fft.cuh): odd radices first (largest first), then 4s, then a single 2
+    int n2 = 0;
+    while (n % 2 == 0) { ++n2; n /= 2; }
+    int odd[FFT_MAXFAC], nodd = 0;
     for (int p = 3; n > 1; p += 2) {
         while (n % p == 0) {
-            if (p > FFT_MAXRADIX || nfac >= FFT_MAXFAC) return 1;
-            fac[nfac++] = p; n /= p;
+            if (p > FFT_MAXRADIX || nodd >= FFT_MAXFAC) return 1;
+            odd[nodd++] = p; n /= p;
         }
         if ((long long)p * p > n && n > 1) {
-            if (n > FFT_MAXRADIX || nfac >= FFT_MAXFAC) return 1;
-            fac[nfac++] = n; n = 1;
+            if (n > FFT_MAXRADIX || nodd >= FFT_MAXFAC) return 1;
+            odd[nodd++] = n; n = 1;
         }
     }
+    for (int i = nodd - 1; i >= 0; --i) fac[nfac++] = odd[i];
+    for (; n2 >= 2; n2 -= 2) { if (nfac >= FFT_MAXFAC) return 1; fac[nfac++] = 4; }
+    if (n2 == 1) { if (nfac >= FFT_MAXFAC) return 1; fac[nfac++] = 2; }
     return 0;
 }
 
@@ -244,9 +251,29 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, P->device));
     P->sm_count = prop.multiProcessorCount;
-    if (P->fft_smem > prop.sharedMemPerBlockOptin)
+    if (P->fft_smem > prop.sharedMemPerBlockOptin || P->nfft > 65535)
         return fail(PIXSHT_ERR_UNSUPPORTED, "ring too long for the single-CTA shared-memory FFT (nphi/2 complex samples must fit in 227 KB)");
-    P->fft_threads = P->nfft >= 4096 ? 1024 : (P->nfft >= 1024 ? 512 : (P->nfft >= 256 ? 256 : 64));
+    {
+        // threads per CTA: the multiple of 32 that wastes the fewest thread-iterations over the passes
+        const int tmin = P->nfft >= 4096 ? 512 : (P->nfft >= 1024 ? 256 : (P->nfft >= 256 ? 128 : 64));
+        const int tmax = P->nfft >= 4096 ? FFT_MAXTHREADS : (P->nfft >= 1024 ? 512 : (P->nfft >= 256 ? 256 : 64));
+        long long best = -1; int bt = tmax;
+        for (int t = tmin; t <= tmax; t += 32) {
+            long long cost = 0;
+            for (int i = 0; i < P->nfac; ++i) { const int nb = P->nfft / P->fac[i]; cost += (long long)((nb + t - 1) / t) * (P->fac[i] + 2); }
+            cost = cost * 64 + (tmax - t) / 32;   // ties: prefer more threads
+            if (best < 0 || cost < best) { best = cost; bt = t; }
+        }
+        P->fft_threads = env_int("PIXSHT_FFT_THREADS", bt);
+        if (P->fft_threads < 32 || P->fft_threads > FFT_MAXTHREADS || P->fft_threads % 32) P->fft_threads = bt;
+    }
+    std::vector<unsigned short> perm(P->nfft);
+    for (int i = 0; i < P->nfft; ++i) perm[i] = (unsigned short)fft_digit_reverse(P->fac, P->nfac, P->nfft, i);
+    {
+        long long L = 1;
+        for (int i = 0; i < P->nfac; ++i) { P->fft_magic[i] = (L == 1) ? 0u : (unsigned)((1ULL << 32) / (unsigned long long)L + 1ULL); L *= P->fac[i]; }
+    }
+    P->MP = ((long long)P->mmax + 1 + 7) / 8 * 8;
 
     // ---- upload ----
     int rc = 0;
@@ -254,7 +281,7 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     rc |= P->d_lch_hi.upload(lch_hi); rc |= P->d_lch_lo.upload(lch_lo); rc |= P->d_mlim.upload(mlim);
     rc |= P->d_ringN.upload(ringN); rc |= P->d_ringS.upload(ringS);
     rc |= P->d_lg0_hi.upload(lg0_hi); rc |= P->d_lg0_lo.upload(lg0_lo); rc |= P->d_lg2_hi.upload(lg2_hi); rc |= P->d_lg2_lo.upload(lg2_lo);
-    rc |= P->d_phi0tw.upload(ph0);
+    rc |= P->d_phi0tw.upload(ph0); rc |= P->d_perm.upload(perm);
     rc |= P->d_wgt.alloc(nr); rc |= P->d_tw.alloc(P->nphi);
     rc |= P->d_ad0.alloc(P->nalm); rc |= P->d_gamma0.alloc(P->nalm);
     rc |= P->d_ad2.alloc(P->nalm); rc |= P->d_gamma2.alloc(P->nalm);
@@ -361,7 +388,7 @@ extern "C" void pixsht_plan_destroy(pixsht_plan* P)
     P->d_mlim.release(); P->d_wgt.release(); P->d_ringN.release(); P->d_ringS.release();
     P->d_lg0_hi.release(); P->d_lg0_lo.release(); P->d_lg2_hi.release(); P->d_lg2_lo.release();
     P->d_ad0.release(); P->d_gamma0.release(); P->d_ad2.release(); P->d_gamma2.release(); P->d_rec0.release(); P->d_rec2.release();
-    P->d_tw.release(); P->d_phi0tw.release(); P->d_phase.release();
+    P->d_tw.release(); P->d_phi0tw.release(); P->d_phase.release(); P->d_perm.release();
     P->d_lact0.release(); P->d_lact2.release(); P->d_st0.release(); P->d_st2.release();
     for (int c = 0; c < 3; ++c) { P->d_map[c].release(); P->d_alm[c].release(); P->d_alm64[c].release(); }
     for (auto& e : P->ev) if (e) cudaEventDestroy(e);
@@ -397,8 +424,10 @@ static int ensure_seek(pixsht_plan* P, int spin, cudaStream_t st)
     return PIXSHT_OK;
 }
 
-static LegParams leg_params(pixsht_plan* P, int spin, int R, int nm, const int* d_m_list, double2* phase, long long stride_c,
-                            long long stride_m)
+// where the phase rows of a launch live: a local buffer (ring r at phase + r*ncomp*MP) or a per-ring pointer table
+struct PhaseRef { double2* phase; double2* const* ring_ptr; };
+
+static LegParams leg_params(pixsht_plan* P, int spin, int R, int nm, const int* d_m_list, PhaseRef ph, int ncomp, int c0)
 {
     LegParams L;
     memset(&L, 0, sizeof(L));
@@ -407,7 +436,7 @@ static LegParams leg_params(pixsht_plan* P, int spin, int R, int nm, const int* 
     L.x = P->d_x.p; L.ringN = P->d_ringN.p; L.ringS = P->d_ringS.p;
     if (spin == 0) { L.lact = P->d_lact0.p; L.st = P->d_st0.p; L.ad = P->d_ad0.p; L.gamma = P->d_gamma0.p; L.rec = P->d_rec0.p; }
     else { L.lact = P->d_lact2.p; L.st = P->d_st2.p; L.ad = P->d_ad2.p; L.gamma = P->d_gamma2.p; L.rec = P->d_rec2.p; }
-    L.phase = phase; L.stride_c = stride_c; L.stride_m = stride_m;
+    L.phase = ph.phase; L.ring_ptr = ph.ring_ptr; L.ring_stride = (long long)ncomp * P->MP; L.MP = P->MP; L.c0 = c0;
     return L;
 }
 
@@ -431,8 +460,7 @@ static void launch_anal(pixsht_plan* P, int R, const LegParams& L, cudaStream_t 
 }
 
 // alm component layout per ncomp: ncomp 1: [T]; 2: [E,B]; 3: [T,E,B].  phase/map components likewise [T] / [Q,U] / [T,Q,U].
-static int stage_alm2phase(pixsht_plan* P, int ncomp, const double2* const* alm, int nm, const int* d_m_list, double2* phase,
-                           long long stride_c, long long stride_m, cudaStream_t st)
+static int stage_alm2phase(pixsht_plan* P, int ncomp, const double2* const* alm, int nm, const int* d_m_list, PhaseRef ph, cudaStream_t st)
 {
     const int prep_grid = P->sm_count > 0 ? P->sm_count * 8 : 256;
     if (ncomp == 1 || ncomp == 3) {
@@ -440,7 +468,7 @@ static int stage_alm2phase(pixsht_plan* P, int ncomp, const double2* const* alm,
         if (P->d_rec0.n < (size_t)P->nalm * 4 && P->d_rec0.alloc((size_t)P->nalm * 4)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
         PIXSHT_LAUNCH(k_prep_synth<0>, prep_grid, 256, 0, st, P->nalm, P->lmax, P->d_ad0.p, P->d_gamma0.p, alm[0], alm[0], P->d_rec0.p);
         P->launches++;
-        LegParams L = leg_params(P, 0, P->R0, nm, d_m_list, phase, stride_c, stride_m);
+        LegParams L = leg_params(P, 0, P->R0, nm, d_m_list, ph, ncomp, 0);
         launch_synth<0>(P, P->R0, L, st);
     }
     if (ncomp >= 2) {
@@ -449,26 +477,25 @@ static int stage_alm2phase(pixsht_plan* P, int ncomp, const double2* const* alm,
         if (P->d_rec2.n < (size_t)P->nalm * 6 && P->d_rec2.alloc((size_t)P->nalm * 6)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
         PIXSHT_LAUNCH(k_prep_synth<2>, prep_grid, 256, 0, st, P->nalm, P->lmax, P->d_ad2.p, P->d_gamma2.p, alm[c0], alm[c0 + 1], P->d_rec2.p);
         P->launches++;
-        LegParams L = leg_params(P, 2, P->R2, nm, d_m_list, phase + (long long)c0 * stride_c, stride_c, stride_m);
+        LegParams L = leg_params(P, 2, P->R2, nm, d_m_list, ph, ncomp, c0);
         launch_synth<2>(P, P->R2, L, st);
     }
     CU(cudaGetLastError());
     return PIXSHT_OK;
 }
 
-static int stage_phase2alm(pixsht_plan* P, int ncomp, double2* phase, long long stride_c, long long stride_m, int nm,
-                           const int* d_m_list, double2* const* alm, cudaStream_t st)
+static int stage_phase2alm(pixsht_plan* P, int ncomp, PhaseRef ph, int nm, const int* d_m_list, double2* const* alm, cudaStream_t st)
 {
     if (ncomp == 1 || ncomp == 3) {
         { int rc = ensure_seek(P, 0, st); if (rc) return rc; }
-        LegParams L = leg_params(P, 0, P->R0a, nm, d_m_list, phase, stride_c, stride_m);
+        LegParams L = leg_params(P, 0, P->R0a, nm, d_m_list, ph, ncomp, 0);
         L.alm_out0 = alm[0];
         launch_anal<0>(P, P->R0a, L, st);
     }
     if (ncomp >= 2) {
         const int c0 = ncomp == 3 ? 1 : 0;
         { int rc = ensure_seek(P, 2, st); if (rc) return rc; }
-        LegParams L = leg_params(P, 2, P->R2a, nm, d_m_list, phase + (long long)c0 * stride_c, stride_c, stride_m);
+        LegParams L = leg_params(P, 2, P->R2a, nm, d_m_list, ph, ncomp, c0);
         L.alm_out0 = alm[c0]; L.alm_out1 = alm[c0 + 1];
         launch_anal<2>(P, P->R2a, L, st);
     }
@@ -476,26 +503,18 @@ static int stage_phase2alm(pixsht_plan* P, int ncomp, double2* phase, long long 
     return PIXSHT_OK;
 }
 
-static FftParams fft_params(pixsht_plan* P, int ncomp, double2* phase, long long stride_c, long long stride_m, const int* d_m_row,
-                            int ring_begin, int ring_count, void* const* maps)
+static int stage_fft(pixsht_plan* P, int dir, int ncomp, double2* phase, int ring_begin, int ring_count, void* const* maps, cudaStream_t st)
 {
+    if (ring_count <= 0) return PIXSHT_OK;
     FftParams F;
     memset(&F, 0, sizeof(F));
     F.nphi = P->nphi; F.n = P->nfft; F.nfac = P->nfac;
-    for (int i = 0; i < P->nfac; ++i) F.fac[i] = P->fac[i];
-    F.tw = P->d_tw.p; F.phi0tw = P->d_phi0tw.p; F.wgt = P->d_wgt.p; F.mmax = P->mmax; F.m_row = d_m_row;
-    F.phase = phase; F.stride_c = stride_c; F.stride_m = stride_m;
+    for (int i = 0; i < P->nfac; ++i) { F.fac[i] = P->fac[i]; F.magic[i] = P->fft_magic[i]; }
+    F.tw = P->d_tw.p; F.phi0tw = P->d_phi0tw.p; F.wgt = P->d_wgt.p; F.perm = P->d_perm.p; F.mmax = P->mmax;
+    F.phase = phase; F.MP = P->MP; F.ncomp = ncomp;
     F.ring_begin = ring_begin; F.ring_count = ring_count;
     F.nx = P->nx; F.ny = P->ny; F.flipx = P->flipx; F.flipy = P->flipy;
     for (int c = 0; c < ncomp; ++c) F.maps[c] = maps[c];
-    return F;
-}
-
-static int stage_fft(pixsht_plan* P, int dir, int ncomp, double2* phase, long long stride_c, long long stride_m, const int* d_m_row,
-                     int ring_begin, int ring_count, void* const* maps, cudaStream_t st)
-{
-    if (ring_count <= 0) return PIXSHT_OK;
-    FftParams F = fft_params(P, ncomp, phase, stride_c, stride_m, d_m_row, ring_begin, ring_count, maps);
     dim3 grid(ring_count, ncomp);
     if (P->dtype == PIXSHT_F64) {
         if (dir == PIXSHT_ALM2MAP) PIXSHT_LAUNCH(fft_phase2map<double>, grid, P->fft_threads, P->fft_smem, st, F);
@@ -512,7 +531,7 @@ static int stage_fft(pixsht_plan* P, int dir, int ncomp, double2* phase, long lo
 static int ensure_phase(pixsht_plan* P, int ncomp)
 {
     if (P->phase_ncomp >= ncomp) return PIXSHT_OK;
-    if (P->d_phase.alloc((size_t)ncomp * (P->mmax + 1) * P->nrings)) return fail(PIXSHT_ERR_NOMEM, "phase buffer allocation failed");
+    if (P->d_phase.alloc((size_t)ncomp * P->MP * P->nrings)) return fail(PIXSHT_ERR_NOMEM, "phase buffer allocation failed");
     P->phase_ncomp = ncomp;
     return PIXSHT_OK;
 }
@@ -551,7 +570,7 @@ extern "C" int pixsht_execute(pixsht_plan* P, int direction, int ncomp, void* co
             dalm64[c] = P->d_alm64[c].p;
         } else dalm64[c] = reinterpret_cast<double2*>(dalm[c]);
     }
-    const long long stride_m = P->nrings, stride_c = (long long)(P->mmax + 1) * P->nrings;
+    const PhaseRef ph = {P->d_phase.p, nullptr};
     const int cvt_grid = P->sm_count > 0 ? P->sm_count * 8 : 256;
 
     CU(cudaEventRecord(P->ev[0], st));
@@ -564,9 +583,9 @@ extern "C" int pixsht_execute(pixsht_plan* P, int direction, int ncomp, void* co
                 PIXSHT_LAUNCH(k_cvt_f32_to_f64, cvt_grid, 256, 0, st, (const float*)dalm[c], (double*)dalm64[c], 2 * P->nalm);
                 P->launches++;
             }
-        rc = stage_alm2phase(P, ncomp, dalm64, P->mmax + 1, nullptr, P->d_phase.p, stride_c, stride_m, st); if (rc) return rc;
+        rc = stage_alm2phase(P, ncomp, dalm64, P->mmax + 1, nullptr, ph, st); if (rc) return rc;
         CU(cudaEventRecord(P->ev[2], st));
-        rc = stage_fft(P, PIXSHT_ALM2MAP, ncomp, P->d_phase.p, stride_c, stride_m, nullptr, 0, P->nrings, dmap, st); if (rc) return rc;
+        rc = stage_fft(P, PIXSHT_ALM2MAP, ncomp, P->d_phase.p, 0, P->nrings, dmap, st); if (rc) return rc;
         CU(cudaEventRecord(P->ev[3], st));
         if (location == PIXSHT_HOST)
             for (int c = 0; c < ncomp; ++c) CU(cudaMemcpyAsync(maps[c], dmap[c], map_bytes, cudaMemcpyDeviceToHost, st));
@@ -575,10 +594,10 @@ extern "C" int pixsht_execute(pixsht_plan* P, int direction, int ncomp, void* co
         if (location == PIXSHT_HOST)
             for (int c = 0; c < ncomp; ++c) CU(cudaMemcpyAsync(dmap[c], maps[c], map_bytes, cudaMemcpyHostToDevice, st));
         CU(cudaEventRecord(P->ev[1], st));
-        rc = stage_fft(P, PIXSHT_MAP2ALM, ncomp, P->d_phase.p, stride_c, stride_m, nullptr, 0, P->nrings, dmap, st); if (rc) return rc;
+        rc = stage_fft(P, PIXSHT_MAP2ALM, ncomp, P->d_phase.p, 0, P->nrings, dmap, st); if (rc) return rc;
         CU(cudaEventRecord(P->ev[2], st));
         for (int c = 0; c < ncomp; ++c) CU(cudaMemsetAsync(dalm64[c], 0, (size_t)P->nalm * sizeof(double2), st));
-        rc = stage_phase2alm(P, ncomp, P->d_phase.p, stride_c, stride_m, P->mmax + 1, nullptr, dalm64, st); if (rc) return rc;
+        rc = stage_phase2alm(P, ncomp, ph, P->mmax + 1, nullptr, dalm64, st); if (rc) return rc;
         if (f32)
             for (int c = 0; c < ncomp; ++c) {
                 PIXSHT_LAUNCH(k_cvt_f64_to_f32, cvt_grid, 256, 0, st, (const double*)dalm64[c], (float*)dalm[c], 2 * P->nalm);
@@ -628,45 +647,139 @@ static int stage_common(pixsht_plan* P, int ncomp)
     return check_device(P->device);
 }
 
+extern "C" int64_t pixsht_phase_row_len(const pixsht_plan* P) { return P ? (int64_t)P->MP : 0; }
+
 extern "C" int pixsht_stage_alm2phase(pixsht_plan* P, int ncomp, const void* const* d_alms, int nm, const int32_t* d_m_list,
-                                      void* d_phase, void* stream)
+                                      void* const* d_ring_ptrs, void* stream)
 {
     int rc = stage_common(P, ncomp); if (rc) return rc;
-    if (!d_alms || !d_phase || nm < 0 || nm > P->mmax + 1) return fail(PIXSHT_ERR_ARG, "bad argument");
+    if (!d_alms || !d_ring_ptrs || nm < 0 || nm > P->mmax + 1) return fail(PIXSHT_ERR_ARG, "bad argument");
     if (nm == 0) return PIXSHT_OK;
     const double2* alm[3] = {nullptr, nullptr, nullptr};
     for (int c = 0; c < ncomp; ++c) alm[c] = (const double2*)d_alms[c];
-    return stage_alm2phase(P, ncomp, alm, nm, d_m_list, (double2*)d_phase, P->nrings, (long long)ncomp * P->nrings, (cudaStream_t)stream);
+    const PhaseRef ph = {nullptr, (double2* const*)d_ring_ptrs};
+    return stage_alm2phase(P, ncomp, alm, nm, d_m_list, ph, (cudaStream_t)stream);
 }
 
-extern "C" int pixsht_stage_phase2alm(pixsht_plan* P, int ncomp, const void* d_phase, int nm, const int32_t* d_m_list,
+extern "C" int pixsht_stage_phase2alm(pixsht_plan* P, int ncomp, void* const* d_ring_ptrs, int nm, const int32_t* d_m_list,
                                       void* const* d_alms, void* stream)
 {
     int rc = stage_common(P, ncomp); if (rc) return rc;
-    if (!d_alms || !d_phase || nm < 0 || nm > P->mmax + 1) return fail(PIXSHT_ERR_ARG, "bad argument");
+    if (!d_alms || !d_ring_ptrs || nm < 0 || nm > P->mmax + 1) return fail(PIXSHT_ERR_ARG, "bad argument");
     if (nm == 0) return PIXSHT_OK;
     double2* alm[3] = {nullptr, nullptr, nullptr};
     for (int c = 0; c < ncomp; ++c) alm[c] = (double2*)d_alms[c];
-    return stage_phase2alm(P, ncomp, (double2*)d_phase, P->nrings, (long long)ncomp * P->nrings, nm, d_m_list, alm, (cudaStream_t)stream);
+    const PhaseRef ph = {nullptr, (double2* const*)d_ring_ptrs};
+    return stage_phase2alm(P, ncomp, ph, nm, d_m_list, alm, (cudaStream_t)stream);
 }
 
-extern "C" int pixsht_stage_phase2map(pixsht_plan* P, int ncomp, const void* d_phase, const int32_t* d_m_row, int ring_begin,
-                                      int ring_count, void* const* d_maps, void* stream)
+extern "C" int pixsht_stage_phase2map(pixsht_plan* P, int ncomp, const void* d_phase, int ring_begin, int ring_count,
+                                      void* const* d_maps, void* stream)
 {
     int rc = stage_common(P, ncomp); if (rc) return rc;
     if (!d_maps || !d_phase || ring_begin < 0 || ring_count < 0 || ring_begin + ring_count > P->nrings) return fail(PIXSHT_ERR_ARG, "bad argument");
-    return stage_fft(P, PIXSHT_ALM2MAP, ncomp, (double2*)d_phase, ring_count, (long long)ncomp * ring_count, d_m_row,
-                     ring_begin, ring_count, d_maps, (cudaStream_t)stream);
+    return stage_fft(P, PIXSHT_ALM2MAP, ncomp, (double2*)d_phase, ring_begin, ring_count, d_maps, (cudaStream_t)stream);
 }
 
-extern "C" int pixsht_stage_map2phase(pixsht_plan* P, int ncomp, const void* const* d_maps, const int32_t* d_m_row, int ring_begin,
-                                      int ring_count, void* d_phase, void* stream)
+extern "C" int pixsht_stage_map2phase(pixsht_plan* P, int ncomp, const void* const* d_maps, int ring_begin, int ring_count,
+                                      void* d_phase, void* stream)
 {
     int rc = stage_common(P, ncomp); if (rc) return rc;
     if (!d_maps || !d_phase || ring_begin < 0 || ring_count < 0 || ring_begin + ring_count > P->nrings) return fail(PIXSHT_ERR_ARG, "bad argument");
-    return stage_fft(P, PIXSHT_MAP2ALM, ncomp, (double2*)d_phase, ring_count, (long long)ncomp * ring_count, d_m_row,
-                     ring_begin, ring_count, (void* const*)d_maps, (cudaStream_t)stream);
+    return stage_fft(P, PIXSHT_MAP2ALM, ncomp, (double2*)d_phase, ring_begin, ring_count, (void* const*)d_maps, (cudaStream_t)stream);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// peer-visible device memory (multi-GPU phase buffers): CUDA IPC between the one-process-per-GPU ranks of a node
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef PIXSHT_EMU
+extern "C" int pixsht_shared_alloc(int device, size_t bytes, void** dptr, unsigned char handle[64])
+{
+    if (!dptr || !handle || bytes == 0) return fail(PIXSHT_ERR_ARG, "bad argument");
+    int rc = check_device(device); if (rc) return rc;
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) { (void)cudaGetLastError(); return fail(PIXSHT_ERR_NOMEM, "shared phase buffer allocation failed"); }
+    static_assert(sizeof(cudaIpcMemHandle_t) <= 64, "IPC handle does not fit");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(PIXSHT_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    memset(handle, 0, 64);
+    memcpy(handle, &h, sizeof(h));
+    *dptr = p;
+    return PIXSHT_OK;
+}
+extern "C" int pixsht_shared_open(int device, const unsigned char handle[64], void** dptr)
+{
+    if (!dptr || !handle) return fail(PIXSHT_ERR_ARG, "bad argument");
+    int rc = check_device(device); if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(PIXSHT_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    *dptr = p;
+    return PIXSHT_OK;
+}
+extern "C" int pixsht_shared_close(void* dptr)
+{
+    if (dptr && cudaIpcCloseMemHandle(dptr) != cudaSuccess) { (void)cudaGetLastError(); return fail(PIXSHT_ERR_CUDA, "cudaIpcCloseMemHandle failed"); }
+    return PIXSHT_OK;
+}
+extern "C" int pixsht_shared_free(void* dptr)
+{
+    if (dptr && cudaFree(dptr) != cudaSuccess) { (void)cudaGetLastError(); return fail(PIXSHT_ERR_CUDA, "cudaFree failed"); }
+    return PIXSHT_OK;
+}
+#else
+// host emulation (tests only): POSIX shared memory stands in for CUDA IPC so that the world-size-2 gloo test runs the
+// same peer-pointer pipeline.  handle = { name[48], size }.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+#include <map>
+static std::map<void*, std::pair<size_t, std::string>> g_shm;
+extern "C" int pixsht_shared_alloc(int, size_t bytes, void** dptr, unsigned char handle[64])
+{
+    static int counter = 0;
+    char name[48];
+    snprintf(name, sizeof(name), "/pixsht_%d_%d", (int)getpid(), counter++);
+    int fd = shm_open(name, O_CREAT | O_RDWR | O_EXCL, 0600);
+    if (fd < 0 || ftruncate(fd, (off_t)bytes) != 0) return fail(PIXSHT_ERR_NOMEM, "shm_open failed");
+    void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) return fail(PIXSHT_ERR_NOMEM, "mmap failed");
+    memset(handle, 0, 64);
+    memcpy(handle, name, strlen(name) + 1);
+    unsigned long long sz = bytes; memcpy(handle + 48, &sz, 8);
+    g_shm[p] = {bytes, std::string(name)};
+    *dptr = p;
+    return PIXSHT_OK;
+}
+extern "C" int pixsht_shared_open(int, const unsigned char handle[64], void** dptr)
+{
+    unsigned long long sz; memcpy(&sz, handle + 48, 8);
+    int fd = shm_open((const char*)handle, O_RDWR, 0600);
+    if (fd < 0) return fail(PIXSHT_ERR_CUDA, "shm_open of a peer segment failed");
+    void* p = mmap(nullptr, (size_t)sz, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) return fail(PIXSHT_ERR_NOMEM, "mmap failed");
+    g_shm[p] = {(size_t)sz, std::string()};
+    *dptr = p;
+    return PIXSHT_OK;
+}
+extern "C" int pixsht_shared_close(void* dptr)
+{
+    auto it = g_shm.find(dptr);
+    if (it != g_shm.end()) { munmap(dptr, it->second.first); g_shm.erase(it); }
+    return PIXSHT_OK;
+}
+extern "C" int pixsht_shared_free(void* dptr)
+{
+    auto it = g_shm.find(dptr);
+    if (it != g_shm.end()) { munmap(dptr, it->second.first); if (!it->second.second.empty()) shm_unlink(it->second.second.c_str()); g_shm.erase(it); }
+    return PIXSHT_OK;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------
 // introspection

@@ -26,6 +26,7 @@ class Geom(ctypes.Structure):
 # every symbol include/pixsht.h and include/pixsht_sharp_shim.h declare
 EXPORTS = ["pixsht_plan_create", "pixsht_plan_create_rings", "pixsht_plan_destroy", "pixsht_execute", "pixsht_get_timings", "pixsht_plan_set_stream",
            "pixsht_stage_alm2phase", "pixsht_stage_phase2alm", "pixsht_stage_phase2map", "pixsht_stage_map2phase",
+           "pixsht_phase_row_len", "pixsht_shared_alloc", "pixsht_shared_open", "pixsht_shared_close", "pixsht_shared_free",
            "pixsht_nalm", "pixsht_plan_info", "pixsht_plan_weights", "pixsht_last_error", "pixsht_version",
            "pixsht_device_count", "pixsht_measure_fma_peak",
            "sharp_make_geom_info", "sharp_destroy_geom_info", "sharp_map_size", "sharp_make_triangular_alm_info",
@@ -54,8 +55,14 @@ class PixshtLib:
         L.pixsht_get_timings.argtypes = [vp, ctypes.POINTER(dbl)]
         L.pixsht_stage_alm2phase.argtypes = [vp, i32, pvp, i32, vp, vp, vp]
         L.pixsht_stage_phase2alm.argtypes = [vp, i32, vp, i32, vp, pvp, vp]
-        L.pixsht_stage_phase2map.argtypes = [vp, i32, vp, vp, i32, i32, pvp, vp]
-        L.pixsht_stage_map2phase.argtypes = [vp, i32, pvp, vp, i32, i32, vp, vp]
+        L.pixsht_stage_phase2map.argtypes = [vp, i32, vp, i32, i32, pvp, vp]
+        L.pixsht_stage_map2phase.argtypes = [vp, i32, pvp, i32, i32, vp, vp]
+        L.pixsht_phase_row_len.argtypes = [vp]
+        L.pixsht_phase_row_len.restype = ctypes.c_int64
+        L.pixsht_shared_alloc.argtypes = [i32, ctypes.c_size_t, pvp, ctypes.c_char_p]
+        L.pixsht_shared_open.argtypes = [i32, ctypes.c_char_p, pvp]
+        L.pixsht_shared_close.argtypes = [vp]
+        L.pixsht_shared_free.argtypes = [vp]
         L.pixsht_nalm.argtypes = [i32, i32]
         L.pixsht_nalm.restype = ctypes.c_int64
         L.pixsht_plan_info.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]

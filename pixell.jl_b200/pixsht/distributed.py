@@ -1,16 +1,22 @@
 """m-sharded multi-GPU pipeline: one process per GPU, torch.distributed for the plumbing.
 
-  alm2map:  Legendre stage on this rank's m values (all rings)  ->  all-to-all (phase transpose)  ->  ring FFTs on this
-            rank's contiguous slab of rings (all m)  ->  the rank's rows of the map.
-  map2alm:  the same pipeline backwards.
+  alm2map:  Legendre stage on this rank's m values (all rings), writing every phase value straight into the phase
+            buffer of the GPU that owns its ring (peer memory over NVLink)  ->  stream-ordered barrier  ->  ring FFTs on
+            this rank's contiguous slab of rings (all m)  ->  the rank's rows of the map.
+  map2alm:  ring FFTs of the rank's rows into its own phase buffer  ->  barrier  ->  Legendre analysis on the rank's m
+            values, reading each ring's phase value from the GPU that owns the ring.
+
+So the phase transpose between the m-sharded and the ring-sharded stage is fused into the Legendre kernels' own loads
+and stores (they are FP64 bound, the memory system and the NVLink ports are idle while they run); there is no pack /
+all-to-all / unpack pass and no second copy of the phase array.  The only collective left is the barrier that orders the
+two stages (a 1-element all-reduce on the compute stream with NCCL; dist.barrier() with gloo).
 
 Partition: m values are dealt out in load-balanced pairs (m, mmax-m) -- the Legendre cost of an m is ~ (lmax-m+1), so a
 pair costs the same whichever it is; rings are split into contiguous slabs, which are contiguous row ranges of the
 caller's column-major map.  Nothing else is partitioned; tables are replicated.
 
-The compute stages are the pixsht_stage_* entry points of the C ABI; this module only owns the partition, the
-pack/unpack of the exchange buffers and the collective (torch.distributed.all_to_all_single: NCCL over NVLink on GPUs,
-gloo in the CPU tests, where the library handle is the host-emulation build).
+The compute stages are the pixsht_stage_* entry points of the C ABI; the peer-visible buffers are pixsht_shared_alloc /
+pixsht_shared_open (CUDA IPC; POSIX shared memory in the host-emulation build that the gloo CPU tests use).
 """
 import ctypes
 
@@ -44,6 +50,8 @@ class ShardedSHT:
     """Distributed map2alm / alm2map on one 8-GPU box.  All tensors live on `device` ('cuda:i', or 'cpu' with the
     emulation library in the gloo tests).  Float64 only (the BASELINE multi-GPU configs are Float64)."""
 
+    MAX_NCOMP = 3
+
     def __init__(self, band, lmax, mmax=None, group=None, device=None, lib=None):
         self.lib = get_lib() if lib is None else lib
         self.group = group
@@ -52,12 +60,13 @@ class ShardedSHT:
         self.band, self.lmax = band, int(lmax)
         self.mmax = int(lmax if mmax is None else mmax)
         self.device = torch.device(device if device is not None else "cuda")
-        dev_index = self.device.index if self.device.type == "cuda" and self.device.index is not None else 0
+        self.dev_index = self.device.index if self.device.type == "cuda" and self.device.index is not None else 0
         g = Geom(band.nphi, band.nrings_total, band.ring_first, band.nrings, band.nx, int(band.flipx), int(band.flipy), 0, band.phi0)
         h = ctypes.c_void_p()
-        self.lib.check(self.lib.lib.pixsht_plan_create(ctypes.byref(h), ctypes.byref(g), self.lmax, self.mmax, F64, dev_index))
+        self.lib.check(self.lib.lib.pixsht_plan_create(ctypes.byref(h), ctypes.byref(g), self.lmax, self.mmax, F64, self.dev_index))
         self.handle = h
         self.nalm = int(self.lib.lib.pixsht_nalm(self.lmax, self.mmax))
+        self.MP = int(self.lib.lib.pixsht_phase_row_len(self.handle))
         self.nrings = band.nrings
         self.m_lists = partition_m(self.mmax, self.world)
         self.ring_ranges = partition_rings(self.nrings, self.world)
@@ -65,13 +74,30 @@ class ShardedSHT:
         self.nm = len(self.my_m)
         self.r0, self.r1 = self.ring_ranges[self.rank]
         self.nloc = self.r1 - self.r0
-        # row of m in the exchanged buffer = position in the concatenation of all ranks' m lists
-        m_row = np.empty(self.mmax + 1, dtype=np.int32)
-        m_row[np.concatenate(self.m_lists)] = np.arange(self.mmax + 1, dtype=np.int32)
         self.d_m_list = torch.from_numpy(self.my_m.copy()).to(self.device)
-        self.d_m_row = torch.from_numpy(m_row).to(self.device)
-        self._bufs = {}
         self.last_ms = {}
+        # ---- peer-visible phase buffer: this rank's rings x MAX_NCOMP components x MP complex doubles ----
+        L = self.lib.lib
+        nbytes = max(1, self.nloc) * self.MAX_NCOMP * self.MP * 16
+        own = ctypes.c_void_p()
+        hbuf = ctypes.create_string_buffer(64)
+        self.lib.check(L.pixsht_shared_alloc(self.dev_index, nbytes, ctypes.byref(own), hbuf))
+        self.own_ptr = own.value
+        self.peer_ptrs = [None] * self.world
+        self.peer_ptrs[self.rank] = self.own_ptr
+        self._opened = []
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(hbuf.raw), group=self.group)
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                p = ctypes.c_void_p()
+                self.lib.check(L.pixsht_shared_open(self.dev_index, handles[r], ctypes.byref(p)))
+                self.peer_ptrs[r] = p.value
+                self._opened.append(p.value)
+        self._ring_tables = {}
+        self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
 
     # ---- the caller's view of the data ---------------------------------------------------------------------------
     def map_rows(self):
@@ -87,21 +113,37 @@ class ShardedSHT:
 
     def close(self):
         if getattr(self, "handle", None):
-            self.lib.lib.pixsht_plan_destroy(self.handle)
+            L = self.lib.lib
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier(group=self.group)      # nobody may still be reading or writing a buffer about to be unmapped
+            for p in self._opened:
+                L.pixsht_shared_close(ctypes.c_void_p(p))
+            self._opened = []
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier(group=self.group)
+            L.pixsht_shared_free(ctypes.c_void_p(self.own_ptr))
+            L.pixsht_plan_destroy(self.handle)
             self.handle = None
 
     def __del__(self):
         try:
-            self.close()
+            if getattr(self, "handle", None) and self.world == 1:
+                self.close()
         except Exception:
             pass
 
     # ---- helpers -----------------------------------------------------------------------------------------------
-    def _buf(self, name, n):
-        b = self._bufs.get(name)
-        if b is None or b.numel() < n:
-            b = self._bufs[name] = torch.empty(n, dtype=torch.complex128, device=self.device)
-        return b[:n]
+    def _ring_table(self, nc):
+        """Device array of nrings pointers: element (ring, component 0, m 0) of every band ring, in its owner's buffer."""
+        t = self._ring_tables.get(nc)
+        if t is None:
+            ptrs = np.empty(self.nrings, dtype=np.int64)
+            for r, (a, b) in enumerate(self.ring_ranges):
+                ptrs[a:b] = self.peer_ptrs[r] + np.arange(b - a, dtype=np.int64) * (nc * self.MP * 16)
+            t = self._ring_tables[nc] = torch.from_numpy(ptrs).to(self.device)
+        return t
 
     def _stream_ptr(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream) if self.device.type == "cuda" else ctypes.c_void_p(0)
@@ -128,12 +170,15 @@ class ShardedSHT:
         e.record(torch.cuda.current_stream(self.device))
         return e
 
-    def _exchange(self, send, out, in_splits, out_splits):
+    def _barrier(self):
+        """Orders the stages across ranks: everything the ranks enqueued before it is complete (and visible in peer
+        memory) before anything enqueued after it starts.  Stream-ordered with NCCL (no host synchronisation)."""
         if self.world == 1:
-            out.copy_(send)
+            return
+        if self.device.type == "cuda":
+            dist.all_reduce(self._flag, group=self.group)
         else:
-            dist.all_to_all_single(torch.view_as_real(out), torch.view_as_real(send), [s * 1 for s in out_splits],
-                                   [s * 1 for s in in_splits], group=self.group)
+            dist.barrier(group=self.group)
 
     # ---- transforms ------------------------------------------------------------------------------------------
     def alm2map(self, d_alms, d_map_slabs):
@@ -142,27 +187,16 @@ class ShardedSHT:
         nc = len(d_alms)
         L = self.lib.lib
         st = self._stream_ptr()
-        nr = self.nrings
+        table = self._ring_table(nc)
+        self._barrier()          # every rank is done with the previous contents of the phase buffers
         ev = [self._ev()]
-        legbuf = self._buf("leg", self.nm * nc * nr)
         self.lib.check(L.pixsht_stage_alm2phase(self.handle, nc, self._ptrs(d_alms), self.nm, ctypes.c_void_p(self.d_m_list.data_ptr()),
-                                                ctypes.c_void_p(legbuf.data_ptr()), st))
+                                                ctypes.c_void_p(table.data_ptr()), st))
         ev.append(self._ev())
-        # pack: [mi][c][ring] -> per destination h: [mi][c][ring in slab h]
-        v = legbuf.view(self.nm, nc, nr)
-        send = self._buf("send", self.nm * nc * nr)
-        in_splits, off = [], 0
-        for (a, b) in self.ring_ranges:
-            n = self.nm * nc * (b - a)
-            send[off:off + n].view(self.nm, nc, b - a).copy_(v[:, :, a:b])
-            in_splits.append(n)
-            off += n
-        out_splits = [len(ml) * nc * self.nloc for ml in self.m_lists]
-        recv = self._buf("recv", (self.mmax + 1) * nc * self.nloc)
-        self._exchange(send, recv, in_splits, out_splits)
+        self._barrier()          # all m of my rings have arrived
         ev.append(self._ev())
-        self.lib.check(L.pixsht_stage_phase2map(self.handle, nc, ctypes.c_void_p(recv.data_ptr()), ctypes.c_void_p(self.d_m_row.data_ptr()),
-                                                self.r0, self.nloc, self._slab_base_ptrs(d_map_slabs), st))
+        self.lib.check(L.pixsht_stage_phase2map(self.handle, nc, ctypes.c_void_p(self.own_ptr), self.r0, self.nloc,
+                                                self._slab_base_ptrs(d_map_slabs), st))
         ev.append(self._ev())
         self._record("alm2map", ev)
 
@@ -172,27 +206,17 @@ class ShardedSHT:
         nc = len(d_alms)
         L = self.lib.lib
         st = self._stream_ptr()
-        nr = self.nrings
+        table = self._ring_table(nc)
+        self._barrier()          # nobody is still reading my phase buffer
         ev = [self._ev()]
-        fftbuf = self._buf("recv", (self.mmax + 1) * nc * self.nloc)
-        self.lib.check(L.pixsht_stage_map2phase(self.handle, nc, self._slab_base_ptrs(d_map_slabs), ctypes.c_void_p(self.d_m_row.data_ptr()),
-                                                self.r0, self.nloc, ctypes.c_void_p(fftbuf.data_ptr()), st))
+        self.lib.check(L.pixsht_stage_map2phase(self.handle, nc, self._slab_base_ptrs(d_map_slabs), self.r0, self.nloc,
+                                                ctypes.c_void_p(self.own_ptr), st))
         ev.append(self._ev())
-        in_splits = [len(ml) * nc * self.nloc for ml in self.m_lists]           # rows of rank g are a contiguous block
-        out_splits = [self.nm * nc * (b - a) for (a, b) in self.ring_ranges]
-        recv = self._buf("send", self.nm * nc * nr)
-        self._exchange(fftbuf, recv, in_splits, out_splits)
-        # unpack: from each source h [mi][c][ring in slab h] -> [mi][c][ring]
-        legbuf = self._buf("leg", self.nm * nc * nr)
-        v = legbuf.view(self.nm, nc, nr)
-        off = 0
-        for (a, b), n in zip(self.ring_ranges, out_splits):
-            v[:, :, a:b].copy_(recv[off:off + n].view(self.nm, nc, b - a))
-            off += n
+        self._barrier()          # every ring's row is complete on its owner
         ev.append(self._ev())
         for t in d_alms:
             t.zero_()   # the analysis kernels accumulate atomically into pre-zeroed columns
-        self.lib.check(L.pixsht_stage_phase2alm(self.handle, nc, ctypes.c_void_p(legbuf.data_ptr()), self.nm,
+        self.lib.check(L.pixsht_stage_phase2alm(self.handle, nc, ctypes.c_void_p(table.data_ptr()), self.nm,
                                                 ctypes.c_void_p(self.d_m_list.data_ptr()), self._ptrs(d_alms), st))
         ev.append(self._ev())
         self._record("map2alm", ev)
@@ -201,7 +225,7 @@ class ShardedSHT:
         self.last_ms[name] = ev
 
     def stage_ms(self, name):
-        """Device milliseconds of the three stages of the last call (Legendre/FFT first, exchange, FFT/Legendre last)."""
+        """Device milliseconds of the three stages of the last call (Legendre/FFT first, barrier, FFT/Legendre last)."""
         ev = self.last_ms.get(name)
         if not ev or ev[0] is None:
             return None

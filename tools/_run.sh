@@ -1,3 +1,5 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --workload C3 --steps 2 --warmup 2 > gpurun_out/bench_c3_n2.log 2>&1; tail -2 gpurun_out/bench_c3_n2.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 2 --warmup 2 > gpurun_out/bench_c4_n2.log 2>&1; tail -2 gpurun_out/bench_c4_n2.log
-nvidia-smi topo -m > gpurun_out/topo.txt 2>&1
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --workload C3 --steps 2 --warmup 2 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_c3_v5.log; python -c "
+import json; d=json.loads(open('gpurun_out/bench_c3_v5.log').read()); print(d['value'], d['stages'], d['roofline']['frac'], d['roofline_fft'], d['e2e'])"
+python bench.py --workload C4 --steps 2 --warmup 2 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_c4_v5.log; python -c "
+import json; d=json.loads(open('gpurun_out/bench_c4_v5.log').read()); print(d['value'], d['stages'], d['roofline']['frac'], d['roofline_fft'], d['e2e'])"

@@ -72,7 +72,9 @@ int pixsht_execute(pixsht_plan *plan, int direction, int ncomp, void *const *alm
 int pixsht_plan_set_stream(pixsht_plan *plan, void *stream, int use_caller_stream);
 
 /* per-stage device time (ms, CUDA events) of the last pixsht_execute on this plan:
- * [0] h2d copy, [1] Legendre stage, [2] FFT stage, [3] d2h copy, [4] whole call (host wall clock), [5..7] reserved */
+ * device pointers: [1] Legendre stage, [2] FFT stage, [4] whole call (host wall clock);
+ * host pointers (copies, Legendre and FFT are pipelined over three streams, so stages overlap): [4] whole call,
+ * [5] span of the compute stream; the rest 0 */
 int pixsht_get_timings(const pixsht_plan *plan, double ms[8]);
 
 /* ---- stage API for the m-sharded multi-GPU pipeline (device pointers, asynchronous on `stream`) ------------

@@ -39,7 +39,7 @@ struct FftParams {
     int mmax;
     double2* phase;             // this launch's rows: (ringlocal, c, m) at ((ringlocal*ncomp + c)*MP + m)
     long long MP;
-    int ncomp;
+    int ncomp, c_begin;         // components per ring in the phase buffer; first component handled by this launch (grid.y of them)
     int ring_begin, ring_count; // band rings handled by this launch; ringlocal = ring - ring_begin
     int nx, ny, flipx, flipy;   // caller's map layout (column-major nx x ny), see pixsht_geom
     void* maps[3];
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
 {
     PIXSHT_DYN_SMEM(smem_raw);
     cpx<T>* buf = reinterpret_cast<cpx<T>*>(smem_raw);   // n + 1 entries
-    const int rl = blockIdx.x, c = blockIdx.y, ring = P.ring_begin + rl;
+    const int rl = blockIdx.x, c = P.c_begin + blockIdx.y, ring = P.ring_begin + rl;
     const int n = P.n;
     const double2* row = P.phase + ((long long)rl * P.ncomp + c) * P.MP;
 
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams 
 {
     PIXSHT_DYN_SMEM(smem_raw);
     cpx<T>* buf = reinterpret_cast<cpx<T>*>(smem_raw);   // n + 1 entries
-    const int rl = blockIdx.x, c = blockIdx.y, ring = P.ring_begin + rl;
+    const int rl = blockIdx.x, c = P.c_begin + blockIdx.y, ring = P.ring_begin + rl;
     const int n = P.n, N = P.nphi;
     const T* in = reinterpret_cast<const T*>(P.maps[c]);
     const int rowy = P.flipy ? (P.ny - 1 - ring) : ring;

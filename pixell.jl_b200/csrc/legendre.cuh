@@ -40,8 +40,10 @@ constexpr int L_NEVER = 0x3fffffff;
 struct LegParams {
     int lmax, mmax;
     int nm;                 // number of m values handled by this launch
-    const int* m_list;      // device; nullptr => m = row index
-    int npairs, nchunks;    // ring pairs; chunks of 32*R pairs per m
+    const int* m_list;      // device; nullptr => m = m_begin + row index
+    int m_begin;
+    int npairs, nchunks;    // ring pairs; this launch handles nchunks chunks of 32*R pairs per m, starting at chunk_begin
+    int chunk_begin;
     const double* x;        // [npairs] cos(theta) of the pair's northern member
     const int* ringN; const int* ringS;           // band ring index of the north/south member, -1 if absent
     const int* lact;        // [(mmax+1) * npairs] first l at which the pair contributes, L_NEVER if none
@@ -351,8 +353,8 @@ __global__ void __launch_bounds__(LEG_NT) leg_synth(const LegParams P)
     __shared__ __align__(8) unsigned long long sbar[2];
     const int lane = threadIdx.x;
     const int row = blockIdx.x / P.nchunks;
-    const int chunk = P.nchunks - 1 - (int)(blockIdx.x % P.nchunks);   // equator-side (longest) units first
-    const int m = P.m_list ? P.m_list[row] : row;
+    const int chunk = P.chunk_begin + P.nchunks - 1 - (int)(blockIdx.x % P.nchunks);   // equator-side (longest) units first
+    const int m = P.m_list ? P.m_list[row] : (P.m_begin + row);
     const int l0 = (SPIN == 0) ? m : (m > 2 ? m : 2);
     const int pair0 = chunk * (32 * R);
 
@@ -481,8 +483,8 @@ __global__ void __launch_bounds__(LEG_NT) leg_anal(const LegParams P)
     __shared__ __align__(8) unsigned long long sbar[2];
     const int lane = threadIdx.x;
     const int row = blockIdx.x / P.nchunks;
-    const int chunk = P.nchunks - 1 - (int)(blockIdx.x % P.nchunks);
-    const int m = P.m_list ? P.m_list[row] : row;
+    const int chunk = P.chunk_begin + P.nchunks - 1 - (int)(blockIdx.x % P.nchunks);
+    const int m = P.m_list ? P.m_list[row] : (P.m_begin + row);
     const int l0 = (SPIN == 0) ? m : (m > 2 ? m : 2);
     const int pair0 = chunk * (32 * R);
 

@@ -7,6 +7,7 @@
 #include "../../include/pixsht.h"
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <mutex>
 #include <string>
@@ -76,7 +77,10 @@ struct pixsht_plan {
     DevBuf<double2> d_phase; int phase_ncomp = 0;
     DevBuf<unsigned char> d_map[3], d_alm[3];
     DevBuf<double2> d_alm64[3];
-    cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t dep[48] = {nullptr};   // dependency events of the pipelined host path
+    std::vector<int> h_ringN, h_ringS;
+    int nsplit = 8;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     double timings[8] = {0};
     int launches = 0;
@@ -288,6 +292,11 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     if (rc) return fail(PIXSHT_ERR_NOMEM, "device allocation of plan tables failed");
 
     CU(cudaStreamCreateWithFlags(&P->own_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&P->s_h2d, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&P->s_d2h, cudaStreamNonBlocking));
+    for (auto& e : P->dep) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    P->h_ringN = ringN; P->h_ringS = ringS;
+    { int v = env_int("PIXSHT_SPLITS", 4); P->nsplit = (v >= 1 && v <= 8) ? v : 4; }
     P->stream = P->own_stream;
     for (auto& e : P->ev) CU(cudaEventCreate(&e));
 
@@ -392,6 +401,9 @@ extern "C" void pixsht_plan_destroy(pixsht_plan* P)
     P->d_lact0.release(); P->d_lact2.release(); P->d_st0.release(); P->d_st2.release();
     for (int c = 0; c < 3; ++c) { P->d_map[c].release(); P->d_alm[c].release(); P->d_alm64[c].release(); }
     for (auto& e : P->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : P->dep) if (e) cudaEventDestroy(e);
+    if (P->s_h2d) cudaStreamDestroy(P->s_h2d);
+    if (P->s_d2h) cudaStreamDestroy(P->s_d2h);
     if (P->own_stream) cudaStreamDestroy(P->own_stream);
     (void)cudaGetLastError();
     delete P;
@@ -427,16 +439,22 @@ static int ensure_seek(pixsht_plan* P, int spin, cudaStream_t st)
 // where the phase rows of a launch live: a local buffer (ring r at phase + r*ncomp*MP) or a per-ring pointer table
 struct PhaseRef { double2* phase; double2* const* ring_ptr; };
 
-static LegParams leg_params(pixsht_plan* P, int spin, int R, int nm, const int* d_m_list, PhaseRef ph, int ncomp, int c0)
+// one Legendre launch: m values [m_begin, m_begin+nm) (or m_list[0..nm)), chunks [chunk_begin, chunk_begin+nchunks) of 32*R pairs
+struct LegJob { int spin, ncomp, c0; int m_begin, nm; const int* m_list; int chunk_begin, nchunks; PhaseRef ph; };
+
+static int leg_R(const pixsht_plan* P, int spin, bool anal) { return spin == 0 ? (anal ? P->R0a : P->R0) : (anal ? P->R2a : P->R2); }
+static int leg_total_chunks(const pixsht_plan* P, int R) { return (P->npairs + 32 * R - 1) / (32 * R); }
+
+static LegParams leg_params(pixsht_plan* P, const LegJob& J, int R)
 {
     LegParams L;
     memset(&L, 0, sizeof(L));
-    L.lmax = P->lmax; L.mmax = P->mmax; L.nm = nm; L.m_list = d_m_list;
-    L.npairs = P->npairs; L.nchunks = (P->npairs + 32 * R - 1) / (32 * R);
+    L.lmax = P->lmax; L.mmax = P->mmax; L.nm = J.nm; L.m_list = J.m_list; L.m_begin = J.m_begin;
+    L.npairs = P->npairs; L.nchunks = J.nchunks; L.chunk_begin = J.chunk_begin;
     L.x = P->d_x.p; L.ringN = P->d_ringN.p; L.ringS = P->d_ringS.p;
-    if (spin == 0) { L.lact = P->d_lact0.p; L.st = P->d_st0.p; L.ad = P->d_ad0.p; L.gamma = P->d_gamma0.p; L.rec = P->d_rec0.p; }
+    if (J.spin == 0) { L.lact = P->d_lact0.p; L.st = P->d_st0.p; L.ad = P->d_ad0.p; L.gamma = P->d_gamma0.p; L.rec = P->d_rec0.p; }
     else { L.lact = P->d_lact2.p; L.st = P->d_st2.p; L.ad = P->d_ad2.p; L.gamma = P->d_gamma2.p; L.rec = P->d_rec2.p; }
-    L.phase = ph.phase; L.ring_ptr = ph.ring_ptr; L.ring_stride = (long long)ncomp * P->MP; L.MP = P->MP; L.c0 = c0;
+    L.phase = J.ph.phase; L.ring_ptr = J.ph.ring_ptr; L.ring_stride = (long long)J.ncomp * P->MP; L.MP = P->MP; L.c0 = J.c0;
     return L;
 }
 
@@ -444,6 +462,7 @@ template <int SPIN>
 static void launch_synth(pixsht_plan* P, int R, const LegParams& L, cudaStream_t st)
 {
     const int grid = L.nm * L.nchunks;
+    if (grid <= 0) return;
     void (*k)(const LegParams) = (R == 1) ? leg_synth<SPIN, 1> : (R == 2 ? leg_synth<SPIN, 2> : (R == 3 ? leg_synth<SPIN, 3> :
                                  (R == 8 && SPIN == 0 ? leg_synth<0, 8> : (R == 6 && SPIN == 0 ? leg_synth<0, 6> : leg_synth<SPIN, 4>))));
     PIXSHT_LAUNCH(k, grid, LEG_NT, 0, st, L);
@@ -453,69 +472,95 @@ template <int SPIN>
 static void launch_anal(pixsht_plan* P, int R, const LegParams& L, cudaStream_t st)
 {
     const int grid = L.nm * L.nchunks;
+    if (grid <= 0) return;
     void (*k)(const LegParams) = (R == 1) ? leg_anal<SPIN, 1> : (R == 2 ? leg_anal<SPIN, 2> : (R == 3 ? leg_anal<SPIN, 3> :
                                  (R == 8 && SPIN == 0 ? leg_anal<0, 8> : (R == 6 && SPIN == 0 ? leg_anal<0, 6> : leg_anal<SPIN, 4>))));
     PIXSHT_LAUNCH(k, grid, LEG_NT, 0, st, L);
     P->launches++;
 }
 
+// per-call pre-scaling of the alm of one spin family into the synthesis records (needs the whole alm of that family)
+static int synth_prep(pixsht_plan* P, int spin, const double2* a0, const double2* a1, cudaStream_t st)
+{
+    const int prep_grid = P->sm_count > 0 ? P->sm_count * 8 : 256;
+    int rc = ensure_seek(P, spin, st); if (rc) return rc;
+    if (spin == 0) {
+        if (P->d_rec0.n < (size_t)P->nalm * 4 && P->d_rec0.alloc((size_t)P->nalm * 4)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
+        PIXSHT_LAUNCH(k_prep_synth<0>, prep_grid, 256, 0, st, P->nalm, P->lmax, P->d_ad0.p, P->d_gamma0.p, a0, a0, P->d_rec0.p);
+    } else {
+        if (P->d_rec2.n < (size_t)P->nalm * 6 && P->d_rec2.alloc((size_t)P->nalm * 6)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
+        PIXSHT_LAUNCH(k_prep_synth<2>, prep_grid, 256, 0, st, P->nalm, P->lmax, P->d_ad2.p, P->d_gamma2.p, a0, a1, P->d_rec2.p);
+    }
+    P->launches++;
+    CU(cudaGetLastError());
+    return PIXSHT_OK;
+}
+static int synth_launch(pixsht_plan* P, const LegJob& J, cudaStream_t st)
+{
+    const int R = leg_R(P, J.spin, false);
+    LegParams L = leg_params(P, J, R);
+    if (J.spin == 0) launch_synth<0>(P, R, L, st); else launch_synth<2>(P, R, L, st);
+    CU(cudaGetLastError());
+    return PIXSHT_OK;
+}
+static int anal_launch(pixsht_plan* P, const LegJob& J, double2* out0, double2* out1, cudaStream_t st)
+{
+    int rc = ensure_seek(P, J.spin, st); if (rc) return rc;
+    const int R = leg_R(P, J.spin, true);
+    LegParams L = leg_params(P, J, R);
+    L.alm_out0 = out0; L.alm_out1 = out1;
+    if (J.spin == 0) launch_anal<0>(P, R, L, st); else launch_anal<2>(P, R, L, st);
+    CU(cudaGetLastError());
+    return PIXSHT_OK;
+}
+
 // alm component layout per ncomp: ncomp 1: [T]; 2: [E,B]; 3: [T,E,B].  phase/map components likewise [T] / [Q,U] / [T,Q,U].
 static int stage_alm2phase(pixsht_plan* P, int ncomp, const double2* const* alm, int nm, const int* d_m_list, PhaseRef ph, cudaStream_t st)
 {
-    const int prep_grid = P->sm_count > 0 ? P->sm_count * 8 : 256;
     if (ncomp == 1 || ncomp == 3) {
-        { int rc = ensure_seek(P, 0, st); if (rc) return rc; }
-        if (P->d_rec0.n < (size_t)P->nalm * 4 && P->d_rec0.alloc((size_t)P->nalm * 4)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
-        PIXSHT_LAUNCH(k_prep_synth<0>, prep_grid, 256, 0, st, P->nalm, P->lmax, P->d_ad0.p, P->d_gamma0.p, alm[0], alm[0], P->d_rec0.p);
-        P->launches++;
-        LegParams L = leg_params(P, 0, P->R0, nm, d_m_list, ph, ncomp, 0);
-        launch_synth<0>(P, P->R0, L, st);
+        int rc = synth_prep(P, 0, alm[0], alm[0], st); if (rc) return rc;
+        const LegJob J = {0, ncomp, 0, 0, nm, d_m_list, 0, leg_total_chunks(P, P->R0), ph};
+        rc = synth_launch(P, J, st); if (rc) return rc;
     }
     if (ncomp >= 2) {
         const int c0 = ncomp == 3 ? 1 : 0;
-        { int rc = ensure_seek(P, 2, st); if (rc) return rc; }
-        if (P->d_rec2.n < (size_t)P->nalm * 6 && P->d_rec2.alloc((size_t)P->nalm * 6)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
-        PIXSHT_LAUNCH(k_prep_synth<2>, prep_grid, 256, 0, st, P->nalm, P->lmax, P->d_ad2.p, P->d_gamma2.p, alm[c0], alm[c0 + 1], P->d_rec2.p);
-        P->launches++;
-        LegParams L = leg_params(P, 2, P->R2, nm, d_m_list, ph, ncomp, c0);
-        launch_synth<2>(P, P->R2, L, st);
+        int rc = synth_prep(P, 2, alm[c0], alm[c0 + 1], st); if (rc) return rc;
+        const LegJob J = {2, ncomp, c0, 0, nm, d_m_list, 0, leg_total_chunks(P, P->R2), ph};
+        rc = synth_launch(P, J, st); if (rc) return rc;
     }
-    CU(cudaGetLastError());
     return PIXSHT_OK;
 }
 
 static int stage_phase2alm(pixsht_plan* P, int ncomp, PhaseRef ph, int nm, const int* d_m_list, double2* const* alm, cudaStream_t st)
 {
     if (ncomp == 1 || ncomp == 3) {
-        { int rc = ensure_seek(P, 0, st); if (rc) return rc; }
-        LegParams L = leg_params(P, 0, P->R0a, nm, d_m_list, ph, ncomp, 0);
-        L.alm_out0 = alm[0];
-        launch_anal<0>(P, P->R0a, L, st);
+        const LegJob J = {0, ncomp, 0, 0, nm, d_m_list, 0, leg_total_chunks(P, P->R0a), ph};
+        int rc = anal_launch(P, J, alm[0], nullptr, st); if (rc) return rc;
     }
     if (ncomp >= 2) {
         const int c0 = ncomp == 3 ? 1 : 0;
-        { int rc = ensure_seek(P, 2, st); if (rc) return rc; }
-        LegParams L = leg_params(P, 2, P->R2a, nm, d_m_list, ph, ncomp, c0);
-        L.alm_out0 = alm[c0]; L.alm_out1 = alm[c0 + 1];
-        launch_anal<2>(P, P->R2a, L, st);
+        const LegJob J = {2, ncomp, c0, 0, nm, d_m_list, 0, leg_total_chunks(P, P->R2a), ph};
+        int rc = anal_launch(P, J, alm[c0], alm[c0 + 1], st); if (rc) return rc;
     }
-    CU(cudaGetLastError());
     return PIXSHT_OK;
 }
 
-static int stage_fft(pixsht_plan* P, int dir, int ncomp, double2* phase, int ring_begin, int ring_count, void* const* maps, cudaStream_t st)
+// FFT stage for components [c_begin, c_begin+c_count) of band rings [ring_begin, ring_begin+ring_count); `phase` points at the
+// row of (ring_begin, component 0) in a buffer with ncomp components per ring
+static int stage_fft(pixsht_plan* P, int dir, int ncomp, int c_begin, int c_count, double2* phase, int ring_begin, int ring_count,
+                     void* const* maps, cudaStream_t st)
 {
-    if (ring_count <= 0) return PIXSHT_OK;
+    if (ring_count <= 0 || c_count <= 0) return PIXSHT_OK;
     FftParams F;
     memset(&F, 0, sizeof(F));
     F.nphi = P->nphi; F.n = P->nfft; F.nfac = P->nfac;
     for (int i = 0; i < P->nfac; ++i) { F.fac[i] = P->fac[i]; F.magic[i] = P->fft_magic[i]; }
     F.tw = P->d_tw.p; F.phi0tw = P->d_phi0tw.p; F.wgt = P->d_wgt.p; F.perm = P->d_perm.p; F.mmax = P->mmax;
-    F.phase = phase; F.MP = P->MP; F.ncomp = ncomp;
+    F.phase = phase; F.MP = P->MP; F.ncomp = ncomp; F.c_begin = c_begin;
     F.ring_begin = ring_begin; F.ring_count = ring_count;
     F.nx = P->nx; F.ny = P->ny; F.flipx = P->flipx; F.flipy = P->flipy;
     for (int c = 0; c < ncomp; ++c) F.maps[c] = maps[c];
-    dim3 grid(ring_count, ncomp);
+    dim3 grid(ring_count, c_count);
     if (P->dtype == PIXSHT_F64) {
         if (dir == PIXSHT_ALM2MAP) PIXSHT_LAUNCH(fft_phase2map<double>, grid, P->fft_threads, P->fft_smem, st, F);
         else PIXSHT_LAUNCH(fft_map2phase<double>, grid, P->fft_threads, P->fft_smem, st, F);
@@ -539,6 +584,183 @@ static int ensure_phase(pixsht_plan* P, int ncomp)
 // ---------------------------------------------------------------------------------------------------------------
 // pixsht_execute
 // ---------------------------------------------------------------------------------------------------------------
+// Band-ring ranges covered by the pair range [p0, p1): at most one range of northern and one of southern members when
+// the pairs are contiguous on the sky (always the case for CAR bands).  Returns false when they are not.
+static bool pair_range_rings(const pixsht_plan* P, int p0, int p1, int rng[2][2])
+{
+    for (int h = 0; h < 2; ++h) {
+        const std::vector<int>& v = h == 0 ? P->h_ringN : P->h_ringS;
+        int lo = 1 << 30, hi = -1, cnt = 0;
+        for (int p = p0; p < p1; ++p) if (v[p] >= 0) { lo = std::min(lo, v[p]); hi = std::max(hi, v[p]); ++cnt; }
+        if (cnt == 0) { rng[h][0] = 0; rng[h][1] = 0; continue; }
+        if (hi - lo + 1 != cnt) return false;
+        rng[h][0] = lo; rng[h][1] = hi + 1;
+    }
+    return true;
+}
+
+// rows of the caller's map for band rings [r0, r1): one contiguous block (the y flip only mirrors it)
+static void ring_rows(const pixsht_plan* P, int r0, int r1, size_t esz, size_t& off_bytes, size_t& nbytes)
+{
+    const int row0 = P->flipy ? (P->ny - r1) : r0;
+    off_bytes = (size_t)row0 * P->nx * esz; nbytes = (size_t)(r1 - r0) * P->nx * esz;
+}
+
+// Host-pointer transform: copies, Legendre and FFT launches are pipelined over three streams so that most of the PCIe
+// time hides under the Legendre kernels (spin-0 work runs while the polarisation inputs arrive; results leave in
+// split-sized pieces while the next split computes).
+static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* alms, void* const* maps)
+{
+    cudaStream_t sc = P->stream, sh = P->s_h2d, sd = P->s_d2h;
+    const bool f32 = P->dtype == PIXSHT_F32;
+    const size_t esz = f32 ? 4 : 8;
+    const size_t map_bytes = (size_t)P->nx * P->ny * esz, alm_bytes = (size_t)P->nalm * 2 * esz;
+    const int cvt_grid = P->sm_count > 0 ? P->sm_count * 8 : 256;
+    void* dmap[3] = {nullptr, nullptr, nullptr};
+    void* dalm[3] = {nullptr, nullptr, nullptr};
+    double2* dalm64[3] = {nullptr, nullptr, nullptr};
+    for (int c = 0; c < ncomp; ++c) {
+        if (P->d_map[c].n < map_bytes && P->d_map[c].alloc(map_bytes)) return fail(PIXSHT_ERR_NOMEM, "map staging allocation failed");
+        if (P->d_alm[c].n < alm_bytes && P->d_alm[c].alloc(alm_bytes)) return fail(PIXSHT_ERR_NOMEM, "alm staging allocation failed");
+        dmap[c] = P->d_map[c].p; dalm[c] = P->d_alm[c].p;
+        if (f32) {
+            if (P->d_alm64[c].n < (size_t)P->nalm && P->d_alm64[c].alloc(P->nalm)) return fail(PIXSHT_ERR_NOMEM, "alm work buffer allocation failed");
+            dalm64[c] = P->d_alm64[c].p;
+        } else dalm64[c] = reinterpret_cast<double2*>(dalm[c]);
+    }
+    const PhaseRef ph = {P->d_phase.p, nullptr};
+    int ndep = 0;
+    auto next_ev = [&]() { return P->dep[ndep++ % 48]; };
+    const int c0 = ncomp == 3 ? 1 : 0;          // first spin-2 component
+    const bool has0 = ncomp != 2, has2 = ncomp >= 2;
+    int rc;
+
+    // the copy streams start after whatever the caller queued on the compute stream
+    cudaEvent_t e_start = next_ev();
+    CU(cudaEventRecord(e_start, sc));
+    CU(cudaStreamWaitEvent(sh, e_start, 0));
+    CU(cudaStreamWaitEvent(sd, e_start, 0));
+    CU(cudaEventRecord(P->ev[0], sc));
+
+    if (direction == PIXSHT_ALM2MAP) {
+        cudaEvent_t e_in[3];
+        for (int c = 0; c < ncomp; ++c) {
+            CU(cudaMemcpyAsync(dalm[c], alms[c], alm_bytes, cudaMemcpyHostToDevice, sh));
+            e_in[c] = next_ev(); CU(cudaEventRecord(e_in[c], sh));
+        }
+        auto cvt_in = [&](int c) {
+            if (f32) { PIXSHT_LAUNCH(k_cvt_f32_to_f64, cvt_grid, 256, 0, sc, (const float*)dalm[c], (double*)dalm64[c], 2 * P->nalm); P->launches++; }
+        };
+        // FFT + D2H of components [cb, cb+cn) for band rings [r0, r1)
+        auto emit_rings = [&](int cb, int cn, int r0, int r1) -> int {
+            if (r1 <= r0) return PIXSHT_OK;
+            int rc2 = stage_fft(P, PIXSHT_ALM2MAP, ncomp, cb, cn, P->d_phase.p + (long long)r0 * ncomp * P->MP, r0, r1 - r0, dmap, sc);
+            if (rc2) return rc2;
+            cudaEvent_t e = next_ev();
+            CU(cudaEventRecord(e, sc));
+            CU(cudaStreamWaitEvent(sd, e, 0));
+            size_t off, nb; ring_rows(P, r0, r1, esz, off, nb);
+            for (int c = cb; c < cb + cn; ++c)
+                CU(cudaMemcpyAsync((char*)maps[c] + off, (char*)dmap[c] + off, nb, cudaMemcpyDeviceToHost, sd));
+            return PIXSHT_OK;
+        };
+        if (has0) {
+            CU(cudaStreamWaitEvent(sc, e_in[0], 0));
+            cvt_in(0);
+            rc = synth_prep(P, 0, dalm64[0], dalm64[0], sc); if (rc) return rc;
+            const LegJob J = {0, ncomp, 0, 0, P->mmax + 1, nullptr, 0, leg_total_chunks(P, P->R0), ph};
+            rc = synth_launch(P, J, sc); if (rc) return rc;
+            rc = emit_rings(0, 1, 0, P->nrings); if (rc) return rc;
+        }
+        if (has2) {
+            CU(cudaStreamWaitEvent(sc, e_in[c0], 0));
+            CU(cudaStreamWaitEvent(sc, e_in[c0 + 1], 0));
+            cvt_in(c0); cvt_in(c0 + 1);
+            rc = synth_prep(P, 2, dalm64[c0], dalm64[c0 + 1], sc); if (rc) return rc;
+            // splits of the ring pairs with equal Legendre work (work per pair ~ sin(theta)): polar side first, so that
+            // the last (exposed) piece of the map copy is the one with the fewest rings
+            const int R = P->R2, nch = leg_total_chunks(P, R);
+            int K = std::min(P->nsplit, nch);
+            std::vector<int> cb(K + 1);
+            for (int k = 0; k <= K; ++k) cb[k] = (int)std::lround(nch * (2.0 / 3.14159265358979323846) * std::acos(1.0 - (double)k / K));
+            cb[0] = 0; cb[K] = nch;
+            for (int k = 1; k <= K; ++k) cb[k] = std::max(cb[k], cb[k - 1]);
+            bool ok = true;
+            std::vector<std::array<int, 4>> rr(K);
+            for (int k = 0; k < K && ok; ++k) {
+                int rng[2][2];
+                ok = pair_range_rings(P, std::min(P->npairs, cb[k] * 32 * R), std::min(P->npairs, cb[k + 1] * 32 * R), rng);
+                rr[k] = {rng[0][0], rng[0][1], rng[1][0], rng[1][1]};
+            }
+            if (!ok) { K = 1; cb = {0, nch}; }
+            for (int k = 0; k < K; ++k) {
+                const LegJob J = {2, ncomp, c0, 0, P->mmax + 1, nullptr, cb[k], cb[k + 1] - cb[k], ph};
+                rc = synth_launch(P, J, sc); if (rc) return rc;
+                if (ok) {
+                    rc = emit_rings(c0, 2, rr[k][0], rr[k][1]); if (rc) return rc;
+                    rc = emit_rings(c0, 2, rr[k][2], rr[k][3]); if (rc) return rc;
+                } else { rc = emit_rings(c0, 2, 0, P->nrings); if (rc) return rc; }
+            }
+        }
+    } else {
+        cudaEvent_t e_in[3];
+        for (int c = 0; c < ncomp; ++c) {
+            CU(cudaMemcpyAsync(dmap[c], maps[c], map_bytes, cudaMemcpyHostToDevice, sh));
+            e_in[c] = next_ev(); CU(cudaEventRecord(e_in[c], sh));
+        }
+        // conversion + D2H of the alm columns of m in [m0, m1) for components [cb, cb+cn)
+        auto emit_alm = [&](int cb, int cn, int m0, int m1) -> int {
+            if (m1 <= m0) return PIXSHT_OK;
+            const long long i0 = alm_index(P->lmax, m0, m0), i1 = (m1 > P->mmax) ? P->nalm : alm_index(P->lmax, m1, m1);
+            if (f32)
+                for (int c = cb; c < cb + cn; ++c) {
+                    PIXSHT_LAUNCH(k_cvt_f64_to_f32, cvt_grid, 256, 0, sc, (const double*)(dalm64[c] + i0), (float*)dalm[c] + 2 * i0, 2 * (i1 - i0));
+                    P->launches++;
+                }
+            cudaEvent_t e = next_ev();
+            CU(cudaEventRecord(e, sc));
+            CU(cudaStreamWaitEvent(sd, e, 0));
+            for (int c = cb; c < cb + cn; ++c)
+                CU(cudaMemcpyAsync((char*)alms[c] + (size_t)i0 * 2 * esz, (char*)dalm[c] + (size_t)i0 * 2 * esz, (size_t)(i1 - i0) * 2 * esz, cudaMemcpyDeviceToHost, sd));
+            return PIXSHT_OK;
+        };
+        for (int c = 0; c < ncomp; ++c) CU(cudaMemsetAsync(dalm64[c], 0, (size_t)P->nalm * sizeof(double2), sc));
+        if (has0) {
+            CU(cudaStreamWaitEvent(sc, e_in[0], 0));
+            rc = stage_fft(P, PIXSHT_MAP2ALM, ncomp, 0, 1, P->d_phase.p, 0, P->nrings, dmap, sc); if (rc) return rc;
+            const LegJob J = {0, ncomp, 0, 0, P->mmax + 1, nullptr, 0, leg_total_chunks(P, P->R0a), ph};
+            rc = anal_launch(P, J, dalm64[0], nullptr, sc); if (rc) return rc;
+            rc = emit_alm(0, 1, 0, P->mmax + 1); if (rc) return rc;
+        }
+        if (has2) {
+            CU(cudaStreamWaitEvent(sc, e_in[c0], 0));
+            CU(cudaStreamWaitEvent(sc, e_in[c0 + 1], 0));
+            rc = stage_fft(P, PIXSHT_MAP2ALM, ncomp, c0, 2, P->d_phase.p, 0, P->nrings, dmap, sc); if (rc) return rc;
+            // splits of m with equal Legendre work (work per m ~ lmax - m + 1), ascending: the last piece is the smallest
+            const int K = std::min(P->nsplit, P->mmax + 1);
+            std::vector<int> mb(K + 1);
+            for (int k = 0; k <= K; ++k) mb[k] = (int)std::lround((P->mmax + 1) * (1.0 - std::sqrt(1.0 - (double)k / K)));
+            mb[0] = 0; mb[K] = P->mmax + 1;
+            for (int k = 1; k <= K; ++k) mb[k] = std::max(mb[k], mb[k - 1]);
+            for (int k = 0; k < K; ++k) {
+                const LegJob J = {2, ncomp, c0, mb[k], mb[k + 1] - mb[k], nullptr, 0, leg_total_chunks(P, P->R2a), ph};
+                rc = anal_launch(P, J, dalm64[c0], dalm64[c0 + 1], sc); if (rc) return rc;
+                rc = emit_alm(c0, 2, mb[k], mb[k + 1]); if (rc) return rc;
+            }
+        }
+    }
+    CU(cudaEventRecord(P->ev[1], sc));
+    CU(cudaStreamSynchronize(sh));
+    CU(cudaStreamSynchronize(sc));
+    CU(cudaStreamSynchronize(sd));
+    CU(cudaGetLastError());
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, P->ev[0], P->ev[1]));
+    for (auto& t : P->timings) t = 0;
+    P->timings[5] = ms;   // compute stream busy span (copies overlap it)
+    return PIXSHT_OK;
+}
+
 extern "C" int pixsht_execute(pixsht_plan* P, int direction, int ncomp, void* const* alms, void* const* maps, int location)
 {
     if (!P || !alms || !maps) return fail(PIXSHT_ERR_ARG, "null argument");
@@ -549,22 +771,20 @@ extern "C" int pixsht_execute(pixsht_plan* P, int direction, int ncomp, void* co
     std::lock_guard<std::mutex> lock(P->mu);
     int rc = check_device(P->device); if (rc) return rc;
     const auto t_begin = std::chrono::steady_clock::now();
-    cudaStream_t st = P->stream;
-    const bool f32 = P->dtype == PIXSHT_F32;
-    const size_t esz = f32 ? 4 : 8;
-    const size_t map_bytes = (size_t)P->nx * P->ny * esz, alm_bytes = (size_t)P->nalm * 2 * esz;
     P->launches = 0;
     rc = ensure_phase(P, ncomp); if (rc) return rc;
-
+    if (location == PIXSHT_HOST) {
+        rc = execute_host(P, direction, ncomp, alms, maps);
+        P->timings[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        return rc;
+    }
+    cudaStream_t st = P->stream;
+    const bool f32 = P->dtype == PIXSHT_F32;
     void* dmap[3] = {nullptr, nullptr, nullptr};
     void* dalm[3] = {nullptr, nullptr, nullptr};     // boundary dtype
     double2* dalm64[3] = {nullptr, nullptr, nullptr}; // what the Legendre kernels see
     for (int c = 0; c < ncomp; ++c) {
-        if (location == PIXSHT_HOST) {
-            if (P->d_map[c].n < map_bytes && P->d_map[c].alloc(map_bytes)) return fail(PIXSHT_ERR_NOMEM, "map staging allocation failed");
-            if (P->d_alm[c].n < alm_bytes && P->d_alm[c].alloc(alm_bytes)) return fail(PIXSHT_ERR_NOMEM, "alm staging allocation failed");
-            dmap[c] = P->d_map[c].p; dalm[c] = P->d_alm[c].p;
-        } else { dmap[c] = maps[c]; dalm[c] = alms[c]; }
+        dmap[c] = maps[c]; dalm[c] = alms[c];
         if (f32) {
             if (P->d_alm64[c].n < (size_t)P->nalm && P->d_alm64[c].alloc(P->nalm)) return fail(PIXSHT_ERR_NOMEM, "alm work buffer allocation failed");
             dalm64[c] = P->d_alm64[c].p;
@@ -574,10 +794,8 @@ extern "C" int pixsht_execute(pixsht_plan* P, int direction, int ncomp, void* co
     const int cvt_grid = P->sm_count > 0 ? P->sm_count * 8 : 256;
 
     CU(cudaEventRecord(P->ev[0], st));
+    CU(cudaEventRecord(P->ev[1], st));
     if (direction == PIXSHT_ALM2MAP) {
-        if (location == PIXSHT_HOST)
-            for (int c = 0; c < ncomp; ++c) CU(cudaMemcpyAsync(dalm[c], alms[c], alm_bytes, cudaMemcpyHostToDevice, st));
-        CU(cudaEventRecord(P->ev[1], st));
         if (f32)
             for (int c = 0; c < ncomp; ++c) {
                 PIXSHT_LAUNCH(k_cvt_f32_to_f64, cvt_grid, 256, 0, st, (const float*)dalm[c], (double*)dalm64[c], 2 * P->nalm);
@@ -585,16 +803,10 @@ extern "C" int pixsht_execute(pixsht_plan* P, int direction, int ncomp, void* co
             }
         rc = stage_alm2phase(P, ncomp, dalm64, P->mmax + 1, nullptr, ph, st); if (rc) return rc;
         CU(cudaEventRecord(P->ev[2], st));
-        rc = stage_fft(P, PIXSHT_ALM2MAP, ncomp, P->d_phase.p, 0, P->nrings, dmap, st); if (rc) return rc;
+        rc = stage_fft(P, PIXSHT_ALM2MAP, ncomp, 0, ncomp, P->d_phase.p, 0, P->nrings, dmap, st); if (rc) return rc;
         CU(cudaEventRecord(P->ev[3], st));
-        if (location == PIXSHT_HOST)
-            for (int c = 0; c < ncomp; ++c) CU(cudaMemcpyAsync(maps[c], dmap[c], map_bytes, cudaMemcpyDeviceToHost, st));
-        CU(cudaEventRecord(P->ev[4], st));
     } else {
-        if (location == PIXSHT_HOST)
-            for (int c = 0; c < ncomp; ++c) CU(cudaMemcpyAsync(dmap[c], maps[c], map_bytes, cudaMemcpyHostToDevice, st));
-        CU(cudaEventRecord(P->ev[1], st));
-        rc = stage_fft(P, PIXSHT_MAP2ALM, ncomp, P->d_phase.p, 0, P->nrings, dmap, st); if (rc) return rc;
+        rc = stage_fft(P, PIXSHT_MAP2ALM, ncomp, 0, ncomp, P->d_phase.p, 0, P->nrings, dmap, st); if (rc) return rc;
         CU(cudaEventRecord(P->ev[2], st));
         for (int c = 0; c < ncomp; ++c) CU(cudaMemsetAsync(dalm64[c], 0, (size_t)P->nalm * sizeof(double2), st));
         rc = stage_phase2alm(P, ncomp, ph, P->mmax + 1, nullptr, dalm64, st); if (rc) return rc;
@@ -604,10 +816,8 @@ extern "C" int pixsht_execute(pixsht_plan* P, int direction, int ncomp, void* co
                 P->launches++;
             }
         CU(cudaEventRecord(P->ev[3], st));
-        if (location == PIXSHT_HOST)
-            for (int c = 0; c < ncomp; ++c) CU(cudaMemcpyAsync(alms[c], dalm[c], alm_bytes, cudaMemcpyDeviceToHost, st));
-        CU(cudaEventRecord(P->ev[4], st));
     }
+    CU(cudaEventRecord(P->ev[4], st));
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
     float ms[4] = {0, 0, 0, 0};
@@ -678,7 +888,7 @@ extern "C" int pixsht_stage_phase2map(pixsht_plan* P, int ncomp, const void* d_p
 {
     int rc = stage_common(P, ncomp); if (rc) return rc;
     if (!d_maps || !d_phase || ring_begin < 0 || ring_count < 0 || ring_begin + ring_count > P->nrings) return fail(PIXSHT_ERR_ARG, "bad argument");
-    return stage_fft(P, PIXSHT_ALM2MAP, ncomp, (double2*)d_phase, ring_begin, ring_count, d_maps, (cudaStream_t)stream);
+    return stage_fft(P, PIXSHT_ALM2MAP, ncomp, 0, ncomp, (double2*)d_phase, ring_begin, ring_count, d_maps, (cudaStream_t)stream);
 }
 
 extern "C" int pixsht_stage_map2phase(pixsht_plan* P, int ncomp, const void* const* d_maps, int ring_begin, int ring_count,
@@ -686,7 +896,7 @@ extern "C" int pixsht_stage_map2phase(pixsht_plan* P, int ncomp, const void* con
 {
     int rc = stage_common(P, ncomp); if (rc) return rc;
     if (!d_maps || !d_phase || ring_begin < 0 || ring_count < 0 || ring_begin + ring_count > P->nrings) return fail(PIXSHT_ERR_ARG, "bad argument");
-    return stage_fft(P, PIXSHT_MAP2ALM, ncomp, (double2*)d_phase, ring_begin, ring_count, (void* const*)d_maps, (cudaStream_t)stream);
+    return stage_fft(P, PIXSHT_MAP2ALM, ncomp, 0, ncomp, (double2*)d_phase, ring_begin, ring_count, (void* const*)d_maps, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

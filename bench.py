@@ -174,8 +174,9 @@ def main():
             return
         vals = []
         base = None
+        per_step = max(1.0, min(8.0, 150.0 / max(1, args.warmup + args.steps)))   # the whole run stays within a few minutes
         for i in range(args.warmup + args.steps):
-            base = cpu_baseline(wl, target_s=8.0)
+            base = cpu_baseline(wl, target_s=per_step)
             if i >= args.warmup:
                 vals.append(base["value"])
         v = float(np.mean(vals))
@@ -247,7 +248,8 @@ def main():
         d_alm = [synth_alm_device(torch, nalm, lmax, seed0 + c, c > 0, device, cdt) for c in range(nc)]
         d_out = [torch.empty_like(a) for a in d_alm]
         d_map = [torch.empty(band.nx * band.nrings, dtype=rdt, device=device) for _ in range(nc)]
-        acc = {"leg": 0.0, "fft": 0.0, "n": 0, "launches": 0}
+        acc = {"leg": 0.0, "fft": 0.0, "n": 0, "launches": 0, "synth0": 0.0, "synth2": 0.0, "anal0": 0.0, "anal2": 0.0,
+               "fft_a2m": 0.0, "fft_m2a": 0.0}
 
         def step_dev():
             plan.execute_ptrs(ALM2MAP, [a.data_ptr() for a in d_alm], [m.data_ptr() for m in d_map], DEVICE)
@@ -255,17 +257,26 @@ def main():
             plan.execute_ptrs(MAP2ALM, [a.data_ptr() for a in d_out], [m.data_ptr() for m in d_map], DEVICE)
             t2 = plan.timings(); l2 = plan.info()["launches"]
             acc["leg"] += t1["legendre"] + t2["legendre"]; acc["fft"] += t1["fft"] + t2["fft"]; acc["n"] += 1
+            acc["synth0"] += t1["leg_spin0"]; acc["synth2"] += t1["leg_spin2"]; acc["anal0"] += t2["leg_spin0"]; acc["anal2"] += t2["leg_spin2"]
+            acc["fft_a2m"] += t1["fft"]; acc["fft_m2a"] += t2["fft"]
             acc["launches"] = l1 + l2
 
         clk = ClockSampler(local_rank); clk.start()
         for _ in range(args.warmup):
             step_dev(); flush_l2()
-        acc.update(leg=0.0, fft=0.0, n=0)
+        for k in list(acc):
+            acc[k] = 0 if k in ("n", "launches") else 0.0
         ms_dev = timed(step_dev, 0, args.steps)
         clocks = clk.stop()
         leg_ms, fft_ms = acc["leg"] / acc["n"], acc["fft"] / acc["n"]
         launches = acc["launches"] * args.steps
         stage = {"legendre_ms": leg_ms, "fft_ms": fft_ms}
+        kern_ms = {k: acc[k] / acc["n"] for k in ("synth0", "synth2", "anal0", "anal2", "fft_a2m", "fft_m2a")}
+        work = {}
+        if nc != 2:
+            work[0] = plan.work(0)
+        if nc >= 2:
+            work[2] = plan.work(2)
         h2d = d2h = 0
         e2e = None
         host_maps = host_alms = None
@@ -358,6 +369,7 @@ def main():
         nrings = band.nrings
         plan_info = {"npairs": math.ceil(nrings / 2), "sm_count": None}
         host_maps = host_alms = None
+        kern_ms, work = None, None
         sht.close()
 
     if rank != 0:
@@ -375,16 +387,47 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
     fp64_peak, fp32_peak = lib.measure_fma_peak(local_rank)
+    peak_src = ("pixsht_measure_fma_peak: FP64 FMA probe (16 independent accumulators per thread, one warp-uniform operand) "
+                "measured on this GPU in this run; datasheet FP64 vector peak 37.2 TFLOP/s at 1965 MHz; MEASURED_PEAKS.json has no FP64 figure")
     flops = 2.0 * algorithmic_flops(nalm, nrings, nc)            # both directions, all ranks together
     leg_tf = flops / world / (leg_ms * 1e-3) / 1e12             # per GPU
-    roofline = {"bound": "fp64_fma", "kernel": "leg_synth<0|2> + leg_anal<0|2> (Legendre stage, both directions)",
-                "achieved": leg_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": leg_tf / fp64_peak, "traffic": None,
-                "peak_source": "pixsht_measure_fma_peak: register-resident DFMA chain measured on this GPU in this run "
-                               "(datasheet FP64 vector peak 37 TFLOP/s); MEASURED_PEAKS.json has no FP64 figure",
-                "algorithmic_flop_per_step": flops, "note": "un-pruned, north/south-folded count of SURVEY.md 8(d); per GPU"}
+    stage_roof = {"kernel": "leg_synth<0|2> + leg_anal<0|2> (Legendre stage, both directions)", "achieved": leg_tf, "peak": fp64_peak,
+                  "unit": "TFLOP/s", "frac": leg_tf / fp64_peak, "algorithmic_flop_per_step": flops,
+                  "note": "un-pruned, north/south-folded count of SURVEY.md 8(d); per GPU"}
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01", "ncu_dram_traffic.json")) as f:
+            traffic = json.load(f).get(args.workload, {})
+    except Exception:
+        pass
+    if kern_ms is not None:
+        # per kernel: algorithmic flop = 2 * (4 | 12) * nominal (l, m, ring pair) steps; "executed" is the share
+        # of those steps the activation table lets the kernel run, so achieved * executed / peak is the FP64 pipe utilisation
+        kernels = []
+        for name, spin, key in (("leg_synth<0,%d>" % plan_info["R0"], 0, "synth0"), ("leg_synth<2,%d>" % plan_info["R2"], 2, "synth2"),
+                                ("leg_anal<0,%d>" % plan_info["R0a"], 0, "anal0"), ("leg_anal<2,%d>" % plan_info["R2a"], 2, "anal2")):
+            if spin not in work:
+                continue
+            ex, nom = work[spin]
+            fl = 2.0 * (4 if spin == 0 else 12) * nom
+            tf = fl / (kern_ms[key] * 1e-3) / 1e12
+            kernels.append({"kernel": name, "ms": kern_ms[key], "algorithmic_flop": fl, "achieved": tf, "frac": tf / fp64_peak,
+                            "executed_share": ex / nom, "fp64_pipe_utilisation": tf * ex / nom / fp64_peak,
+                            "traffic": traffic.get(name.split(",")[0] + ">")})
+        dom = max(kernels, key=lambda k: k["ms"])
+        roofline = {"bound": "fp64_fma", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peak_src,
+                    "algorithmic_flop_per_launch": dom["algorithmic_flop"], "executed_share": dom["executed_share"],
+                    "fp64_pipe_utilisation": dom["fp64_pipe_utilisation"], "launch_ms": dom["ms"],
+                    "note": "dominant kernel; algorithmic = un-pruned, north/south-folded count of SURVEY.md 8(d) (12 FP64 FMA-class ops per "
+                            "(l, m, ring pair) for spin 2); timed with CUDA events around the launch inside pixsht_execute",
+                    "kernels": kernels, "legendre_stage": stage_roof}
+    else:
+        roofline = dict(stage_roof, bound="fp64_fma", traffic=None, peak_source=peak_src)
     fft_bytes = 2.0 * (nc * band.nx * nrings * esz + nc * (lmax + 1) * nrings * 16)
     roofline_fft = {"bound": "hbm", "kernel": "fft_phase2map + fft_map2phase", "achieved": fft_bytes / world / (fft_ms * 1e-3) / 1e9,
-                    "peak": hbm_peak, "unit": "GB/s", "traffic": None, "peak_source": hbm_src}
+                    "peak": hbm_peak, "unit": "GB/s", "traffic": traffic.get("fft"), "peak_source": hbm_src,
+                    "algorithmic_bytes_per_step": fft_bytes}
     roofline_fft["frac"] = roofline_fft["achieved"] / hbm_peak
 
     line = {"metric": METRIC, "value": ms_dev, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

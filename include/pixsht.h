@@ -72,7 +72,8 @@ int pixsht_execute(pixsht_plan *plan, int direction, int ncomp, void *const *alm
 int pixsht_plan_set_stream(pixsht_plan *plan, void *stream, int use_caller_stream);
 
 /* per-stage device time (ms, CUDA events) of the last pixsht_execute on this plan:
- * device pointers: [1] Legendre stage, [2] FFT stage, [4] whole call (host wall clock);
+ * device pointers: [1] Legendre stage, [2] FFT stage, [4] whole call (host wall clock), [6] the spin-0 Legendre kernel
+ * alone (leg_synth<0,R> or leg_anal<0,R>), [7] the spin-2 Legendre kernel alone;
  * host pointers (copies, Legendre and FFT are pipelined over three streams, so stages overlap): [4] whole call,
  * [5] span of the compute stream; the rest 0 */
 int pixsht_get_timings(const pixsht_plan *plan, double ms[8]);
@@ -110,6 +111,9 @@ int pixsht_plan_info(const pixsht_plan *plan, int32_t info[16]);
 /* info: [0] nphi [1] nrings [2] lmax [3] mmax [4] dtype [5] device [6] npairs (north/south folded ring pairs)
  *       [7] SM count [8] FFT length [9] kernels launched by the last execute [10..13] ring pairs per thread of the
  *       spin-0 / spin-2 synthesis and spin-0 / spin-2 analysis kernels [14..15] reserved */
+/* (l, m, ring pair) steps of one spin family (0 or 2): out[0] = executed by the kernels (the plan-time activation table
+ * skips what stays below 2^-90), out[1] = nominal count of SURVEY.md 8(d) (every l >= max(m,|s|) for every pair) */
+int pixsht_plan_work(pixsht_plan *plan, int spin, double out[2]);
 int pixsht_plan_weights(const pixsht_plan *plan, double *weights /* nrings */, double *theta /* nrings */);
 const char *pixsht_last_error(void);
 const char *pixsht_version(void);

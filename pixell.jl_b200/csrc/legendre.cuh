@@ -211,6 +211,9 @@ __global__ void __launch_bounds__(128) k_seek_table(const SeekParams P)
 }
 
 // ---- per-thread ring state of the transform kernels ------------------------------------------------------------
+// The two recurrence registers of a function alternate roles instead of being rotated: at an even local step (PAR 0)
+// `p` holds the current value and `pp` the previous one, the step overwrites `pp` with the next value; at an odd local
+// step (PAR 1) the roles are swapped.  No register moves, and a predicated step is a handful of predicated FMAs.
 template <int SPIN, int R>
 struct RingState {
     double x[R];
@@ -232,51 +235,63 @@ __device__ __forceinline__ int warp_max(int v)
     return v;
 }
 
-// loads the activation state of the warp's rings; lmin / lmaxact = earliest / latest l_act over the live rings of the warp
+// loads the activation state of the warp's rings; lmin / lmaxact = earliest / latest l_act over the live rings of the
+// warp; lstart = first l of the warp's stream (same parity as l0, <= lmin)
 template <int SPIN, int R>
-__device__ __forceinline__ void load_rings(const LegParams& P, int m, int pair0, int lane, RingState<SPIN, R>& S, int& lmin, int& lmaxact)
+__device__ __forceinline__ void load_rings(const LegParams& P, int m, int l0, int pair0, int lane, RingState<SPIN, R>& S, int& lmin,
+                                           int& lmaxact, int& lstart)
 {
     int mn = L_NEVER, mx = -1;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
         const int pair = pair0 + j * 32 + lane;
         S.x[j] = 0.0; S.la[j] = L_NEVER;
-        S.p[0][j] = 0.0; S.pp[0][j] = 0.0;
-        if (SPIN != 0) { S.p[SPIN != 0][j] = 0.0; S.pp[SPIN != 0][j] = 0.0; }
         if (pair < P.npairs) {
-            const size_t k = (size_t)m * P.npairs + pair;
-            const int la = P.lact[k];
-            if (la <= P.lmax) {
-                S.la[j] = la; S.x[j] = P.x[pair];
-                if (SPIN == 0) {
-                    const double2 v = reinterpret_cast<const double2*>(P.st)[k];
-                    S.p[0][j] = v.x; S.pp[0][j] = v.y;
-                } else {
-                    const double2 v = reinterpret_cast<const double2*>(P.st)[2 * k], w = reinterpret_cast<const double2*>(P.st)[2 * k + 1];
-                    S.p[0][j] = v.x; S.p[SPIN != 0][j] = v.y; S.pp[0][j] = w.x; S.pp[SPIN != 0][j] = w.y;
-                }
-                mn = la < mn ? la : mn; mx = la > mx ? la : mx;
-            }
+            const int la = P.lact[(size_t)m * P.npairs + pair];
+            if (la <= P.lmax) { S.la[j] = la; S.x[j] = P.x[pair]; mn = la < mn ? la : mn; mx = la > mx ? la : mx; }
         }
     }
     lmin = warp_min(mn); lmaxact = warp_max(mx);
+    lstart = l0 + ((lmin - l0) & ~1);
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        S.p[0][j] = 0.0; S.pp[0][j] = 0.0;
+        if (SPIN != 0) { S.p[SPIN != 0][j] = 0.0; S.pp[SPIN != 0][j] = 0.0; }
+        if (S.la[j] != L_NEVER) {
+            const size_t k = (size_t)m * P.npairs + (pair0 + j * 32 + lane);
+            const bool odd = ((S.la[j] - lstart) & 1) != 0;   // the ring's first step is an odd local step: roles swapped
+            if (SPIN == 0) {
+                const double2 v = reinterpret_cast<const double2*>(P.st)[k];
+                S.p[0][j] = odd ? v.y : v.x; S.pp[0][j] = odd ? v.x : v.y;
+            } else {
+                const double2 v = reinterpret_cast<const double2*>(P.st)[2 * k], w = reinterpret_cast<const double2*>(P.st)[2 * k + 1];
+                S.p[0][j] = odd ? w.x : v.x; S.pp[0][j] = odd ? v.x : w.x;
+                S.p[SPIN != 0][j] = odd ? w.y : v.y; S.pp[SPIN != 0][j] = odd ? v.y : w.y;
+            }
+        }
+    }
 }
 
-// one recurrence step for ring slot j
-template <int SPIN, int R>
+// one recurrence step for ring slot j at local step parity PAR
+template <int SPIN, int R, int PAR>
 __device__ __forceinline__ void rec_step(RingState<SPIN, R>& S, int j, double alpha, double delta)
 {
     if (SPIN == 0) {
-        const double u = alpha * S.x[j];
-        const double pn = fma(u, S.p[0][j], -S.pp[0][j]);
-        S.pp[0][j] = S.p[0][j]; S.p[0][j] = pn;
+        // alpha * (x * p) - p_prev rather than (alpha * x) * p - p_prev: the FMA then has the warp-uniform alpha (served by
+        // the operand reuse cache) and only two fresh vector-register operands.  A DFMA with three fresh register operands
+        // issues at half rate on sm_100 (tools/dfma_mix.cu, DESIGN.md "operand bandwidth").
+        if (PAR == 0) { const double t = S.x[j] * S.p[0][j]; S.pp[0][j] = fma(alpha, t, -S.pp[0][j]); }
+        else { const double t = S.x[j] * S.pp[0][j]; S.p[0][j] = fma(alpha, t, -S.p[0][j]); }
     } else {
         const double up = fma(alpha, S.x[j], delta);
         const double um = fma(alpha, S.x[j], -delta);
-        const double pn = fma(up, S.p[0][j], -S.pp[0][j]);
-        const double mn = fma(um, S.p[SPIN != 0][j], -S.pp[SPIN != 0][j]);
-        S.pp[0][j] = S.p[0][j]; S.p[0][j] = pn;
-        S.pp[SPIN != 0][j] = S.p[SPIN != 0][j]; S.p[SPIN != 0][j] = mn;
+        if (PAR == 0) {
+            S.pp[0][j] = fma(up, S.p[0][j], -S.pp[0][j]);
+            S.pp[SPIN != 0][j] = fma(um, S.p[SPIN != 0][j], -S.pp[SPIN != 0][j]);
+        } else {
+            S.p[0][j] = fma(up, S.pp[0][j], -S.p[0][j]);
+            S.p[SPIN != 0][j] = fma(um, S.pp[SPIN != 0][j], -S.p[SPIN != 0][j]);
+        }
     }
 }
 
@@ -315,8 +330,8 @@ __device__ __forceinline__ void synth_step(RingState<SPIN, R>& S, double (&acc)[
 #pragma unroll
     for (int j = 0; j < R; ++j) {
         if (!MIXED || l >= S.la[j]) {
-            const double p0 = S.p[0][j];
-            const double p1 = S.p[SPIN != 0][j];
+            const double p0 = (PAR == 0) ? S.p[0][j] : S.pp[0][j];
+            const double p1 = (PAR == 0) ? S.p[SPIN != 0][j] : S.pp[SPIN != 0][j];
             if (SPIN == 0) {
                 acc[2 * PAR + 0][j] = fma(p0, g0.x, acc[2 * PAR + 0][j]);
                 acc[2 * PAR + 1][j] = fma(p0, g0.y, acc[2 * PAR + 1][j]);
@@ -339,7 +354,7 @@ __device__ __forceinline__ void synth_step(RingState<SPIN, R>& S, double (&acc)[
                     acc[A4 + 3][j] = fma(-p0, g1.y, acc[A4 + 3][j]);
                 }
             }
-            rec_step<SPIN, R>(S, j, c.x, c.y);
+            rec_step<SPIN, R, PAR>(S, j, c.x, c.y);
         }
     }
 }
@@ -359,8 +374,8 @@ __global__ void __launch_bounds__(LEG_NT) leg_synth(const LegParams P)
     const int pair0 = chunk * (32 * R);
 
     RingState<SPIN, R> S;
-    int lmin, lmaxact;
-    load_rings<SPIN, R>(P, m, pair0, lane, S, lmin, lmaxact);
+    int lmin, lmaxact, lstart;
+    load_rings<SPIN, R>(P, m, l0, pair0, lane, S, lmin, lmaxact, lstart);
     double acc[NACC][R];
 #pragma unroll
     for (int a = 0; a < NACC; ++a)
@@ -369,7 +384,6 @@ __global__ void __launch_bounds__(LEG_NT) leg_synth(const LegParams P)
 
     if (lmin <= P.lmax) {
         // local step t <-> l = lstart + t; lstart keeps the parity of l0 so that step parity = parity of (l - l0)
-        const int lstart = l0 + ((lmin - l0) & ~1);
         const int nl = P.lmax - lstart + 1;
         const int nmixed = (lmaxact - lstart + 1) & ~1;   // steps [0, nmixed) need the per-ring predicate
         if (lane == 0) { mbar_init(&sbar[0], 1); mbar_init(&sbar[1], 1); mbar_init_fence(); }
@@ -441,8 +455,8 @@ __device__ __forceinline__ void anal_step(RingState<SPIN, R>& S, const double (&
 #pragma unroll
     for (int j = 0; j < R; ++j) {
         if (!MIXED || l >= S.la[j]) {
-            const double p0 = S.p[0][j];
-            const double p1 = S.p[SPIN != 0][j];
+            const double p0 = (PAR == 0) ? S.p[0][j] : S.pp[0][j];
+            const double p1 = (PAR == 0) ? S.p[SPIN != 0][j] : S.pp[SPIN != 0][j];
             if (SPIN == 0) {
                 // even (l-m): X_N + X_S ; odd: X_N - X_S
                 part[0] = fma(p0, X[2 * PAR + 0][j], part[0]);
@@ -466,7 +480,7 @@ __device__ __forceinline__ void anal_step(RingState<SPIN, R>& S, const double (&
                     part[NPP - 1] = fma(-p0, X[NXX - 1][j], part[NPP - 1]);
                 }
             }
-            rec_step<SPIN, R>(S, j, c.x, c.y);
+            rec_step<SPIN, R, PAR>(S, j, c.x, c.y);
         }
     }
 }
@@ -489,8 +503,8 @@ __global__ void __launch_bounds__(LEG_NT) leg_anal(const LegParams P)
     const int pair0 = chunk * (32 * R);
 
     RingState<SPIN, R> S;
-    int lmin, lmaxact;
-    load_rings<SPIN, R>(P, m, pair0, lane, S, lmin, lmaxact);
+    int lmin, lmaxact, lstart;
+    load_rings<SPIN, R>(P, m, l0, pair0, lane, S, lmin, lmaxact, lstart);
     if (lmin > P.lmax) return;   // nothing to add (outputs are pre-zeroed)
 
     // folded inputs
@@ -517,7 +531,6 @@ __global__ void __launch_bounds__(LEG_NT) leg_anal(const LegParams P)
         }
     }
 
-    const int lstart = l0 + ((lmin - l0) & ~1);
     const int nl = P.lmax - lstart + 1;
     const int nmixed = (lmaxact - lstart + 1) & ~1;
     if (lane == 0) { mbar_init(&sbar[0], 1); mbar_init(&sbar[1], 1); mbar_init_fence(); }

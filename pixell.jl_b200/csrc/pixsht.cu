@@ -82,6 +82,8 @@ struct pixsht_plan {
     std::vector<int> h_ringN, h_ringS;
     int nsplit = 8;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t kev[4] = {nullptr, nullptr, nullptr, nullptr};   // around the spin-0 / spin-2 Legendre kernel of the device path
+    bool kev_on = false;
     double timings[8] = {0};
     int launches = 0;
     std::mutex mu;
@@ -104,19 +106,36 @@ __global__ void k_cvt_f64_to_f32(const double* __restrict__ in, float* __restric
 }
 
 #ifndef PIXSHT_EMU
-// register-resident FMA chains: 8 independent accumulators per thread, ITER*8 FMAs per thread
+// FMA peak probe: 16 independent accumulators per thread, acc[a][j] += p[j] * g[a] with warp-uniform g (uniform-register
+// operand) -> two vector-register reads per FMA, the shape that reaches the pipe's issue rate (tools/dfma_mix.cu: chains with
+// constant operands stop at ~34 TFLOP/s FP64 on B200, this shape reaches ~36.7 of the 37.2 TFLOP/s datasheet figure).
+// ITER*64 FMAs per thread.
 template <class T>
-__global__ void __launch_bounds__(256) k_fma_peak(T* out, int iters, T a, T b)
+__global__ void __launch_bounds__(256) k_fma_peak(T* out, int iters, const T* __restrict__ in)
 {
-    T v0 = (T)threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+    T p[4], g[4], acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = in[j] + (T)threadIdx.x * (T)1e-9;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) g[a] = in[8 + a];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[a][j] = (T)0;
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
-            v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
-        }
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[a][j] = fma(p[j], g[a], acc[a][j]);
     }
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+    T s = (T)0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += acc[a][j];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 #endif
 
@@ -167,8 +186,11 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     P->nalm = pixsht_nalm(lmax, mmax);
     P->h_theta = theta;
     {
-        int v = env_int("PIXSHT_R0", 4); P->R0 = (v == 1 || v == 2 || v == 3 || v == 4 || v == 6 || v == 8) ? v : 4;
-        v = env_int("PIXSHT_R2", 2); P->R2 = (v == 1 || v == 2 || v == 3 || v == 4) ? v : 2;
+        // ring pairs per thread: more pairs amortise the per-step operand loads (DESIGN.md "operand bandwidth") but widen a
+        // warp's spread of activation degrees; the wide setting pays off once a chunk is < 5 % of the pairs
+        const bool wide = (nr + 1) / 2 >= 4096;
+        int v = env_int("PIXSHT_R0", wide ? 8 : 4); P->R0 = (v == 1 || v == 2 || v == 3 || v == 4 || v == 6 || v == 8) ? v : 4;
+        v = env_int("PIXSHT_R2", wide ? 4 : 2); P->R2 = (v == 1 || v == 2 || v == 3 || v == 4) ? v : 2;
         v = env_int("PIXSHT_R0A", P->R0); P->R0a = (v == 1 || v == 2 || v == 3 || v == 4 || v == 6 || v == 8) ? v : 4;
         v = env_int("PIXSHT_R2A", 4); P->R2a = (v == 1 || v == 2 || v == 3 || v == 4) ? v : 4;
     }
@@ -296,9 +318,10 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     CU(cudaStreamCreateWithFlags(&P->s_d2h, cudaStreamNonBlocking));
     for (auto& e : P->dep) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     P->h_ringN = ringN; P->h_ringS = ringS;
-    { int v = env_int("PIXSHT_SPLITS", 4); P->nsplit = (v >= 1 && v <= 8) ? v : 4; }
+    { int v = env_int("PIXSHT_SPLITS", 8); P->nsplit = (v >= 1 && v <= 8) ? v : 8; }
     P->stream = P->own_stream;
     for (auto& e : P->ev) CU(cudaEventCreate(&e));
+    for (auto& e : P->kev) CU(cudaEventCreate(&e));
 
     // ---- device-side precompute ----
     if (wgt_or_empty.empty()) {
@@ -401,6 +424,7 @@ extern "C" void pixsht_plan_destroy(pixsht_plan* P)
     P->d_lact0.release(); P->d_lact2.release(); P->d_st0.release(); P->d_st2.release();
     for (int c = 0; c < 3; ++c) { P->d_map[c].release(); P->d_alm[c].release(); P->d_alm64[c].release(); }
     for (auto& e : P->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : P->kev) if (e) cudaEventDestroy(e);
     for (auto& e : P->dep) if (e) cudaEventDestroy(e);
     if (P->s_h2d) cudaStreamDestroy(P->s_h2d);
     if (P->s_d2h) cudaStreamDestroy(P->s_d2h);
@@ -495,11 +519,23 @@ static int synth_prep(pixsht_plan* P, int spin, const double2* a0, const double2
     CU(cudaGetLastError());
     return PIXSHT_OK;
 }
+// PIXSHT_DBG_NM / PIXSHT_DBG_CHUNKS (profiling aid, tools/loop_eff.py): restrict a launch to the first NM m values and the
+// CHUNKS equator-most chunks, where every ring is active for almost the whole l range -> pure inner-loop throughput
+static void dbg_restrict(LegParams& L)
+{
+    const int nm = env_int("PIXSHT_DBG_NM", 0), nc = env_int("PIXSHT_DBG_CHUNKS", 0);
+    if (nm > 0 && nm < L.nm) L.nm = nm;
+    if (nc > 0 && nc < L.nchunks) { L.chunk_begin += L.nchunks - nc; L.nchunks = nc; }
+}
+
 static int synth_launch(pixsht_plan* P, const LegJob& J, cudaStream_t st)
 {
     const int R = leg_R(P, J.spin, false);
     LegParams L = leg_params(P, J, R);
+    dbg_restrict(L);
+    if (P->kev_on) CU(cudaEventRecord(P->kev[J.spin == 0 ? 0 : 2], st));
     if (J.spin == 0) launch_synth<0>(P, R, L, st); else launch_synth<2>(P, R, L, st);
+    if (P->kev_on) CU(cudaEventRecord(P->kev[J.spin == 0 ? 1 : 3], st));
     CU(cudaGetLastError());
     return PIXSHT_OK;
 }
@@ -508,8 +544,11 @@ static int anal_launch(pixsht_plan* P, const LegJob& J, double2* out0, double2* 
     int rc = ensure_seek(P, J.spin, st); if (rc) return rc;
     const int R = leg_R(P, J.spin, true);
     LegParams L = leg_params(P, J, R);
+    dbg_restrict(L);
     L.alm_out0 = out0; L.alm_out1 = out1;
+    if (P->kev_on) CU(cudaEventRecord(P->kev[J.spin == 0 ? 0 : 2], st));
     if (J.spin == 0) launch_anal<0>(P, R, L, st); else launch_anal<2>(P, R, L, st);
+    if (P->kev_on) CU(cudaEventRecord(P->kev[J.spin == 0 ? 1 : 3], st));
     CU(cudaGetLastError());
     return PIXSHT_OK;
 }
@@ -795,6 +834,8 @@ extern "C" int pixsht_execute(pixsht_plan* P, int direction, int ncomp, void* co
 
     CU(cudaEventRecord(P->ev[0], st));
     CU(cudaEventRecord(P->ev[1], st));
+    P->kev_on = true;
+    struct KevOff { pixsht_plan* p; ~KevOff() { p->kev_on = false; } } kev_off{P};
     if (direction == PIXSHT_ALM2MAP) {
         if (f32)
             for (int c = 0; c < ncomp; ++c) {
@@ -828,6 +869,8 @@ extern "C" int pixsht_execute(pixsht_plan* P, int direction, int ncomp, void* co
     else { P->timings[2] = ms[1]; P->timings[1] = ms[2]; }
     P->timings[3] = ms[3];
     P->timings[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    if (ncomp != 2) { float k; CU(cudaEventElapsedTime(&k, P->kev[0], P->kev[1])); P->timings[6] = k; }
+    if (ncomp >= 2) { float k; CU(cudaEventElapsedTime(&k, P->kev[2], P->kev[3])); P->timings[7] = k; }
     return PIXSHT_OK;
 }
 
@@ -1003,6 +1046,39 @@ extern "C" int pixsht_plan_info(const pixsht_plan* P, int32_t info[16])
     return PIXSHT_OK;
 }
 
+// executed vs nominal (l, m, ring pair) steps of one spin family: the activation table decides what runs
+__global__ void k_count_work(int lmax, int mmax, int npairs, int s, const int* __restrict__ lact, unsigned long long* out)
+{
+    const long long n = (long long)(mmax + 1) * npairs;
+    unsigned long long exec = 0, nominal = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int m = (int)(i / npairs);
+        const int l0 = m > s ? m : s;
+        if (l0 <= lmax) nominal += (unsigned long long)(lmax - l0 + 1);
+        const int la = lact[i];
+        if (la <= lmax) exec += (unsigned long long)(lmax - la + 1);
+    }
+    atomicAdd(&out[0], exec); atomicAdd(&out[1], nominal);
+}
+
+extern "C" int pixsht_plan_work(pixsht_plan* P, int spin, double out[2])
+{
+    if (!P || !out || (spin != 0 && spin != 2)) return fail(PIXSHT_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lock(P->mu);
+    int rc = check_device(P->device); if (rc) return rc;
+    rc = ensure_seek(P, spin, P->stream); if (rc) return rc;
+    DevBuf<unsigned long long> d;
+    if (d.alloc(2)) return fail(PIXSHT_ERR_NOMEM, "allocation failed");
+    CU(cudaMemsetAsync(d.p, 0, 16, P->stream));
+    PIXSHT_LAUNCH(k_count_work, 1024, 256, 0, P->stream, P->lmax, P->mmax, P->npairs, spin, spin == 0 ? P->d_lact0.p : P->d_lact2.p, d.p);
+    unsigned long long h[2] = {0, 0};
+    CU(cudaMemcpyAsync(h, d.p, 16, cudaMemcpyDeviceToHost, P->stream));
+    CU(cudaStreamSynchronize(P->stream));
+    d.release();
+    out[0] = (double)h[0]; out[1] = (double)h[1];
+    return PIXSHT_OK;
+}
+
 extern "C" int pixsht_plan_weights(const pixsht_plan* P, double* weights, double* theta)
 {
     if (!P) return fail(PIXSHT_ERR_ARG, "null argument");
@@ -1037,17 +1113,22 @@ extern "C" int pixsht_measure_fma_peak(int device, double* fp64_tflops, double* 
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     const int blocks = prop.multiProcessorCount * 8, threads = 256;
-    void* buf = nullptr;
+    void* buf = nullptr; void* din = nullptr;
     CU(cudaMalloc(&buf, (size_t)blocks * threads * sizeof(double)));
+    CU(cudaMalloc(&din, 16 * sizeof(double)));
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     for (int pass = 0; pass < 2; ++pass) {
         const int iters = pass == 0 ? 4096 : 16384;   // fp64, fp32
+        double hd[16]; float hf[16];
+        for (int i = 0; i < 16; ++i) { hd[i] = 1e-3 * (i + 1); hf[i] = (float)hd[i]; }
+        if (pass == 0) CU(cudaMemcpy(din, hd, sizeof(hd), cudaMemcpyHostToDevice));
+        else CU(cudaMemcpy(din, hf, sizeof(hf), cudaMemcpyHostToDevice));
         float best = 1e30f;
         for (int rep = 0; rep < 4; ++rep) {
             CU(cudaEventRecord(e0, 0));
-            if (pass == 0) k_fma_peak<double><<<blocks, threads>>>((double*)buf, iters, 1.0000001, 1e-9);
-            else k_fma_peak<float><<<blocks, threads>>>((float*)buf, iters, 1.0000001f, 1e-9f);
+            if (pass == 0) k_fma_peak<double><<<blocks, threads>>>((double*)buf, iters, (const double*)din);
+            else k_fma_peak<float><<<blocks, threads>>>((float*)buf, iters, (const float*)din);
             CU(cudaEventRecord(e1, 0));
             CU(cudaEventSynchronize(e1));
             float ms; CU(cudaEventElapsedTime(&ms, e0, e1));
@@ -1058,6 +1139,7 @@ extern "C" int pixsht_measure_fma_peak(int device, double* fp64_tflops, double* 
         if (pass == 0) { if (fp64_tflops) *fp64_tflops = tf; }
         else { if (fp32_tflops) *fp32_tflops = tf; }
     }
+    cudaFree(din);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
     CU(cudaGetLastError());
     return PIXSHT_OK;

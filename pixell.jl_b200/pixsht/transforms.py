@@ -55,7 +55,13 @@ class Plan:
     def timings(self):
         t = (ctypes.c_double * 8)()
         self.lib.check(self.lib.lib.pixsht_get_timings(self.handle, t))
-        return dict(h2d=t[0], legendre=t[1], fft=t[2], d2h=t[3], total=t[4])
+        return dict(h2d=t[0], legendre=t[1], fft=t[2], d2h=t[3], total=t[4], compute_span=t[5], leg_spin0=t[6], leg_spin2=t[7])
+
+    def work(self, spin):
+        """(executed, nominal) (l, m, ring pair) steps of one spin family."""
+        w = (ctypes.c_double * 2)()
+        self.lib.check(self.lib.lib.pixsht_plan_work(self.handle, spin, w))
+        return w[0], w[1]
 
     def info(self):
         v = (ctypes.c_int32 * 16)()

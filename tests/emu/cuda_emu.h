@@ -120,6 +120,12 @@ static inline double atomicAdd(double* addr, double v)
     double old = *addr; *addr = old + v; return old;
 }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+static inline unsigned long long atomicAdd(unsigned long long* addr, unsigned long long v)
+{
+    static std::mutex mu;
+    std::lock_guard<std::mutex> g(mu);
+    unsigned long long old = *addr; *addr = old + v; return old;
+}
 static inline int __double2hiint(double d) { uint64_t u; memcpy(&u, &d, 8); return (int)(u >> 32); }
 static inline int __double2loint(double d) { uint64_t u; memcpy(&u, &d, 8); return (int)(u & 0xffffffffu); }
 static inline double __hiloint2double(int hi, int lo)

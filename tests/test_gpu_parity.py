@@ -205,3 +205,174 @@ def test_sharp_shim_runs_the_reference_call_sequence():
     assert rel_rms(back, ref) < TOL64
     L.sharp_destroy_alm_info(ainfo)
     L.sharp_destroy_geom_info(geom)
+
+
+# ---- BASELINE-size checks (C3 / C4 geometries): sampled parity against the oracle + size-independent properties ----------
+POLE_TOL64 = 5e-9
+
+
+def _ring_errors(band, maps, alms, lmax, spin, rings):
+    """rel-RMS error per selected band ring of alm2map output against the long-double oracle evaluated on those rings."""
+    theta, _ = cc_geometry(band.nrings_total, band.nphi, band.ring_first, band.nrings)
+    ref = get_oracle("ld").alm2map(np.stack(alms), theta[rings], band.phi0, band.nphi, lmax, spin=spin)
+    num, den = np.zeros(len(rings)), np.zeros(len(rings))
+    for i, r in enumerate(rings):
+        row = (band.nrings - 1 - r) if band.flipy else r
+        for c in range(len(alms)):
+            g = maps[c][:, row]
+            g = g[::-1] if band.flipx else g
+            num[i] += np.sum((g[:band.nx] - ref[c, i, :band.nx]) ** 2)
+            den[i] += np.sum(ref[c, i, :band.nx] ** 2)
+    return num, den
+
+
+def _sampled_checks(plan, band, shape, wcs, lmax, alms, spin, ring_stride, ring_offset, m_stride, m_offset, seed):
+    """alm2map on sampled rings and map2alm on sampled m against the long-double oracle, plus adjointness of the pair.
+
+    Tolerances: rel-RMS <= 1e-10 (north_star) over the sampled rings / m.  The few rings within ~0.2 deg of a pole are held
+    to POLE_TOL64 instead: FP64 three-term recurrences in cos(theta) (this engine and libsharp2 alike) lose ~l^1.5 eps there
+    -- measured 1e-9 on the pole ring itself at lmax = 10800 with a white spectrum, 1e-11 from 0.5 deg on (tools/pole_accuracy.py);
+    the whole-map rel-RMS stays ~1e-11."""
+    nc = len(alms)
+    maps = plan.alm2map(alms)
+    rings = list(range(ring_offset, band.nrings, ring_stride))
+    num, den = _ring_errors(band, maps, alms, lmax, spin, rings)
+    assert np.sqrt(num.sum() / den.sum()) < TOL64
+    polar = [0, 1, 2, band.nrings - 2, band.nrings - 1]
+    num, den = _ring_errors(band, maps, alms, lmax, spin, polar)
+    assert np.all(np.sqrt(num / den) < POLE_TOL64)
+    rng = np.random.default_rng(seed)
+    x = [np.asfortranarray(rng.standard_normal(shape[:2])) for _ in range(nc)]
+    ytx = plan.map2alm(x)
+    xm = Enmap(x[0], wcs) if nc == 1 else Enmap(np.asfortranarray(np.stack(x, axis=2)), wcs)
+    ref_alm = oracle_map2alm(xm, lmax, spin=spin, m_stride=m_stride, m_offset=m_offset)
+    sel = np.concatenate([np.arange(alm_index(lmax, m, m), alm_index(lmax, lmax, m) + 1) for m in range(m_offset, lmax + 1, m_stride)])
+    for c in range(nc):
+        assert rel_rms(ytx[c][sel], ref_alm[c][sel]) < TOL64
+    # <W Y a, x> = <a, Y^T W x> over all components
+    w, _ = plan.weights()
+    wrow = w[::-1] if band.flipy else w
+    lhs = sum(float(np.sum(maps[c] * x[c] * wrow[None, :])) for c in range(nc))
+    fac = np.full(alms[0].shape, 2.0)
+    fac[:lmax + 1] = 1.0
+    rhs = sum(float(np.sum(fac * (np.conj(alms[c]) * ytx[c]).real)) for c in range(nc))
+    assert abs(lhs - rhs) < 1e-10 * max(abs(lhs), abs(rhs))
+    return maps, ytx
+
+
+def test_c3_size_iqu_sampled_parity_and_adjointness():
+    """BASELINE config C3: full-sky CAR 2' (10800 x 5401), lmax 5400, T and (E,B)."""
+    shape, wcs = fullsky_geometry(2.0 * arcminute)
+    lmax = 5400
+    band = pixsht.sht_band(shape, wcs)
+    plan = Plan(band, lmax)
+    _sampled_checks(plan, band, shape, wcs, lmax, [synth_alm(lmax, lmax, 3000)], 0, 1201, 150, 1777, 5, 31)
+    _sampled_checks(plan, band, shape, wcs, lmax, [synth_alm(lmax, lmax, 3001, spin2=True), synth_alm(lmax, lmax, 3002, spin2=True)],
+                    2, 1201, 600, 1777, 2, 32)
+    plan.close()
+
+
+def test_c4_size_spin0_and_spin2_sampled_parity():
+    """BASELINE config C4 (the headline): full-sky CAR 1' (21600 x 10801), lmax 10800.  Rings next to the pole, mid latitude
+    and the equator; low, middle and Nyquist-adjacent m."""
+    shape, wcs = fullsky_geometry(1.0 * arcminute)
+    lmax = 10800
+    band = pixsht.sht_band(shape, wcs)
+    plan = Plan(band, lmax)
+    _sampled_checks(plan, band, shape, wcs, lmax, [synth_alm(lmax, lmax, 4000)], 0, 1350, 337, 3600, 0, 41)
+    _sampled_checks(plan, band, shape, wcs, lmax, [synth_alm(lmax, lmax, 4001, spin2=True), synth_alm(lmax, lmax, 4002, spin2=True)],
+                    2, 2700, 1337, 5400, 5399, 42)
+    plan.close()
+
+
+def test_host_and_device_paths_agree_and_iqu_is_t_plus_qu():
+    """The pipelined host-pointer path (three streams, split launches) equals the single-stream device path, and the fused
+    IQU call equals a T call plus a QU call (the reference runs IQU as two libsharp jobs, src/transforms.jl:143-144)."""
+    import torch
+    shape, wcs = fullsky_geometry(8.0 * arcminute)
+    lmax = 1350
+    band = pixsht.sht_band(shape, wcs)
+    plan = Plan(band, lmax)
+    alms = [synth_alm(lmax, lmax, 70), synth_alm(lmax, lmax, 71, spin2=True), synth_alm(lmax, lmax, 72, spin2=True)]
+    host = plan.alm2map(alms)
+    t_only = plan.alm2map(alms[:1])
+    qu_only = plan.alm2map(alms[1:])
+    assert np.array_equal(host[0], t_only[0]) and np.array_equal(host[1], qu_only[0]) and np.array_equal(host[2], qu_only[1])
+    dev = torch.device("cuda", 0)
+    d_alm = [torch.from_numpy(a).to(dev) for a in alms]
+    d_map = [torch.empty(band.nx * band.nrings, dtype=torch.float64, device=dev) for _ in alms]
+    plan.execute_ptrs(_lib.ALM2MAP, [a.data_ptr() for a in d_alm], [m.data_ptr() for m in d_map], _lib.DEVICE)
+    for c in range(3):
+        assert np.array_equal(d_map[c].cpu().numpy().reshape(band.nrings, band.nx).T, host[c])
+    back_host = plan.map2alm(host)
+    d_out = [torch.empty_like(a) for a in d_alm]
+    plan.execute_ptrs(_lib.MAP2ALM, [a.data_ptr() for a in d_out], [m.data_ptr() for m in d_map], _lib.DEVICE)
+    for c in range(3):   # atomic accumulation order differs between the split and the single launch: equal to rounding
+        assert rel_rms(d_out[c].cpu().numpy(), back_host[c]) < 1e-13
+    ex, nom = plan.work(0)
+    assert 0.5 < ex / nom < 0.9          # the activation table prunes what never reaches 2^-90
+    plan.close()
+
+
+def _mgpu_worker(rank, world, port, out_dir):
+    import os
+    import sys
+    import torch
+    import torch.distributed as dist
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), os.path.join(os.path.dirname(here), "pixell.jl_b200"), here):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import pixsht as px
+    from pixsht.distributed import ShardedSHT
+    from helpers import synth_alm as sa
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world, device_id=dev)
+    shape, wcs = px.fullsky_geometry(8.0 * px.arcminute)
+    lmax = 1350
+    band = px.sht_band(shape, wcs)
+    sht = ShardedSHT(band, lmax, device=dev)
+    alms = [torch.from_numpy(sa(lmax, lmax, 70 + c, spin2=c > 0)).to(dev) for c in range(3)]
+    a, b = sht.map_rows()
+    slabs = [torch.zeros((b - a) * band.nx, dtype=torch.float64, device=dev) for _ in range(3)]
+    for _ in range(2):      # twice: the second pass reuses the peer buffers (exercises the stage-ordering barriers)
+        sht.alm2map(alms, slabs)
+        out = [torch.full((sht.nalm,), 7.0, dtype=torch.complex128, device=dev) for _ in range(3)]
+        sht.map2alm(slabs, out)
+    torch.cuda.synchronize(dev)
+    np.save(os.path.join(out_dir, "slab_%d.npy" % rank), np.stack([s.cpu().numpy() for s in slabs]))
+    np.save(os.path.join(out_dir, "alm_%d.npy" % rank), np.stack([o.cpu().numpy() for o in out]))
+    np.save(os.path.join(out_dir, "rows_%d.npy" % rank), np.array([a, b]))
+    sht.close()
+    dist.destroy_process_group()
+
+
+def test_multi_gpu_peer_memory_pipeline_matches_single_gpu(tmp_path):
+    """m-sharded Legendre + ring-sharded FFT with the phase rows exchanged through peer memory (no all-to-all pass):
+    every rank's slab and alm columns equal the single-GPU transform.  Needs >= 2 GPUs on the box."""
+    import os
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    port = 29700 + os.getpid() % 200
+    mp.spawn(_mgpu_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    shape, wcs = fullsky_geometry(8.0 * arcminute)
+    lmax = 1350
+    band = pixsht.sht_band(shape, wcs)
+    plan = Plan(band, lmax)
+    alms = [synth_alm(lmax, lmax, 70 + c, spin2=c > 0) for c in range(3)]
+    maps = plan.alm2map(alms)
+    back = plan.map2alm(maps)
+    got = np.zeros((3, band.nrings, band.nx))
+    for r in range(world):
+        a, b = np.load(tmp_path / ("rows_%d.npy" % r))
+        got[:, a:b, :] = np.load(tmp_path / ("slab_%d.npy" % r)).reshape(3, b - a, band.nx)
+    for c in range(3):
+        assert np.array_equal(got[c].T, maps[c])
+    alm_sum = sum(np.load(tmp_path / ("alm_%d.npy" % r)) for r in range(world))
+    for c in range(3):
+        assert rel_rms(alm_sum[c], back[c]) < 1e-13
+    plan.close()

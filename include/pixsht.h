@@ -114,6 +114,8 @@ int pixsht_plan_info(const pixsht_plan *plan, int32_t info[16]);
 /* (l, m, ring pair) steps of one spin family (0 or 2): out[0] = executed by the kernels (the plan-time activation table
  * skips what stays below 2^-90), out[1] = nominal count of SURVEY.md 8(d) (every l >= max(m,|s|) for every pair) */
 int pixsht_plan_work(pixsht_plan *plan, int spin, double out[2]);
+/* executed steps per m (mmax+1 doubles, host): the load-balancing weight of the m-sharded multi-GPU partition */
+int pixsht_plan_work_per_m(pixsht_plan *plan, int spin, double *out);
 int pixsht_plan_weights(const pixsht_plan *plan, double *weights /* nrings */, double *theta /* nrings */);
 const char *pixsht_last_error(void);
 const char *pixsht_version(void);

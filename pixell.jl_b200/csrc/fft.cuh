@@ -53,12 +53,35 @@ template <class T> __device__ __forceinline__ cpx<T> cconj(cpx<T> a) { cpx<T> r;
 // multiply by +i (SIGN=+1) or -i (SIGN=-1)
 template <class T, int SIGN> __device__ __forceinline__ cpx<T> cmuli(cpx<T> a) { cpx<T> r; if (SIGN > 0) { r.x = -a.y; r.y = a.x; } else { r.x = a.y; r.y = -a.x; } return r; }
 
-// exp(SIGN * 2 pi i t / nphi) from the forward table
-template <class T, int SIGN>
-__device__ __forceinline__ cpx<T> twid(const FftParams& P, int t)
+// Twiddles: exp(SIGN * 2 pi i t / nphi) = A[t >> 7] * B[t & 127] from two small tables held in shared memory behind the ring
+// buffer (A: every 128th entry of the global table, B: its first 128 entries).  Reading the full table from global memory
+// cost ~4x the algorithmic HBM bytes in L2 traffic (ncu lts__t_bytes, profiles/r01): the 227 KB carve-out leaves no L1.
+constexpr int FFT_TWLO_BITS = 7;
+constexpr int FFT_TWLO = 1 << FFT_TWLO_BITS;
+__host__ __device__ __forceinline__ int fft_tw_entries(int nphi) { return FFT_TWLO + (nphi + FFT_TWLO - 1) / FFT_TWLO; }
+
+template <class T>
+struct TwTab { const cpx<T>* A; const cpx<T>* B; };
+
+template <class T>
+__device__ __forceinline__ TwTab<T> tw_setup(const FftParams& P, cpx<T>* tab)
 {
-    const double2 w = P.tw[t];
-    cpx<T> r; r.x = (T)w.x; r.y = (T)(SIGN < 0 ? w.y : -w.y);
+    const int na = (P.nphi + FFT_TWLO - 1) / FFT_TWLO;
+    for (int i = threadIdx.x; i < FFT_TWLO + na; i += blockDim.x) {
+        const double2 w = (i < FFT_TWLO) ? P.tw[i < P.nphi ? i : 0] : P.tw[(i - FFT_TWLO) * FFT_TWLO];
+        cpx<T> v; v.x = (T)w.x; v.y = (T)w.y;
+        tab[i] = v;
+    }
+    TwTab<T> t; t.B = tab; t.A = tab + FFT_TWLO;
+    return t;
+}
+
+template <class T, int SIGN>
+__device__ __forceinline__ cpx<T> twid(const TwTab<T>& W, int t)
+{
+    const cpx<T> a = W.A[t >> FFT_TWLO_BITS], b = W.B[t & (FFT_TWLO - 1)];
+    cpx<T> r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x;
+    if (SIGN > 0) r.y = -r.y;
     return r;
 }
 
@@ -112,15 +135,15 @@ __device__ __forceinline__ void dft5(cpx<T>* a)
 // one butterfly of a radix-Q pass at element pointer e (stride L), twiddle exponent base tk = kk * tstep.
 // DIF == false: decimation in time (twiddle, then DFT);  DIF == true: the transpose (DFT, then twiddle).
 template <class T, int SIGN, int Q, bool DIF>
-__device__ __forceinline__ void butterfly(const FftParams& P, cpx<T>* e, int L, int tk)
+__device__ __forceinline__ void butterfly(const TwTab<T>& W, cpx<T>* e, int L, int tk)
 {
     cpx<T> a[Q];
 #pragma unroll
     for (int j = 0; j < Q; ++j) a[j] = e[(size_t)j * L];
     cpx<T> w[5];
     if (tk) {
-        w[1] = twid<T, SIGN>(P, tk);
-        if constexpr (Q > 2) w[2] = twid<T, SIGN>(P, 2 * tk);
+        w[1] = twid<T, SIGN>(W, tk);
+        if constexpr (Q > 2) w[2] = twid<T, SIGN>(W, 2 * tk);
         if constexpr (Q > 3) w[3] = cmul(w[1], w[2]);
         if constexpr (Q > 4) w[4] = cmul(w[2], w[2]);
     }
@@ -142,27 +165,38 @@ __device__ __forceinline__ void butterfly(const FftParams& P, cpx<T>* e, int L, 
 
 // generic (odd prime) radix, O(q^2)
 template <class T, int SIGN, bool DIF>
-__device__ void butterfly_generic(const FftParams& P, cpx<T>* e, int q, int L, int tk)
+__device__ void butterfly_generic(const FftParams& P, const TwTab<T>& W, cpx<T>* e, int q, int L, int tk)
 {
     cpx<T> a[FFT_MAXRADIX];
     for (int j = 0; j < q; ++j) {
         cpx<T> v = e[(size_t)j * L];
-        if (!DIF && tk && j) v = cmul(v, twid<T, SIGN>(P, j * tk));
+        if (!DIF && tk && j) v = cmul(v, twid<T, SIGN>(W, j * tk));
         a[j] = v;
     }
     const int qstep = P.nphi / q;
     for (int u = 0; u < q; ++u) {
         cpx<T> s = a[0];
-        for (int j = 1; j < q; ++j) s = cadd(s, cmul(a[j], twid<T, SIGN>(P, ((j * u) % q) * qstep)));
-        if (DIF && tk && u) s = cmul(s, twid<T, SIGN>(P, u * tk));
+        for (int j = 1; j < q; ++j) s = cadd(s, cmul(a[j], twid<T, SIGN>(W, ((j * u) % q) * qstep)));
+        if (DIF && tk && u) s = cmul(s, twid<T, SIGN>(W, u * tk));
         e[(size_t)u * L] = s;
+    }
+}
+
+// all butterflies of one radix-Q pass (Q a template parameter so that the loop body is straight-line code)
+template <class T, int SIGN, int Q, bool DIF>
+__device__ __forceinline__ void pass_loop(const TwTab<T>& W, cpx<T>* buf, int L, int nb, int tstep, unsigned magic)
+{
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+        const int g = (L == 1) ? b : (int)__umulhi((unsigned)b, magic);
+        const int kk = b - g * L;
+        butterfly<T, SIGN, Q, DIF>(W, buf + (size_t)g * Q * L + kk, L, kk * tstep);
     }
 }
 
 // in-place mixed-radix passes over buf[0..n).  DIF == false: digit-reversed input -> natural output (pass order 0..nfac-1);
 // DIF == true: natural input -> digit-reversed output (pass order nfac-1..0).  SIGN = -1 forward.
 template <class T, int SIGN, bool DIF>
-__device__ void fft_passes(const FftParams& P, cpx<T>* buf)
+__device__ void fft_passes(const FftParams& P, const TwTab<T>& W, cpx<T>* buf)
 {
     const int n = P.n;
     int L = 1;
@@ -174,16 +208,16 @@ __device__ void fft_passes(const FftParams& P, cpx<T>* buf)
         const int nb = n / q;
         const int tstep = P.nphi / (q * L);   // W_{qL}^{a} = tw[a * tstep]
         const unsigned magic = P.magic[t];
-        for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-            const int g = (L == 1) ? b : (int)__umulhi((unsigned)b, magic);
-            const int kk = b - g * L;
-            cpx<T>* e = buf + (size_t)g * q * L + kk;
-            const int tk = kk * tstep;
-            if (q == 4) butterfly<T, SIGN, 4, DIF>(P, e, L, tk);
-            else if (q == 3) butterfly<T, SIGN, 3, DIF>(P, e, L, tk);
-            else if (q == 5) butterfly<T, SIGN, 5, DIF>(P, e, L, tk);
-            else if (q == 2) butterfly<T, SIGN, 2, DIF>(P, e, L, tk);
-            else butterfly_generic<T, SIGN, DIF>(P, e, q, L, tk);
+        if (q == 4) pass_loop<T, SIGN, 4, DIF>(W, buf, L, nb, tstep, magic);
+        else if (q == 3) pass_loop<T, SIGN, 3, DIF>(W, buf, L, nb, tstep, magic);
+        else if (q == 5) pass_loop<T, SIGN, 5, DIF>(W, buf, L, nb, tstep, magic);
+        else if (q == 2) pass_loop<T, SIGN, 2, DIF>(W, buf, L, nb, tstep, magic);
+        else {
+            for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+                const int g = (L == 1) ? b : (int)__umulhi((unsigned)b, magic);
+                const int kk = b - g * L;
+                butterfly_generic<T, SIGN, DIF>(P, W, buf + (size_t)g * q * L + kk, q, L, kk * tstep);
+            }
         }
         if (!DIF) L *= q;
         __syncthreads();
@@ -207,27 +241,70 @@ __device__ __forceinline__ cpx<T> load_X(const FftParams& P, const double2* row,
     return v;
 }
 
+// ring samples (x[2j], x[2j+1]) of the caller's row as one complex: a single 2-element vector access when the row is a full,
+// even-length ring (the band bookkeeping of create_sht_band otherwise: flips and zero padding by index arithmetic)
+template <class T> struct Pair2 { T x, y; };
+template <class T>
+__device__ __forceinline__ cpx<T> load_pair(const FftParams& P, const T* irow, int j, bool vec)
+{
+    cpx<T> z;
+    if (vec) {
+        const int i = P.flipx ? (P.nx - 2 - 2 * j) : 2 * j;
+        const cpx<T> v = *reinterpret_cast<const cpx<T>*>(irow + i);
+        if (P.flipx) { z.x = v.y; z.y = v.x; } else z = v;
+    } else {
+        const int i0 = 2 * j, i1 = 2 * j + 1;
+        z.x = (i0 < P.nx) ? irow[P.flipx ? (P.nx - 1 - i0) : i0] : (T)0;
+        z.y = (i1 < P.nx) ? irow[P.flipx ? (P.nx - 1 - i1) : i1] : (T)0;
+    }
+    return z;
+}
+template <class T>
+__device__ __forceinline__ void store_pair(const FftParams& P, T* orow, int j, cpx<T> z, bool vec)
+{
+    if (vec) {
+        const int i = P.flipx ? (P.nx - 2 - 2 * j) : 2 * j;
+        cpx<T> v; if (P.flipx) { v.x = z.y; v.y = z.x; } else v = z;
+        *reinterpret_cast<cpx<T>*>(orow + i) = v;
+    } else {
+        const int i0 = 2 * j, i1 = 2 * j + 1;
+        if (i0 < P.nx) orow[P.flipx ? (P.nx - 1 - i0) : i0] = z.x;
+        if (i1 < P.nx) orow[P.flipx ? (P.nx - 1 - i1) : i1] = z.y;
+    }
+}
+constexpr int FFT_IO_UNROLL = 4;   // independent global accesses in flight per thread in the load / store loops
+
 // phase -> map  (synthesis).  grid = (ring_count, ncomp)
 template <class T>
 __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams P)
 {
     PIXSHT_DYN_SMEM(smem_raw);
-    cpx<T>* buf = reinterpret_cast<cpx<T>*>(smem_raw);   // n + 1 entries
+    cpx<T>* buf = reinterpret_cast<cpx<T>*>(smem_raw);   // n + 1 entries, then the twiddle tables
+    const TwTab<T> W = tw_setup<T>(P, buf + P.n + 1);
     const int rl = blockIdx.x, c = P.c_begin + blockIdx.y, ring = P.ring_begin + rl;
     const int n = P.n;
     const double2* row = P.phase + ((long long)rl * P.ncomp + c) * P.MP;
 
     // X[k], k = 0..n, natural order (coalesced row read)
     if (P.mmax <= n) {
-        for (int k = threadIdx.x; k <= n; k += blockDim.x) {
-            cpx<T> v; v.x = (T)0; v.y = (T)0;
-            if (k <= P.mmax) {
-                const double2 a = row[k], r = P.phi0tw[k];
-                const double sx = a.x * r.x - a.y * r.y, sy = a.x * r.y + a.y * r.x;
-                if (k == n) { v.x = (T)(2.0 * sx); }          // m = nphi/2: the ring carries only the (doubled) real part
-                else { v.x = (T)sx; v.y = (T)sy; }
+        for (int k0 = threadIdx.x; k0 <= n; k0 += FFT_IO_UNROLL * blockDim.x) {
+            double2 a[FFT_IO_UNROLL], r[FFT_IO_UNROLL];
+#pragma unroll
+            for (int u = 0; u < FFT_IO_UNROLL; ++u) {
+                const int k = k0 + u * blockDim.x;
+                a[u] = make_double2(0.0, 0.0); r[u] = a[u];
+                if (k <= P.mmax) { a[u] = row[k]; r[u] = P.phi0tw[k]; }
             }
-            buf[k] = v;
+#pragma unroll
+            for (int u = 0; u < FFT_IO_UNROLL; ++u) {
+                const int k = k0 + u * blockDim.x;
+                if (k > n) break;
+                const double sx = a[u].x * r[u].x - a[u].y * r[u].y, sy = a[u].x * r[u].y + a[u].y * r[u].x;
+                cpx<T> v;
+                if (k == n) { v.x = (T)(2.0 * sx); v.y = (T)0; }          // m = nphi/2: the ring carries only the (doubled) real part
+                else { v.x = (T)sx; v.y = (T)sy; }
+                buf[k] = v;
+            }
         }
     } else {
         for (int k = threadIdx.x; k <= n; k += blockDim.x) buf[k] = load_X<T>(P, row, k);
@@ -242,10 +319,10 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
             buf[0] = z;
         } else {
             const cpx<T> xa = buf[k], xb = buf[n - k];
-            const cpx<T> wa = twid<T, +1>(P, k);
+            const cpx<T> wa = twid<T, +1>(W, k);
             const cpx<T> ea = cadd(xa, cconj(xb)), oa = cmul(csub(xa, cconj(xb)), wa);
             if (k != n - k) {
-                const cpx<T> wb = twid<T, +1>(P, n - k);
+                const cpx<T> wb = twid<T, +1>(W, n - k);
                 const cpx<T> eb = cadd(xb, cconj(xa)), ob = cmul(csub(xb, cconj(xa)), wb);
                 buf[n - k] = cadd(eb, cmuli<T, +1>(ob));
             }
@@ -253,17 +330,22 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
         }
     }
     __syncthreads();
-    fft_passes<T, +1, true>(P, buf);
+    fft_passes<T, +1, true>(P, W, buf);
 
     // store x[2j] = Re z[j], x[2j+1] = Im z[j] into the caller's array (flips / partial rings by index arithmetic)
     T* out = reinterpret_cast<T*>(P.maps[c]);
     const int rowy = P.flipy ? (P.ny - 1 - ring) : ring;
     T* orow = out + (size_t)rowy * P.nx;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        const cpx<T> z = buf[P.perm[j]];
-        const int i0 = 2 * j, i1 = 2 * j + 1;
-        if (i0 < P.nx) orow[P.flipx ? (P.nx - 1 - i0) : i0] = z.x;
-        if (i1 < P.nx) orow[P.flipx ? (P.nx - 1 - i1) : i1] = z.y;
+    const bool vec = (P.nx == P.nphi);
+    for (int j0 = threadIdx.x; j0 < n; j0 += FFT_IO_UNROLL * blockDim.x) {
+        int pj[FFT_IO_UNROLL];
+#pragma unroll
+        for (int u = 0; u < FFT_IO_UNROLL; ++u) { const int j = j0 + u * blockDim.x; pj[u] = (j < n) ? (int)P.perm[j] : 0; }
+#pragma unroll
+        for (int u = 0; u < FFT_IO_UNROLL; ++u) {
+            const int j = j0 + u * blockDim.x;
+            if (j < n) store_pair<T>(P, orow, j, buf[pj[u]], vec);
+        }
     }
 }
 
@@ -272,21 +354,27 @@ template <class T>
 __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams P)
 {
     PIXSHT_DYN_SMEM(smem_raw);
-    cpx<T>* buf = reinterpret_cast<cpx<T>*>(smem_raw);   // n + 1 entries
+    cpx<T>* buf = reinterpret_cast<cpx<T>*>(smem_raw);   // n + 1 entries, then the twiddle tables
+    const TwTab<T> W = tw_setup<T>(P, buf + P.n + 1);
     const int rl = blockIdx.x, c = P.c_begin + blockIdx.y, ring = P.ring_begin + rl;
     const int n = P.n, N = P.nphi;
     const T* in = reinterpret_cast<const T*>(P.maps[c]);
     const int rowy = P.flipy ? (P.ny - 1 - ring) : ring;
     const T* irow = in + (size_t)rowy * P.nx;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        const int i0 = 2 * j, i1 = 2 * j + 1;
-        cpx<T> z;
-        z.x = (i0 < P.nx) ? irow[P.flipx ? (P.nx - 1 - i0) : i0] : (T)0;
-        z.y = (i1 < P.nx) ? irow[P.flipx ? (P.nx - 1 - i1) : i1] : (T)0;
-        buf[P.perm[j]] = z;
+    const bool vec = (P.nx == P.nphi);
+    for (int j0 = threadIdx.x; j0 < n; j0 += FFT_IO_UNROLL * blockDim.x) {
+        cpx<T> z[FFT_IO_UNROLL]; int pj[FFT_IO_UNROLL];
+#pragma unroll
+        for (int u = 0; u < FFT_IO_UNROLL; ++u) {
+            const int j = j0 + u * blockDim.x;
+            pj[u] = 0; z[u].x = (T)0; z[u].y = (T)0;
+            if (j < n) { pj[u] = (int)P.perm[j]; z[u] = load_pair<T>(P, irow, j, vec); }
+        }
+#pragma unroll
+        for (int u = 0; u < FFT_IO_UNROLL; ++u) if ((int)(j0 + u * blockDim.x) < n) buf[pj[u]] = z[u];
     }
     __syncthreads();
-    fft_passes<T, -1, false>(P, buf);
+    fft_passes<T, -1, false>(P, W, buf);
 
     // post-processing in place: F[k] = ((Z[k] + conj Z[n-k]) - i e^{-2 pi i k/N} (Z[k] - conj Z[n-k])) / 2,  k = 0..n
     for (int k = threadIdx.x; k <= n / 2; k += blockDim.x) {
@@ -296,11 +384,11 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams 
             buf[0] = f0; buf[n] = fn;
         } else {
             const cpx<T> za = buf[k], zb = buf[n - k];
-            const cpx<T> ea = cadd(za, cconj(zb)), oa = cmul(csub(za, cconj(zb)), twid<T, -1>(P, k));
+            const cpx<T> ea = cadd(za, cconj(zb)), oa = cmul(csub(za, cconj(zb)), twid<T, -1>(W, k));
             const cpx<T> fa = cadd(ea, cmuli<T, -1>(oa));
             cpx<T> r; r.x = (T)0.5 * fa.x; r.y = (T)0.5 * fa.y;
             if (k != n - k) {
-                const cpx<T> eb = cadd(zb, cconj(za)), ob = cmul(csub(zb, cconj(za)), twid<T, -1>(P, n - k));
+                const cpx<T> eb = cadd(zb, cconj(za)), ob = cmul(csub(zb, cconj(za)), twid<T, -1>(W, n - k));
                 const cpx<T> fb = cadd(eb, cmuli<T, -1>(ob));
                 cpx<T> rb; rb.x = (T)0.5 * fb.x; rb.y = (T)0.5 * fb.y;
                 buf[n - k] = rb;
@@ -313,12 +401,19 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams 
     // phase_m = w * e^{-i m phi0} * F[m mod N]  (conjugate symmetric upper half); coalesced row write
     const double w = P.wgt[ring];
     double2* row = P.phase + ((long long)rl * P.ncomp + c) * P.MP;
-    for (int m = threadIdx.x; m <= P.mmax; m += blockDim.x) {
-        const int kk = (m < N) ? m : (m % N);
-        cpx<T> f = (kk <= n) ? buf[kk] : cconj(buf[N - kk]);
-        const double2 r = P.phi0tw[m];
-        const double fx = (double)f.x, fy = (double)f.y;
-        row[m] = make_double2(w * (fx * r.x + fy * r.y), w * (fy * r.x - fx * r.y));
+    for (int m0 = threadIdx.x; m0 <= P.mmax; m0 += FFT_IO_UNROLL * blockDim.x) {
+        double2 r[FFT_IO_UNROLL];
+#pragma unroll
+        for (int u = 0; u < FFT_IO_UNROLL; ++u) { const int m = m0 + u * blockDim.x; r[u] = (m <= P.mmax) ? P.phi0tw[m] : make_double2(0.0, 0.0); }
+#pragma unroll
+        for (int u = 0; u < FFT_IO_UNROLL; ++u) {
+            const int m = m0 + u * blockDim.x;
+            if (m > P.mmax) break;
+            const int kk = (m < N) ? m : (m % N);
+            const cpx<T> f = (kk <= n) ? buf[kk] : cconj(buf[N - kk]);
+            const double fx = (double)f.x, fy = (double)f.y;
+            row[m] = make_double2(w * (fx * r[u].x + fy * r[u].y), w * (fy * r[u].x - fx * r[u].y));
+        }
     }
 }
 

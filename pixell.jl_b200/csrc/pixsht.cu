@@ -273,7 +273,7 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     P->nfft = P->nphi / 2;
     if (factorize(P->nfft, P->fac, P->nfac)) return fail(PIXSHT_ERR_UNSUPPORTED, "nphi/2 has a prime factor > 64");
     const size_t elem = (P->dtype == PIXSHT_F64) ? 16 : 8;
-    P->fft_smem = (size_t)(P->nfft + 1) * elem;
+    P->fft_smem = (size_t)(P->nfft + 1 + fft_tw_entries(P->nphi)) * elem;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, P->device));
     P->sm_count = prop.multiProcessorCount;
@@ -1059,6 +1059,38 @@ __global__ void k_count_work(int lmax, int mmax, int npairs, int s, const int* _
         if (la <= lmax) exec += (unsigned long long)(lmax - la + 1);
     }
     atomicAdd(&out[0], exec); atomicAdd(&out[1], nominal);
+}
+
+// executed steps per m (one CTA per m): the load-balancing weight of the m-sharded multi-GPU partition
+__global__ void k_count_work_m(int lmax, int npairs, const int* __restrict__ lact, double* out)
+{
+    __shared__ double red[128];
+    const int m = blockIdx.x;
+    double acc = 0.0;
+    for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
+        const int la = lact[(size_t)m * npairs + p];
+        if (la <= lmax) acc += (double)(lmax - la + 1);
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) { if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) out[m] = red[0];
+}
+
+extern "C" int pixsht_plan_work_per_m(pixsht_plan* P, int spin, double* out)
+{
+    if (!P || !out || (spin != 0 && spin != 2)) return fail(PIXSHT_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lock(P->mu);
+    int rc = check_device(P->device); if (rc) return rc;
+    rc = ensure_seek(P, spin, P->stream); if (rc) return rc;
+    DevBuf<double> d;
+    if (d.alloc(P->mmax + 1)) return fail(PIXSHT_ERR_NOMEM, "allocation failed");
+    PIXSHT_LAUNCH(k_count_work_m, P->mmax + 1, 128, 0, P->stream, P->lmax, P->npairs, spin == 0 ? P->d_lact0.p : P->d_lact2.p, d.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, d.p, sizeof(double) * (P->mmax + 1), cudaMemcpyDeviceToHost, P->stream));
+    CU(cudaStreamSynchronize(P->stream));
+    d.release();
+    return PIXSHT_OK;
 }
 
 extern "C" int pixsht_plan_work(pixsht_plan* P, int spin, double out[2])

@@ -40,6 +40,19 @@ def partition_m(mmax, world):
     return [np.array(sorted(x), dtype=np.int32) for x in lists]
 
 
+def partition_m_weighted(weights, world):
+    """Longest-processing-time assignment of m values to ranks by measured work (executed Legendre steps per m, taken
+    from the plan's activation table), equal m counts not required.  Deterministic: every rank computes the same lists."""
+    order = np.argsort(-np.asarray(weights, dtype=np.float64), kind="stable")
+    load = np.zeros(world)
+    lists = [[] for _ in range(world)]
+    for m in order:
+        r = int(np.argmin(load))
+        lists[r].append(int(m))
+        load[r] += weights[m]
+    return [np.array(sorted(x), dtype=np.int32) for x in lists]
+
+
 def partition_rings(nrings, world):
     """Contiguous slabs [begin, end) of band rings per rank."""
     edges = [(nrings * r) // world for r in range(world + 1)]
@@ -52,7 +65,7 @@ class ShardedSHT:
 
     MAX_NCOMP = 3
 
-    def __init__(self, band, lmax, mmax=None, group=None, device=None, lib=None):
+    def __init__(self, band, lmax, mmax=None, group=None, device=None, lib=None, balance="work"):
         self.lib = get_lib() if lib is None else lib
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -68,7 +81,16 @@ class ShardedSHT:
         self.nalm = int(self.lib.lib.pixsht_nalm(self.lmax, self.mmax))
         self.MP = int(self.lib.lib.pixsht_phase_row_len(self.handle))
         self.nrings = band.nrings
-        self.m_lists = partition_m(self.mmax, self.world)
+        # m partition: by measured work per m when the library can report it (activation tables of both spin families,
+        # spin 2 weighted 3x: 12 vs 4 FP64 ops per step), else the closed-form (m, mmax-m) pairing
+        if self.world > 1 and balance == "work":
+            w0 = (ctypes.c_double * (self.mmax + 1))()
+            w2 = (ctypes.c_double * (self.mmax + 1))()
+            self.lib.check(self.lib.lib.pixsht_plan_work_per_m(self.handle, 0, w0))
+            self.lib.check(self.lib.lib.pixsht_plan_work_per_m(self.handle, 2, w2))
+            self.m_lists = partition_m_weighted(np.array(w0[:]) + 3.0 * np.array(w2[:]), self.world)
+        else:
+            self.m_lists = partition_m(self.mmax, self.world)
         self.ring_ranges = partition_rings(self.nrings, self.world)
         self.my_m = self.m_lists[self.rank]
         self.nm = len(self.my_m)

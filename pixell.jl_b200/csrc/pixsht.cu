@@ -190,9 +190,9 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
         // warp's spread of activation degrees; the wide setting pays off once a chunk is < 5 % of the pairs
         const bool wide = (nr + 1) / 2 >= 4096;
         int v = env_int("PIXSHT_R0", wide ? 8 : 4); P->R0 = (v == 1 || v == 2 || v == 3 || v == 4 || v == 6 || v == 8) ? v : 4;
-        v = env_int("PIXSHT_R2", wide ? 4 : 2); P->R2 = (v == 1 || v == 2 || v == 3 || v == 4) ? v : 2;
+        v = env_int("PIXSHT_R2", wide ? 4 : 2); P->R2 = (v == 1 || v == 2 || v == 3 || v == 4 || v == 6) ? v : 2;
         v = env_int("PIXSHT_R0A", P->R0); P->R0a = (v == 1 || v == 2 || v == 3 || v == 4 || v == 6 || v == 8) ? v : 4;
-        v = env_int("PIXSHT_R2A", 4); P->R2a = (v == 1 || v == 2 || v == 3 || v == 4) ? v : 4;
+        v = env_int("PIXSHT_R2A", 4); P->R2a = (v == 1 || v == 2 || v == 3 || v == 4 || v == 6) ? v : 4;
     }
 
     // ---- north/south pairing (equatorial symmetry): pair rings whose cos(theta) are opposite ----
@@ -281,8 +281,13 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
         return fail(PIXSHT_ERR_UNSUPPORTED, "ring too long for the single-CTA shared-memory FFT (nphi/2 complex samples must fit in 227 KB)");
     {
         // threads per CTA: the multiple of 32 that wastes the fewest thread-iterations over the passes
-        const int tmin = P->nfft >= 4096 ? 512 : (P->nfft >= 1024 ? 256 : (P->nfft >= 256 ? 128 : 64));
-        const int tmax = P->nfft >= 4096 ? FFT_MAXTHREADS : (P->nfft >= 1024 ? 512 : (P->nfft >= 256 ? 256 : 64));
+        // as many CTAs per SM as the shared memory allows (their load / compute / store phases then overlap), threads per CTA
+        // scaled down accordingly; among the candidates the multiple of 32 that wastes the fewest thread-iterations
+        int ctas = (int)(prop.sharedMemPerMultiprocessor / (P->fft_smem + 1024));
+        ctas = std::max(1, std::min(ctas, 4));
+        const int tcap = std::max(64, std::min(FFT_MAXTHREADS, (FFT_MAXTHREADS / ctas) / 32 * 32));
+        const int tmax = std::max(64, std::min(tcap, (P->nfft / 2 + 31) / 32 * 32));
+        const int tmin = std::max(64, tmax * 3 / 4 / 32 * 32);
         long long best = -1; int bt = tmax;
         for (int t = tmin; t <= tmax; t += 32) {
             long long cost = 0;
@@ -488,7 +493,7 @@ static void launch_synth(pixsht_plan* P, int R, const LegParams& L, cudaStream_t
     const int grid = L.nm * L.nchunks;
     if (grid <= 0) return;
     void (*k)(const LegParams) = (R == 1) ? leg_synth<SPIN, 1> : (R == 2 ? leg_synth<SPIN, 2> : (R == 3 ? leg_synth<SPIN, 3> :
-                                 (R == 8 && SPIN == 0 ? leg_synth<0, 8> : (R == 6 && SPIN == 0 ? leg_synth<0, 6> : leg_synth<SPIN, 4>))));
+                                 (R == 8 && SPIN == 0 ? leg_synth<0, 8> : (R == 6 ? leg_synth<SPIN, 6> : leg_synth<SPIN, 4>))));
     PIXSHT_LAUNCH(k, grid, LEG_NT, 0, st, L);
     P->launches++;
 }
@@ -498,7 +503,7 @@ static void launch_anal(pixsht_plan* P, int R, const LegParams& L, cudaStream_t 
     const int grid = L.nm * L.nchunks;
     if (grid <= 0) return;
     void (*k)(const LegParams) = (R == 1) ? leg_anal<SPIN, 1> : (R == 2 ? leg_anal<SPIN, 2> : (R == 3 ? leg_anal<SPIN, 3> :
-                                 (R == 8 && SPIN == 0 ? leg_anal<0, 8> : (R == 6 && SPIN == 0 ? leg_anal<0, 6> : leg_anal<SPIN, 4>))));
+                                 (R == 8 && SPIN == 0 ? leg_anal<0, 8> : (R == 6 ? leg_anal<SPIN, 6> : leg_anal<SPIN, 4>))));
     PIXSHT_LAUNCH(k, grid, LEG_NT, 0, st, L);
     P->launches++;
 }

@@ -152,7 +152,7 @@ enum { cudaSuccess = 0, cudaErrorUnknown = 999 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum { cudaStreamNonBlocking = 1 };
-struct cudaDeviceProp { int multiProcessorCount; size_t sharedMemPerBlockOptin; char name[64]; int major, minor; };
+struct cudaDeviceProp { int multiProcessorCount; size_t sharedMemPerBlockOptin; size_t sharedMemPerMultiprocessor = 233472; char name[64]; int major, minor; };
 static inline const char* cudaGetErrorString(cudaError_t) { return "emu error"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }

@@ -34,6 +34,7 @@ WORKLOADS = {
     "C2": dict(res_arcmin=4.0, lmax=2700, ncomp=1, dtype="f32", desc="full-sky CAR 4' (5400x2701) Float32 T-only, lmax=2700"),
     "C3": dict(res_arcmin=2.0, lmax=5400, ncomp=3, dtype="f64", desc="full-sky CAR 2' (10800x5401) Float64 IQU, lmax=5400"),
     "C4": dict(res_arcmin=1.0, lmax=10800, ncomp=3, dtype="f64", desc="full-sky CAR 1' (21600x10801) Float64 IQU, lmax=10800"),
+    "C5": dict(res_arcmin=0.5, lmax=21600, ncomp=1, dtype="f32", desc="full-sky CAR 0.5' (43200x21601) Float32 T-only, lmax=21600"),
 }
 METRIC = "alm2map+map2alm wall time"
 
@@ -166,7 +167,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": "%s: %s" % (args.workload, wl["desc"]), "ncomp": wl["ncomp"], "lmax": wl["lmax"],
-              "step": "one alm2map + one map2alm", "l2": "inputs larger than L2 (map+alm+phase >> 126 MB)" if args.workload in ("C3", "C4") else
+              "step": "one alm2map + one map2alm", "l2": "inputs larger than L2 (map+alm+phase >> 126 MB)" if args.workload in ("C3", "C4", "C5") else
               "inputs smaller than L2; 256 MB scratch written between timed steps"}
 
     if args.impl == "reference":
@@ -213,7 +214,7 @@ def main():
     esz = 8 if f64 else 4
     seed0 = 1000 * int(args.workload[1])
     stream = torch.cuda.current_stream(device)
-    l2_scratch = None if args.workload in ("C3", "C4") else torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)
+    l2_scratch = None if args.workload in ("C3", "C4", "C5") else torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)
 
     def flush_l2():
         if l2_scratch is not None:
@@ -305,9 +306,7 @@ def main():
         nrings = band.nrings
         plan_info = plan.info()
     else:
-        if not f64:
-            raise SystemExit("multi-GPU runs are Float64 (C3/C4)")
-        sht = ShardedSHT(band, lmax, device=device)
+        sht = ShardedSHT(band, lmax, device=device, dtype=rdt)
         nalm = sht.nalm
         a, b = sht.map_rows()
         d_alm = [synth_alm_device(torch, nalm, lmax, seed0 + c, c > 0, device, cdt) for c in range(nc)]
@@ -330,7 +329,8 @@ def main():
         stage = {"legendre_ms": leg_ms, "fft_ms": fft_ms, "exchange_ms": a2a_ms,
                  "exchange": "fused: Legendre kernels load/store phase rows in the owning GPU's memory over NVLink; exchange_ms is the "
                              "stage-ordering barrier (includes waiting for the slowest rank)"}
-        launches = 8 * args.steps   # 2 Legendre + 1 FFT kernels per direction of our own per rank (+ torch pack/unpack copies)
+        nfam = 2 if nc == 3 else 1   # spin families: each costs a prep + a synthesis launch one way and an analysis launch back
+        launches = (3 * nfam + 2) * args.steps   # + one FFT launch per direction; per rank
         e2e = None
         if not args.no_e2e:
             # each rank moves only what it owns: its alm columns (packed) and its rows of the map

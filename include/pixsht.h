@@ -84,7 +84,9 @@ int pixsht_get_timings(const pixsht_plan *plan, double ms[8]);
  * ALL m.  The Legendre stages, which run on a rank's own m values over all rings, reach every ring's row through a
  * device array of nrings pointers (d_ring_ptrs[ring] -> element (ring, 0, 0)); rows of rings owned by another GPU are
  * addresses inside that GPU's buffer (pixsht_shared_open), so the phase transpose of SURVEY.md 8(e) happens inside the
- * Legendre kernels' own loads/stores over NVLink and there is no separate exchange pass. */
+ * Legendre kernels' own loads/stores over NVLink and there is no separate exchange pass.
+ * Element types: phase rows and the alm of the Legendre stages are always complex double (a Float32 plan converts at the
+ * pixsht_execute boundary only); the maps of the FFT stages are of the plan's dtype. */
 int64_t pixsht_phase_row_len(const pixsht_plan *plan);
 /* Legendre stage over the m values m_list[0..nm) (device array of int32, or NULL for m = 0..nm-1). */
 int pixsht_stage_alm2phase(pixsht_plan *plan, int ncomp, const void *const *d_alms, int nm, const int32_t *d_m_list,

@@ -901,7 +901,6 @@ static int stage_common(pixsht_plan* P, int ncomp)
 {
     if (!P) return fail(PIXSHT_ERR_ARG, "null plan");
     if (ncomp < 1 || ncomp > 3) return fail(PIXSHT_ERR_ARG, "SHTs require 1 <= ncomp <= 3, for I, QU, and IQU.");
-    if (P->dtype != PIXSHT_F64) return fail(PIXSHT_ERR_UNSUPPORTED, "the stage API works on Float64 plans");
     return check_device(P->device);
 }
 

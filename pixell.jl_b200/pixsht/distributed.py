@@ -24,7 +24,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from ._lib import get_lib, Geom, F64
+from ._lib import get_lib, Geom, F64, F32
 
 
 def partition_m(mmax, world):
@@ -61,11 +61,12 @@ def partition_rings(nrings, world):
 
 class ShardedSHT:
     """Distributed map2alm / alm2map on one 8-GPU box.  All tensors live on `device` ('cuda:i', or 'cpu' with the
-    emulation library in the gloo tests).  Float64 only (the BASELINE multi-GPU configs are Float64)."""
+    emulation library in the gloo tests).  dtype = element type of the map slabs (float64 | float32); alm tensors are
+    complex128 or complex64 accordingly (Float32 data is widened on the device: the Legendre stage computes in FP64)."""
 
     MAX_NCOMP = 3
 
-    def __init__(self, band, lmax, mmax=None, group=None, device=None, lib=None, balance="work"):
+    def __init__(self, band, lmax, mmax=None, group=None, device=None, lib=None, balance="work", dtype=torch.float64):
         self.lib = get_lib() if lib is None else lib
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -76,7 +77,12 @@ class ShardedSHT:
         self.dev_index = self.device.index if self.device.type == "cuda" and self.device.index is not None else 0
         g = Geom(band.nphi, band.nrings_total, band.ring_first, band.nrings, band.nx, int(band.flipx), int(band.flipy), 0, band.phi0)
         h = ctypes.c_void_p()
-        self.lib.check(self.lib.lib.pixsht_plan_create(ctypes.byref(h), ctypes.byref(g), self.lmax, self.mmax, F64, self.dev_index))
+        self.dtype = dtype
+        if dtype not in (torch.float64, torch.float32):
+            raise TypeError("maps must be float64 or float32")
+        self.cdtype = torch.complex128 if dtype == torch.float64 else torch.complex64
+        self.lib.check(self.lib.lib.pixsht_plan_create(ctypes.byref(h), ctypes.byref(g), self.lmax, self.mmax,
+                                                       F64 if dtype == torch.float64 else F32, self.dev_index))
         self.handle = h
         self.nalm = int(self.lib.lib.pixsht_nalm(self.lmax, self.mmax))
         self.MP = int(self.lib.lib.pixsht_phase_row_len(self.handle))
@@ -180,9 +186,9 @@ class ShardedSHT:
         a, _ = self.map_rows()
         out = []
         for s in slabs:
-            if s.dtype != torch.float64 or not s.is_contiguous() or s.numel() != self.nloc * self.band.nx:
-                raise ValueError("map slab must be a contiguous float64 tensor of nx * (local rows) elements")
-            out.append(s.data_ptr() - a * self.band.nx * 8)
+            if s.dtype != self.dtype or not s.is_contiguous() or s.numel() != self.nloc * self.band.nx:
+                raise ValueError("map slab must be a contiguous %s tensor of nx * (local rows) elements" % self.dtype)
+            out.append(s.data_ptr() - a * self.band.nx * s.element_size())
         return (ctypes.c_void_p * len(out))(*out)
 
     def _ev(self):
@@ -210,6 +216,8 @@ class ShardedSHT:
         L = self.lib.lib
         st = self._stream_ptr()
         table = self._ring_table(nc)
+        if self.dtype != torch.float64:
+            d_alms = [a.to(torch.complex128) for a in d_alms]
         self._barrier()          # every rank is done with the previous contents of the phase buffers
         ev = [self._ev()]
         self.lib.check(L.pixsht_stage_alm2phase(self.handle, nc, self._ptrs(d_alms), self.nm, ctypes.c_void_p(self.d_m_list.data_ptr()),
@@ -236,10 +244,14 @@ class ShardedSHT:
         ev.append(self._ev())
         self._barrier()          # every ring's row is complete on its owner
         ev.append(self._ev())
-        for t in d_alms:
+        outs = d_alms if self.dtype == torch.float64 else [torch.empty(a.shape, dtype=torch.complex128, device=a.device) for a in d_alms]
+        for t in outs:
             t.zero_()   # the analysis kernels accumulate atomically into pre-zeroed columns
         self.lib.check(L.pixsht_stage_phase2alm(self.handle, nc, ctypes.c_void_p(table.data_ptr()), self.nm,
-                                                ctypes.c_void_p(self.d_m_list.data_ptr()), self._ptrs(d_alms), st))
+                                                ctypes.c_void_p(self.d_m_list.data_ptr()), self._ptrs(outs), st))
+        if outs is not d_alms:
+            for a, o in zip(d_alms, outs):
+                a.copy_(o)
         ev.append(self._ev())
         self._record("map2alm", ev)
 

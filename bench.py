@@ -327,8 +327,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         leg_ms, fft_ms, a2a_ms = [float(x) for x in t.tolist()]
         stage = {"legendre_ms": leg_ms, "fft_ms": fft_ms, "exchange_ms": a2a_ms,
-                 "exchange": "fused: Legendre kernels load/store phase rows in the owning GPU's memory over NVLink; exchange_ms is the "
-                             "stage-ordering barrier (includes waiting for the slowest rank)"}
+                 "exchange": "fused: the FFT kernels' row loads/stores fetch/put every m in the phase buffer of the GPU that owns it "
+                             "(peer memory over NVLink, 256-byte runs); exchange_ms is the stage-ordering barrier (includes waiting "
+                             "for the slowest rank)"}
         nfam = 2 if nc == 3 else 1   # spin families: each costs a prep + a synthesis launch one way and an analysis launch back
         launches = (3 * nfam + 2) * args.steps   # + one FFT launch per direction; per rank
         e2e = None

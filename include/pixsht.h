@@ -79,26 +79,27 @@ int pixsht_plan_set_stream(pixsht_plan *plan, void *stream, int use_caller_strea
 int pixsht_get_timings(const pixsht_plan *plan, double ms[8]);
 
 /* ---- stage API for the m-sharded multi-GPU pipeline (device pointers, asynchronous on `stream`) ------------
- * Phase rows: one contiguous row of MP = pixsht_phase_row_len(plan) complex doubles per (ring, component), element
- * (ring_local, c, m) at ((ring_local*ncomp + c)*MP + m).  A rank's phase buffer holds the rows of ITS slab of rings for
- * ALL m.  The Legendre stages, which run on a rank's own m values over all rings, reach every ring's row through a
- * device array of nrings pointers (d_ring_ptrs[ring] -> element (ring, 0, 0)); rows of rings owned by another GPU are
- * addresses inside that GPU's buffer (pixsht_shared_open), so the phase transpose of SURVEY.md 8(e) happens inside the
- * Legendre kernels' own loads/stores over NVLink and there is no separate exchange pass.
+ * m-sharded phase layout: a rank's phase buffer holds ITS m values for ALL band rings, element (ring, c, i) at
+ * ((ring*ncomp + c)*row_len + i) with i the position of m in the rank's m_list and row_len >= nm.  The Legendre stages work
+ * on that local buffer.  The FFT stages, which run on a rank's slab of rings over all m, reach every m through a device
+ * table d_mtab of 2*(mmax+1) int64: [2m] = address of element (ring 0, comp 0, m) in the buffer of the rank that owns m
+ * (pixsht_shared_open for peers), [2m+1] = that buffer's row_len.  With m dealt to ranks in runs of 16 the remote
+ * accesses are 256-byte runs, so the phase transpose of SURVEY.md 8(e) happens inside the FFT kernels' own row loads /
+ * stores over NVLink and there is no separate exchange pass.
  * Element types: phase rows and the alm of the Legendre stages are always complex double (a Float32 plan converts at the
  * pixsht_execute boundary only); the maps of the FFT stages are of the plan's dtype. */
-int64_t pixsht_phase_row_len(const pixsht_plan *plan);
+int64_t pixsht_phase_row_len(const pixsht_plan *plan);   /* row length of the single-GPU layout (mmax+1 rounded up to 8) */
 /* Legendre stage over the m values m_list[0..nm) (device array of int32, or NULL for m = 0..nm-1). */
 int pixsht_stage_alm2phase(pixsht_plan *plan, int ncomp, const void *const *d_alms, int nm, const int32_t *d_m_list,
-                           void *const *d_ring_ptrs, void *stream);
-int pixsht_stage_phase2alm(pixsht_plan *plan, int ncomp, void *const *d_ring_ptrs, int nm, const int32_t *d_m_list,
+                           void *d_phase, int64_t row_len, void *stream);
+int pixsht_stage_phase2alm(pixsht_plan *plan, int ncomp, const void *d_phase, int64_t row_len, int nm, const int32_t *d_m_list,
                            void *const *d_alms, void *stream);
-/* FFT stage over band rings [ring_begin, ring_begin+ring_count): d_phase holds the rows of exactly those rings;
- * d_maps are the full caller-layout maps (only the rows of those rings are touched). */
-int pixsht_stage_phase2map(pixsht_plan *plan, int ncomp, const void *d_phase, int ring_begin, int ring_count,
+/* FFT stage over band rings [ring_begin, ring_begin+ring_count); d_maps are the full caller-layout maps (only the rows of
+ * those rings are touched). */
+int pixsht_stage_phase2map(pixsht_plan *plan, int ncomp, const int64_t *d_mtab, int ring_begin, int ring_count,
                            void *const *d_maps, void *stream);
 int pixsht_stage_map2phase(pixsht_plan *plan, int ncomp, const void *const *d_maps, int ring_begin, int ring_count,
-                           void *d_phase, void *stream);
+                           const int64_t *d_mtab, void *stream);
 /* Peer-visible device memory for the phase buffers (CUDA IPC between the one-process-per-GPU ranks of a node):
  * alloc on the owner and export a 64-byte handle; open maps a peer's buffer into this process (peer access over
  * NVLink is enabled lazily); close unmaps an opened buffer; free releases an owned one. */

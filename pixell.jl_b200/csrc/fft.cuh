@@ -38,6 +38,8 @@ struct FftParams {
     const unsigned short* perm; // [n] position of natural index j in the permuted buffer
     int mmax;
     double2* phase;             // this launch's rows: (ringlocal, c, m) at ((ringlocal*ncomp + c)*MP + m)
+    const long long* mtab;      // m-sharded layout (multi-GPU), else nullptr: per m the address of element (ring 0, comp 0, m)
+                                // in the buffer of the GPU that owns m (possibly peer memory) and that buffer's row length
     long long MP;
     int ncomp, c_begin;         // components per ring in the phase buffer; first component handled by this launch (grid.y of them)
     int ring_begin, ring_count; // band rings handled by this launch; ringlocal = ring - ring_begin
@@ -224,17 +226,25 @@ __device__ void fft_passes(const FftParams& P, const TwTab<T>& W, cpx<T>* buf)
     }
 }
 
+// phase element (band ring, component c, m): in this launch's local rows, or -- m-sharded -- in the buffer of m's owner
+__device__ __forceinline__ double2* phase_elem(const FftParams& P, double2* localrow, int ring, int c, int m)
+{
+    if (!P.mtab) return localrow + m;
+    const long long base = P.mtab[2 * m], mp = P.mtab[2 * m + 1];
+    return reinterpret_cast<double2*>(base) + ((long long)ring * P.ncomp + c) * mp;
+}
+
 // aliased half-spectrum entry X[k], 0 <= k <= n: sum over m == +-k (mod nphi) of the rotated phases (general mmax)
 template <class T>
-__device__ __forceinline__ cpx<T> load_X(const FftParams& P, const double2* row, int k)
+__device__ __forceinline__ cpx<T> load_X(const FftParams& P, double2* row, int ring, int c, int k)
 {
     double sx = 0.0, sy = 0.0;
     for (int m = k; m <= P.mmax; m += P.nphi) {
-        const double2 a = row[m], r = P.phi0tw[m];
+        const double2 a = *phase_elem(P, row, ring, c, m), r = P.phi0tw[m];
         sx += a.x * r.x - a.y * r.y; sy += a.x * r.y + a.y * r.x;
     }
     for (int m = P.nphi - k; m <= P.mmax; m += P.nphi) {
-        const double2 a = row[m], r = P.phi0tw[m];
+        const double2 a = *phase_elem(P, row, ring, c, m), r = P.phi0tw[m];
         sx += a.x * r.x - a.y * r.y; sy -= a.x * r.y + a.y * r.x;
     }
     cpx<T> v; v.x = (T)sx; v.y = (T)sy;
@@ -283,7 +293,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
     const TwTab<T> W = tw_setup<T>(P, buf + P.n + 1);
     const int rl = blockIdx.x, c = P.c_begin + blockIdx.y, ring = P.ring_begin + rl;
     const int n = P.n;
-    const double2* row = P.phase + ((long long)rl * P.ncomp + c) * P.MP;
+    double2* row = P.phase + ((long long)rl * P.ncomp + c) * P.MP;
 
     // X[k], k = 0..n, natural order (coalesced row read)
     if (P.mmax <= n) {
@@ -293,7 +303,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
             for (int u = 0; u < FFT_IO_UNROLL; ++u) {
                 const int k = k0 + u * blockDim.x;
                 a[u] = make_double2(0.0, 0.0); r[u] = a[u];
-                if (k <= P.mmax) { a[u] = row[k]; r[u] = P.phi0tw[k]; }
+                if (k <= P.mmax) { a[u] = *phase_elem(P, row, ring, c, k); r[u] = P.phi0tw[k]; }
             }
 #pragma unroll
             for (int u = 0; u < FFT_IO_UNROLL; ++u) {
@@ -307,7 +317,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
             }
         }
     } else {
-        for (int k = threadIdx.x; k <= n; k += blockDim.x) buf[k] = load_X<T>(P, row, k);
+        for (int k = threadIdx.x; k <= n; k += blockDim.x) buf[k] = load_X<T>(P, row, ring, c, k);
     }
     __syncthreads();
 
@@ -412,7 +422,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams 
             const int kk = (m < N) ? m : (m % N);
             const cpx<T> f = (kk <= n) ? buf[kk] : cconj(buf[N - kk]);
             const double fx = (double)f.x, fy = (double)f.y;
-            row[m] = make_double2(w * (fx * r[u].x + fy * r[u].y), w * (fy * r[u].x - fx * r[u].y));
+            *phase_elem(P, row, ring, c, m) = make_double2(w * (fx * r[u].x + fy * r[u].y), w * (fy * r[u].x - fx * r[u].y));
         }
     }
 }

@@ -52,18 +52,16 @@ struct LegParams {
     const double* gamma;    // [nalm]
     const double* rec;      // synthesis: [nalm * SynthRec::ND] records
     double2* alm_out0; double2* alm_out1;               // analysis output  (T | E,B), pre-zeroed, accumulated atomically
-    // phase element (ring, component c, m) lives at ring_base(ring) + c*MP + m, where ring_base(ring) is
-    // ring_ptr[ring] when a pointer table is given (multi-GPU: the row may sit in a peer GPU's memory, reached over
-    // NVLink) and phase + ring*ring_stride otherwise.  c0 = first component handled by this launch.
+    // phase element (ring, component c, column) lives at phase + ring*ring_stride + c*MP + column.  The column of an m is m
+    // itself in the single-GPU layout (rows hold all m) and the launch row (position in m_list) in the m-sharded layout,
+    // where a rank's buffer holds only its own m values for all rings.  c0 = first component handled by this launch.
     double2* phase; long long ring_stride;
-    double2* const* ring_ptr;
-    long long MP; int c0;
+    long long MP; int c0; int col_is_row;
 };
 
-__device__ __forceinline__ double2* phase_row(const LegParams& P, int ring, int m)
+__device__ __forceinline__ double2* phase_row(const LegParams& P, int ring, int col)
 {
-    double2* base = P.ring_ptr ? P.ring_ptr[ring] : (P.phase + (long long)ring * P.ring_stride);
-    return base + (long long)P.c0 * P.MP + m;
+    return P.phase + (long long)ring * P.ring_stride + (long long)P.c0 * P.MP + col;
 }
 
 // plan-time inputs of the activation table
@@ -417,6 +415,7 @@ __global__ void __launch_bounds__(LEG_NT) leg_synth(const LegParams P)
     }
 
     // ---- write phase (zeros for pruned / never-activated rings) ----
+    const int col = P.col_is_row ? row : m;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
         const int pair = pair0 + j * 32 + lane;
@@ -424,19 +423,19 @@ __global__ void __launch_bounds__(LEG_NT) leg_synth(const LegParams P)
         const int rN = P.ringN[pair], rS = P.ringS[pair];
         if (SPIN == 0) {
             const double er = acc[0][j], ei = acc[1][j], orr = acc[2][j], oi = acc[3][j];
-            if (rN >= 0) *phase_row(P, rN, m) = make_double2(er + orr, ei + oi);
-            if (rS >= 0) *phase_row(P, rS, m) = make_double2(er - orr, ei - oi);
+            if (rN >= 0) *phase_row(P, rN, col) = make_double2(er + orr, ei + oi);
+            if (rS >= 0) *phase_row(P, rS, col) = make_double2(er - orr, ei - oi);
         } else {
             // q = S+ + S-, u = -i (S+ - S-);  south: base sign (-1)^(l0+m) times the alternating sums
             const double bs = ((l0 + m) & 1) ? -1.0 : 1.0;
             constexpr int A4 = (SPIN == 0 ? 0 : 4);
             if (rN >= 0) {
-                double2* ph = phase_row(P, rN, m);
+                double2* ph = phase_row(P, rN, col);
                 ph[0] = make_double2(acc[0][j] + acc[2][j], acc[1][j] + acc[3][j]);
                 ph[P.MP] = make_double2(acc[1][j] - acc[3][j], -(acc[0][j] - acc[2][j]));
             }
             if (rS >= 0) {
-                double2* ph = phase_row(P, rS, m);
+                double2* ph = phase_row(P, rS, col);
                 ph[0] = make_double2(bs * (acc[A4 + 0][j] + acc[A4 + 2][j]), bs * (acc[A4 + 1][j] + acc[A4 + 3][j]));
                 ph[P.MP] = make_double2(bs * (acc[A4 + 1][j] - acc[A4 + 3][j]), -bs * (acc[A4 + 0][j] - acc[A4 + 2][j]));
             }
@@ -510,14 +509,15 @@ __global__ void __launch_bounds__(LEG_NT) leg_anal(const LegParams P)
     // folded inputs
     double X[NX][R];
     const double bs = ((l0 + m) & 1) ? -1.0 : 1.0;
+    const int col = P.col_is_row ? row : m;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
         const int pair = pair0 + j * 32 + lane;
         double2 qN = make_double2(0.0, 0.0), qS = qN, uN = qN, uS = qN;
         if (S.la[j] != L_NEVER) {
             const int rN = P.ringN[pair], rS = P.ringS[pair];
-            if (rN >= 0) { const double2* ph = phase_row(P, rN, m); qN = ph[0]; if (SPIN != 0) uN = ph[P.MP]; }
-            if (rS >= 0) { const double2* ph = phase_row(P, rS, m); qS = ph[0]; if (SPIN != 0) uS = ph[P.MP]; }
+            if (rN >= 0) { const double2* ph = phase_row(P, rN, col); qN = ph[0]; if (SPIN != 0) uN = ph[P.MP]; }
+            if (rS >= 0) { const double2* ph = phase_row(P, rS, col); qS = ph[0]; if (SPIN != 0) uS = ph[P.MP]; }
         }
         if (SPIN == 0) {
             X[0][j] = qN.x + qS.x; X[1][j] = qN.y + qS.y;

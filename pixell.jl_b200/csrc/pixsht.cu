@@ -465,8 +465,8 @@ static int ensure_seek(pixsht_plan* P, int spin, cudaStream_t st)
     return PIXSHT_OK;
 }
 
-// where the phase rows of a launch live: a local buffer (ring r at phase + r*ncomp*MP) or a per-ring pointer table
-struct PhaseRef { double2* phase; double2* const* ring_ptr; };
+// where the phase rows of a Legendre launch live: ring r at phase + r*ncomp*MP; columns are m (single GPU) or launch rows (m-sharded)
+struct PhaseRef { double2* phase; long long MP; int col_is_row; };   // MP = 0: the plan's own row length
 
 // one Legendre launch: m values [m_begin, m_begin+nm) (or m_list[0..nm)), chunks [chunk_begin, chunk_begin+nchunks) of 32*R pairs
 struct LegJob { int spin, ncomp, c0; int m_begin, nm; const int* m_list; int chunk_begin, nchunks; PhaseRef ph; };
@@ -483,7 +483,8 @@ static LegParams leg_params(pixsht_plan* P, const LegJob& J, int R)
     L.x = P->d_x.p; L.ringN = P->d_ringN.p; L.ringS = P->d_ringS.p;
     if (J.spin == 0) { L.lact = P->d_lact0.p; L.st = P->d_st0.p; L.ad = P->d_ad0.p; L.gamma = P->d_gamma0.p; L.rec = P->d_rec0.p; }
     else { L.lact = P->d_lact2.p; L.st = P->d_st2.p; L.ad = P->d_ad2.p; L.gamma = P->d_gamma2.p; L.rec = P->d_rec2.p; }
-    L.phase = J.ph.phase; L.ring_ptr = J.ph.ring_ptr; L.ring_stride = (long long)J.ncomp * P->MP; L.MP = P->MP; L.c0 = J.c0;
+    L.MP = J.ph.MP > 0 ? J.ph.MP : P->MP; L.col_is_row = J.ph.col_is_row;
+    L.phase = J.ph.phase; L.ring_stride = (long long)J.ncomp * L.MP; L.c0 = J.c0;
     return L;
 }
 
@@ -592,7 +593,7 @@ static int stage_phase2alm(pixsht_plan* P, int ncomp, PhaseRef ph, int nm, const
 // FFT stage for components [c_begin, c_begin+c_count) of band rings [ring_begin, ring_begin+ring_count); `phase` points at the
 // row of (ring_begin, component 0) in a buffer with ncomp components per ring
 static int stage_fft(pixsht_plan* P, int dir, int ncomp, int c_begin, int c_count, double2* phase, int ring_begin, int ring_count,
-                     void* const* maps, cudaStream_t st)
+                     void* const* maps, cudaStream_t st, const long long* mtab = nullptr)
 {
     if (ring_count <= 0 || c_count <= 0) return PIXSHT_OK;
     FftParams F;
@@ -600,7 +601,7 @@ static int stage_fft(pixsht_plan* P, int dir, int ncomp, int c_begin, int c_coun
     F.nphi = P->nphi; F.n = P->nfft; F.nfac = P->nfac;
     for (int i = 0; i < P->nfac; ++i) { F.fac[i] = P->fac[i]; F.magic[i] = P->fft_magic[i]; }
     F.tw = P->d_tw.p; F.phi0tw = P->d_phi0tw.p; F.wgt = P->d_wgt.p; F.perm = P->d_perm.p; F.mmax = P->mmax;
-    F.phase = phase; F.MP = P->MP; F.ncomp = ncomp; F.c_begin = c_begin;
+    F.phase = phase; F.mtab = mtab; F.MP = P->MP; F.ncomp = ncomp; F.c_begin = c_begin;
     F.ring_begin = ring_begin; F.ring_count = ring_count;
     F.nx = P->nx; F.ny = P->ny; F.flipx = P->flipx; F.flipy = P->flipy;
     for (int c = 0; c < ncomp; ++c) F.maps[c] = maps[c];
@@ -672,7 +673,7 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
             dalm64[c] = P->d_alm64[c].p;
         } else dalm64[c] = reinterpret_cast<double2*>(dalm[c]);
     }
-    const PhaseRef ph = {P->d_phase.p, nullptr};
+    const PhaseRef ph = {P->d_phase.p, 0, 0};
     int ndep = 0;
     auto next_ev = [&]() { return P->dep[ndep++ % 48]; };
     const int c0 = ncomp == 3 ? 1 : 0;          // first spin-2 component
@@ -834,7 +835,7 @@ extern "C" int pixsht_execute(pixsht_plan* P, int direction, int ncomp, void* co
             dalm64[c] = P->d_alm64[c].p;
         } else dalm64[c] = reinterpret_cast<double2*>(dalm[c]);
     }
-    const PhaseRef ph = {P->d_phase.p, nullptr};
+    const PhaseRef ph = {P->d_phase.p, 0, 0};
     const int cvt_grid = P->sm_count > 0 ? P->sm_count * 8 : 256;
 
     CU(cudaEventRecord(P->ev[0], st));
@@ -907,43 +908,43 @@ static int stage_common(pixsht_plan* P, int ncomp)
 extern "C" int64_t pixsht_phase_row_len(const pixsht_plan* P) { return P ? (int64_t)P->MP : 0; }
 
 extern "C" int pixsht_stage_alm2phase(pixsht_plan* P, int ncomp, const void* const* d_alms, int nm, const int32_t* d_m_list,
-                                      void* const* d_ring_ptrs, void* stream)
+                                      void* d_phase, int64_t row_len, void* stream)
 {
     int rc = stage_common(P, ncomp); if (rc) return rc;
-    if (!d_alms || !d_ring_ptrs || nm < 0 || nm > P->mmax + 1) return fail(PIXSHT_ERR_ARG, "bad argument");
+    if (!d_alms || !d_phase || nm < 0 || nm > P->mmax + 1 || row_len < nm) return fail(PIXSHT_ERR_ARG, "bad argument");
     if (nm == 0) return PIXSHT_OK;
     const double2* alm[3] = {nullptr, nullptr, nullptr};
     for (int c = 0; c < ncomp; ++c) alm[c] = (const double2*)d_alms[c];
-    const PhaseRef ph = {nullptr, (double2* const*)d_ring_ptrs};
+    const PhaseRef ph = {(double2*)d_phase, (long long)row_len, 1};
     return stage_alm2phase(P, ncomp, alm, nm, d_m_list, ph, (cudaStream_t)stream);
 }
 
-extern "C" int pixsht_stage_phase2alm(pixsht_plan* P, int ncomp, void* const* d_ring_ptrs, int nm, const int32_t* d_m_list,
+extern "C" int pixsht_stage_phase2alm(pixsht_plan* P, int ncomp, const void* d_phase, int64_t row_len, int nm, const int32_t* d_m_list,
                                       void* const* d_alms, void* stream)
 {
     int rc = stage_common(P, ncomp); if (rc) return rc;
-    if (!d_alms || !d_ring_ptrs || nm < 0 || nm > P->mmax + 1) return fail(PIXSHT_ERR_ARG, "bad argument");
+    if (!d_alms || !d_phase || nm < 0 || nm > P->mmax + 1 || row_len < nm) return fail(PIXSHT_ERR_ARG, "bad argument");
     if (nm == 0) return PIXSHT_OK;
     double2* alm[3] = {nullptr, nullptr, nullptr};
     for (int c = 0; c < ncomp; ++c) alm[c] = (double2*)d_alms[c];
-    const PhaseRef ph = {nullptr, (double2* const*)d_ring_ptrs};
+    const PhaseRef ph = {(double2*)d_phase, (long long)row_len, 1};
     return stage_phase2alm(P, ncomp, ph, nm, d_m_list, alm, (cudaStream_t)stream);
 }
 
-extern "C" int pixsht_stage_phase2map(pixsht_plan* P, int ncomp, const void* d_phase, int ring_begin, int ring_count,
+extern "C" int pixsht_stage_phase2map(pixsht_plan* P, int ncomp, const int64_t* d_mtab, int ring_begin, int ring_count,
                                       void* const* d_maps, void* stream)
 {
     int rc = stage_common(P, ncomp); if (rc) return rc;
-    if (!d_maps || !d_phase || ring_begin < 0 || ring_count < 0 || ring_begin + ring_count > P->nrings) return fail(PIXSHT_ERR_ARG, "bad argument");
-    return stage_fft(P, PIXSHT_ALM2MAP, ncomp, 0, ncomp, (double2*)d_phase, ring_begin, ring_count, d_maps, (cudaStream_t)stream);
+    if (!d_maps || !d_mtab || ring_begin < 0 || ring_count < 0 || ring_begin + ring_count > P->nrings) return fail(PIXSHT_ERR_ARG, "bad argument");
+    return stage_fft(P, PIXSHT_ALM2MAP, ncomp, 0, ncomp, nullptr, ring_begin, ring_count, d_maps, (cudaStream_t)stream, (const long long*)d_mtab);
 }
 
 extern "C" int pixsht_stage_map2phase(pixsht_plan* P, int ncomp, const void* const* d_maps, int ring_begin, int ring_count,
-                                      void* d_phase, void* stream)
+                                      const int64_t* d_mtab, void* stream)
 {
     int rc = stage_common(P, ncomp); if (rc) return rc;
-    if (!d_maps || !d_phase || ring_begin < 0 || ring_count < 0 || ring_begin + ring_count > P->nrings) return fail(PIXSHT_ERR_ARG, "bad argument");
-    return stage_fft(P, PIXSHT_MAP2ALM, ncomp, 0, ncomp, (double2*)d_phase, ring_begin, ring_count, (void* const*)d_maps, (cudaStream_t)stream);
+    if (!d_maps || !d_mtab || ring_begin < 0 || ring_count < 0 || ring_begin + ring_count > P->nrings) return fail(PIXSHT_ERR_ARG, "bad argument");
+    return stage_fft(P, PIXSHT_MAP2ALM, ncomp, 0, ncomp, nullptr, ring_begin, ring_count, (void* const*)d_maps, (cudaStream_t)stream, (const long long*)d_mtab);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

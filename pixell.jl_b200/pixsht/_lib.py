@@ -53,8 +53,8 @@ class PixshtLib:
         L.pixsht_execute.argtypes = [vp, i32, i32, pvp, pvp, i32]
         L.pixsht_plan_set_stream.argtypes = [vp, vp, i32]
         L.pixsht_get_timings.argtypes = [vp, ctypes.POINTER(dbl)]
-        L.pixsht_stage_alm2phase.argtypes = [vp, i32, pvp, i32, vp, vp, vp]
-        L.pixsht_stage_phase2alm.argtypes = [vp, i32, vp, i32, vp, pvp, vp]
+        L.pixsht_stage_alm2phase.argtypes = [vp, i32, pvp, i32, vp, vp, ctypes.c_int64, vp]
+        L.pixsht_stage_phase2alm.argtypes = [vp, i32, vp, ctypes.c_int64, i32, vp, pvp, vp]
         L.pixsht_stage_phase2map.argtypes = [vp, i32, vp, i32, i32, pvp, vp]
         L.pixsht_stage_map2phase.argtypes = [vp, i32, pvp, i32, i32, vp, vp]
         L.pixsht_plan_work.argtypes = [vp, i32, ctypes.POINTER(dbl)]

@@ -1,19 +1,21 @@
 """m-sharded multi-GPU pipeline: one process per GPU, torch.distributed for the plumbing.
 
-  alm2map:  Legendre stage on this rank's m values (all rings), writing every phase value straight into the phase
-            buffer of the GPU that owns its ring (peer memory over NVLink)  ->  stream-ordered barrier  ->  ring FFTs on
-            this rank's contiguous slab of rings (all m)  ->  the rank's rows of the map.
-  map2alm:  ring FFTs of the rank's rows into its own phase buffer  ->  barrier  ->  Legendre analysis on the rank's m
-            values, reading each ring's phase value from the GPU that owns the ring.
+  alm2map:  Legendre stage on this rank's m values (all rings) into the rank's own phase buffer  ->  stream-ordered
+            barrier  ->  ring FFTs on this rank's contiguous slab of rings, whose row loads fetch every m from the phase
+            buffer of the GPU that owns it (peer memory over NVLink)  ->  the rank's rows of the map.
+  map2alm:  ring FFTs of the rank's rows, whose row stores put every m into its owner's phase buffer  ->  barrier  ->
+            Legendre analysis on the rank's m values from its own buffer.
 
-So the phase transpose between the m-sharded and the ring-sharded stage is fused into the Legendre kernels' own loads
-and stores (they are FP64 bound, the memory system and the NVLink ports are idle while they run); there is no pack /
-all-to-all / unpack pass and no second copy of the phase array.  The only collective left is the barrier that orders the
-two stages (a 1-element all-reduce on the compute stream with NCCL; dist.barrier() with gloo).
+So the phase transpose between the m-sharded and the ring-sharded stage is fused into the FFT kernels' own row loads and
+stores; there is no pack / all-to-all / unpack pass and no second copy of the phase array.  m values are dealt to ranks
+in runs of 16 consecutive m, so the remote accesses are 256-byte runs (16-byte remote stores from the Legendre kernels --
+the first design -- hit an NVLink transaction-rate ceiling at 8 GPUs: 106 ms instead of 74 ms of Legendre time at C4).
+The only collective left is the barrier that orders the two stages (a 1-element all-reduce on the compute stream with
+NCCL; dist.barrier() with gloo).
 
-Partition: m values are dealt out in load-balanced pairs (m, mmax-m) -- the Legendre cost of an m is ~ (lmax-m+1), so a
-pair costs the same whichever it is; rings are split into contiguous slabs, which are contiguous row ranges of the
-caller's column-major map.  Nothing else is partitioned; tables are replicated.
+Partition: runs of 16 m are assigned by longest-processing-time on the measured work per m (executed Legendre steps from
+the plan's activation tables); rings are split into contiguous slabs, which are contiguous row ranges of the caller's
+column-major map.  Nothing else is partitioned; tables are replicated.
 
 The compute stages are the pixsht_stage_* entry points of the C ABI; the peer-visible buffers are pixsht_shared_alloc /
 pixsht_shared_open (CUDA IPC; POSIX shared memory in the host-emulation build that the gloo CPU tests use).
@@ -40,16 +42,24 @@ def partition_m(mmax, world):
     return [np.array(sorted(x), dtype=np.int32) for x in lists]
 
 
-def partition_m_weighted(weights, world):
-    """Longest-processing-time assignment of m values to ranks by measured work (executed Legendre steps per m, taken
-    from the plan's activation table), equal m counts not required.  Deterministic: every rank computes the same lists."""
-    order = np.argsort(-np.asarray(weights, dtype=np.float64), kind="stable")
+M_RUN = 16   # consecutive m per assignment unit: 256-byte runs in the phase rows
+
+
+def partition_m_weighted(weights, world, run=M_RUN):
+    """Longest-processing-time assignment of runs of `run` consecutive m values to ranks by work (weights[m]; measured:
+    executed Legendre steps per m from the plan's activation tables), equal m counts not required.  Deterministic: every
+    rank computes the same lists."""
+    weights = np.asarray(weights, dtype=np.float64)
+    n = len(weights)
+    starts = np.arange(0, n, run)
+    wrun = np.add.reduceat(weights, starts)
+    order = np.argsort(-wrun, kind="stable")
     load = np.zeros(world)
     lists = [[] for _ in range(world)]
-    for m in order:
+    for b in order:
         r = int(np.argmin(load))
-        lists[r].append(int(m))
-        load[r] += weights[m]
+        lists[r].extend(range(int(starts[b]), min(n, int(starts[b]) + run)))
+        load[r] += wrun[b]
     return [np.array(sorted(x), dtype=np.int32) for x in lists]
 
 
@@ -96,7 +106,8 @@ class ShardedSHT:
             self.lib.check(self.lib.lib.pixsht_plan_work_per_m(self.handle, 2, w2))
             self.m_lists = partition_m_weighted(np.array(w0[:]) + 3.0 * np.array(w2[:]), self.world)
         else:
-            self.m_lists = partition_m(self.mmax, self.world)
+            # closed form: cost of an m ~ lmax - m + 1 (no pruning)
+            self.m_lists = partition_m_weighted(self.lmax + 1.0 - np.arange(self.mmax + 1), self.world)
         self.ring_ranges = partition_rings(self.nrings, self.world)
         self.my_m = self.m_lists[self.rank]
         self.nm = len(self.my_m)
@@ -104,9 +115,11 @@ class ShardedSHT:
         self.nloc = self.r1 - self.r0
         self.d_m_list = torch.from_numpy(self.my_m.copy()).to(self.device)
         self.last_ms = {}
-        # ---- peer-visible phase buffer: this rank's rings x MAX_NCOMP components x MP complex doubles ----
+        # ---- peer-visible phase buffer: all rings x MAX_NCOMP components x (this rank's m values, padded) complex doubles ----
         L = self.lib.lib
-        nbytes = max(1, self.nloc) * self.MAX_NCOMP * self.MP * 16
+        self.row_lens = [(len(ml) + 7) // 8 * 8 for ml in self.m_lists]
+        self.row_len = self.row_lens[self.rank]
+        nbytes = self.nrings * self.MAX_NCOMP * max(8, self.row_len) * 16
         own = ctypes.c_void_p()
         hbuf = ctypes.create_string_buffer(64)
         self.lib.check(L.pixsht_shared_alloc(self.dev_index, nbytes, ctypes.byref(own), hbuf))
@@ -124,7 +137,7 @@ class ShardedSHT:
                 self.lib.check(L.pixsht_shared_open(self.dev_index, handles[r], ctypes.byref(p)))
                 self.peer_ptrs[r] = p.value
                 self._opened.append(p.value)
-        self._ring_tables = {}
+        self._mtab = None
         self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
 
     # ---- the caller's view of the data ---------------------------------------------------------------------------
@@ -163,15 +176,16 @@ class ShardedSHT:
             pass
 
     # ---- helpers -----------------------------------------------------------------------------------------------
-    def _ring_table(self, nc):
-        """Device array of nrings pointers: element (ring, component 0, m 0) of every band ring, in its owner's buffer."""
-        t = self._ring_tables.get(nc)
-        if t is None:
-            ptrs = np.empty(self.nrings, dtype=np.int64)
-            for r, (a, b) in enumerate(self.ring_ranges):
-                ptrs[a:b] = self.peer_ptrs[r] + np.arange(b - a, dtype=np.int64) * (nc * self.MP * 16)
-            t = self._ring_tables[nc] = torch.from_numpy(ptrs).to(self.device)
-        return t
+    def _m_table(self):
+        """Device table of 2*(mmax+1) int64 for the FFT stages: per m the address of element (ring 0, component 0, m) in the
+        buffer of the rank that owns m, and that buffer's row length."""
+        if self._mtab is None:
+            tab = np.empty((self.mmax + 1, 2), dtype=np.int64)
+            for r, ml in enumerate(self.m_lists):
+                tab[ml, 0] = self.peer_ptrs[r] + np.arange(len(ml), dtype=np.int64) * 16
+                tab[ml, 1] = self.row_lens[r]
+            self._mtab = torch.from_numpy(tab.reshape(-1)).to(self.device)
+        return self._mtab
 
     def _stream_ptr(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream) if self.device.type == "cuda" else ctypes.c_void_p(0)
@@ -210,44 +224,44 @@ class ShardedSHT:
 
     # ---- transforms ------------------------------------------------------------------------------------------
     def alm2map(self, d_alms, d_map_slabs):
-        """d_alms: ncomp full-length complex128 alm tensors on the device (only this rank's m columns are read);
-        d_map_slabs: ncomp float64 tensors with this rank's rows (map_rows()) of the column-major map, nx fastest."""
+        """d_alms: ncomp full-length complex alm tensors on the device (only this rank's m columns are read);
+        d_map_slabs: ncomp real tensors with this rank's rows (map_rows()) of the column-major map, nx fastest."""
         nc = len(d_alms)
         L = self.lib.lib
         st = self._stream_ptr()
-        table = self._ring_table(nc)
+        mtab = self._m_table()
         if self.dtype != torch.float64:
             d_alms = [a.to(torch.complex128) for a in d_alms]
-        self._barrier()          # every rank is done with the previous contents of the phase buffers
+        self._barrier()          # every rank is done reading the previous contents of my phase buffer
         ev = [self._ev()]
         self.lib.check(L.pixsht_stage_alm2phase(self.handle, nc, self._ptrs(d_alms), self.nm, ctypes.c_void_p(self.d_m_list.data_ptr()),
-                                                ctypes.c_void_p(table.data_ptr()), st))
+                                                ctypes.c_void_p(self.own_ptr), self.row_len, st))
         ev.append(self._ev())
-        self._barrier()          # all m of my rings have arrived
+        self._barrier()          # every rank's m columns are complete
         ev.append(self._ev())
-        self.lib.check(L.pixsht_stage_phase2map(self.handle, nc, ctypes.c_void_p(self.own_ptr), self.r0, self.nloc,
+        self.lib.check(L.pixsht_stage_phase2map(self.handle, nc, ctypes.c_void_p(mtab.data_ptr()), self.r0, self.nloc,
                                                 self._slab_base_ptrs(d_map_slabs), st))
         ev.append(self._ev())
         self._record("alm2map", ev)
 
     def map2alm(self, d_map_slabs, d_alms):
-        """Inverse pipeline.  d_alms: ncomp full-length complex128 tensors; this rank's m columns receive the result,
+        """Inverse pipeline.  d_alms: ncomp full-length complex tensors; this rank's m columns receive the result,
         every other entry is zeroed (so the sum over ranks is the full alm)."""
         nc = len(d_alms)
         L = self.lib.lib
         st = self._stream_ptr()
-        table = self._ring_table(nc)
-        self._barrier()          # nobody is still reading my phase buffer
+        mtab = self._m_table()
+        self._barrier()          # every rank is done with the previous contents of the phase buffers I am about to write
         ev = [self._ev()]
         self.lib.check(L.pixsht_stage_map2phase(self.handle, nc, self._slab_base_ptrs(d_map_slabs), self.r0, self.nloc,
-                                                ctypes.c_void_p(self.own_ptr), st))
+                                                ctypes.c_void_p(mtab.data_ptr()), st))
         ev.append(self._ev())
-        self._barrier()          # every ring's row is complete on its owner
+        self._barrier()          # all rings of my m columns have arrived
         ev.append(self._ev())
         outs = d_alms if self.dtype == torch.float64 else [torch.empty(a.shape, dtype=torch.complex128, device=a.device) for a in d_alms]
         for t in outs:
             t.zero_()   # the analysis kernels accumulate atomically into pre-zeroed columns
-        self.lib.check(L.pixsht_stage_phase2alm(self.handle, nc, ctypes.c_void_p(table.data_ptr()), self.nm,
+        self.lib.check(L.pixsht_stage_phase2alm(self.handle, nc, ctypes.c_void_p(self.own_ptr), self.row_len, self.nm,
                                                 ctypes.c_void_p(self.d_m_list.data_ptr()), self._ptrs(outs), st))
         if outs is not d_alms:
             for a, o in zip(d_alms, outs):

@@ -43,7 +43,7 @@ def _worker(rank, world, port, lmax, res_deg, out_dir):
 
 def test_partitions():
     sys.path.insert(0, os.path.join(ROOT, "pixell.jl_b200"))
-    from pixsht.distributed import partition_m, partition_rings
+    from pixsht.distributed import partition_m, partition_m_weighted, partition_rings
     for mmax in (0, 1, 7, 36, 10800):
         for world in (1, 2, 3, 8):
             lists = partition_m(mmax, world)
@@ -51,6 +51,13 @@ def test_partitions():
             assert np.array_equal(allm, np.arange(mmax + 1))
             cost = [int(np.sum(mmax - l + 1)) for l in lists]
             assert max(cost) - min(cost) <= mmax + 2   # at most one (m, mmax-m) pair of imbalance
+            wl = partition_m_weighted(mmax + 1.0 - np.arange(mmax + 1), world)
+            assert np.array_equal(np.sort(np.concatenate(wl)), np.arange(mmax + 1))
+            if mmax >= 16 * 8 * world:   # enough runs of 16 to balance: within one run of the mean
+                cw = [float(np.sum(mmax + 1.0 - l)) for l in wl]
+                assert max(cw) - min(cw) <= 16 * (mmax + 1)
+            for l in wl:                 # runs of 16 consecutive m stay together
+                assert all(np.array_equal(l[l // 16 == b], np.arange(b * 16, min(mmax + 1, b * 16 + 16))) for b in np.unique(l // 16))
             rr = partition_rings(mmax + 1, world)
             assert rr[0][0] == 0 and rr[-1][1] == mmax + 1 and all(rr[i][1] == rr[i + 1][0] for i in range(world - 1))
 

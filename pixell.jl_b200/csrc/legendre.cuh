@@ -76,14 +76,14 @@ struct SeekParams {
     int* lact; double* st;
 };
 
-// ---- pre-scaling pass: alm -> records (element-wise over the alm index; ~1 ms at lmax = 10800) ----------------------
+// ---- pre-scaling pass: alm -> records (element-wise over the alm index range [first, first+count); ~1 ms at lmax = 10800) ----
 template <int SPIN>
-__global__ void k_prep_synth(long long nalm, int lmax, const double2* __restrict__ ad, const double* __restrict__ gamma,
+__global__ void k_prep_synth(long long first, long long count, int lmax, const double2* __restrict__ ad, const double* __restrict__ gamma,
                              const double2* __restrict__ a0, const double2* __restrict__ a1, double* __restrict__ rec)
 {
-    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long step = (long long)gridDim.x * blockDim.x;
-    for (; k < nalm; k += step) {
+    long long k = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long step = (long long)gridDim.x * blockDim.x, end = first + count;
+    for (; k < end; k += step) {
         const double2 c = ad[k];
         const double g = gamma[k];
         double2* r = reinterpret_cast<double2*>(rec + k * SynthRec<SPIN>::ND);

@@ -510,16 +510,18 @@ static void launch_anal(pixsht_plan* P, int R, const LegParams& L, cudaStream_t 
 }
 
 // per-call pre-scaling of the alm of one spin family into the synthesis records (needs the whole alm of that family)
-static int synth_prep(pixsht_plan* P, int spin, const double2* a0, const double2* a1, cudaStream_t st)
+static int synth_prep(pixsht_plan* P, int spin, const double2* a0, const double2* a1, cudaStream_t st, long long first = 0, long long count = -1)
 {
+    if (count < 0) count = P->nalm - first;
+    if (count <= 0) return PIXSHT_OK;
     const int prep_grid = P->sm_count > 0 ? P->sm_count * 8 : 256;
     int rc = ensure_seek(P, spin, st); if (rc) return rc;
     if (spin == 0) {
         if (P->d_rec0.n < (size_t)P->nalm * 4 && P->d_rec0.alloc((size_t)P->nalm * 4)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
-        PIXSHT_LAUNCH(k_prep_synth<0>, prep_grid, 256, 0, st, P->nalm, P->lmax, P->d_ad0.p, P->d_gamma0.p, a0, a0, P->d_rec0.p);
+        PIXSHT_LAUNCH(k_prep_synth<0>, prep_grid, 256, 0, st, first, count, P->lmax, P->d_ad0.p, P->d_gamma0.p, a0, a0, P->d_rec0.p);
     } else {
         if (P->d_rec2.n < (size_t)P->nalm * 6 && P->d_rec2.alloc((size_t)P->nalm * 6)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
-        PIXSHT_LAUNCH(k_prep_synth<2>, prep_grid, 256, 0, st, P->nalm, P->lmax, P->d_ad2.p, P->d_gamma2.p, a0, a1, P->d_rec2.p);
+        PIXSHT_LAUNCH(k_prep_synth<2>, prep_grid, 256, 0, st, first, count, P->lmax, P->d_ad2.p, P->d_gamma2.p, a0, a1, P->d_rec2.p);
     }
     P->launches++;
     CU(cudaGetLastError());
@@ -688,8 +690,21 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
     CU(cudaEventRecord(P->ev[0], sc));
 
     if (direction == PIXSHT_ALM2MAP) {
-        cudaEvent_t e_in[3];
-        for (int c = 0; c < ncomp; ++c) {
+        // input copies: the spin-0 alm goes first, in m ranges of equal Legendre work, so that its synthesis starts after a
+        // fraction of one component has arrived; the polarisation alm follow and arrive under the spin-0 work
+        const int K0 = has0 ? std::min(P->nsplit, P->mmax + 1) : 0;
+        std::vector<int> mb0(K0 + 1, 0);
+        std::vector<cudaEvent_t> e_t(K0);
+        for (int k = 0; k <= K0; ++k) mb0[k] = (k == K0) ? P->mmax + 1 : (int)std::lround((P->mmax + 1) * (1.0 - std::sqrt(1.0 - (double)k / K0)));
+        for (int k = 1; k <= K0; ++k) mb0[k] = std::max(mb0[k], mb0[k - 1]);
+        auto col0 = [&](int m) { return (m > P->mmax) ? P->nalm : alm_index(P->lmax, m, m); };
+        for (int k = 0; k < K0; ++k) {
+            const long long i0 = col0(mb0[k]), i1 = col0(mb0[k + 1]);
+            if (i1 > i0) CU(cudaMemcpyAsync((char*)dalm[0] + (size_t)i0 * 2 * esz, (const char*)alms[0] + (size_t)i0 * 2 * esz, (size_t)(i1 - i0) * 2 * esz, cudaMemcpyHostToDevice, sh));
+            e_t[k] = next_ev(); CU(cudaEventRecord(e_t[k], sh));
+        }
+        cudaEvent_t e_in[3] = {nullptr, nullptr, nullptr};
+        for (int c = (has0 ? 1 : 0); c < ncomp; ++c) {
             CU(cudaMemcpyAsync(dalm[c], alms[c], alm_bytes, cudaMemcpyHostToDevice, sh));
             e_in[c] = next_ev(); CU(cudaEventRecord(e_in[c], sh));
         }
@@ -710,11 +725,16 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
             return PIXSHT_OK;
         };
         if (has0) {
-            CU(cudaStreamWaitEvent(sc, e_in[0], 0));
-            cvt_in(0);
-            rc = synth_prep(P, 0, dalm64[0], dalm64[0], sc); if (rc) return rc;
-            const LegJob J = {0, ncomp, 0, 0, P->mmax + 1, nullptr, 0, leg_total_chunks(P, P->R0), ph};
-            rc = synth_launch(P, J, sc); if (rc) return rc;
+            { int rc2 = ensure_seek(P, 0, sc); if (rc2) return rc2; }
+            for (int k = 0; k < K0; ++k) {
+                const long long i0 = col0(mb0[k]), i1 = col0(mb0[k + 1]);
+                CU(cudaStreamWaitEvent(sc, e_t[k], 0));
+                if (i1 <= i0) continue;
+                if (f32) { PIXSHT_LAUNCH(k_cvt_f32_to_f64, cvt_grid, 256, 0, sc, (const float*)dalm[0] + 2 * i0, (double*)(dalm64[0] + i0), 2 * (i1 - i0)); P->launches++; }
+                rc = synth_prep(P, 0, dalm64[0], dalm64[0], sc, i0, i1 - i0); if (rc) return rc;
+                const LegJob J = {0, ncomp, 0, mb0[k], mb0[k + 1] - mb0[k], nullptr, 0, leg_total_chunks(P, P->R0), ph};
+                rc = synth_launch(P, J, sc); if (rc) return rc;
+            }
             rc = emit_rings(0, 1, 0, P->nrings); if (rc) return rc;
         }
         if (has2) {
@@ -748,8 +768,31 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
             }
         }
     } else {
-        cudaEvent_t e_in[3];
-        for (int c = 0; c < ncomp; ++c) {
+        // input copies: the spin-0 map goes first, in ring-pair ranges (north rows + mirrored south rows), so that its FFTs
+        // and analysis start after a fraction of one component has arrived; the polarisation maps follow
+        const int Ra = P->R0a, nch0 = leg_total_chunks(P, Ra);
+        int K0 = has0 ? std::min(P->nsplit, nch0) : 0;
+        std::vector<int> cb0(K0 + 1, 0);
+        for (int k = 0; k <= K0; ++k) cb0[k] = (int)((long long)nch0 * k / std::max(K0, 1));
+        std::vector<std::array<int, 4>> rr0(K0);
+        bool ok0 = K0 > 0;
+        for (int k = 0; k < K0 && ok0; ++k) {
+            int rng[2][2];
+            ok0 = pair_range_rings(P, std::min(P->npairs, cb0[k] * 32 * Ra), std::min(P->npairs, cb0[k + 1] * 32 * Ra), rng);
+            rr0[k] = {rng[0][0], rng[0][1], rng[1][0], rng[1][1]};
+        }
+        if (has0 && !ok0) { K0 = 1; cb0 = {0, nch0}; rr0.assign(1, {0, P->nrings, 0, 0}); }
+        std::vector<cudaEvent_t> e_t(K0);
+        for (int k = 0; k < K0; ++k) {
+            for (int h = 0; h < 2; ++h) {
+                if (rr0[k][2 * h + 1] <= rr0[k][2 * h]) continue;
+                size_t off, nb; ring_rows(P, rr0[k][2 * h], rr0[k][2 * h + 1], esz, off, nb);
+                CU(cudaMemcpyAsync((char*)dmap[0] + off, (const char*)maps[0] + off, nb, cudaMemcpyHostToDevice, sh));
+            }
+            e_t[k] = next_ev(); CU(cudaEventRecord(e_t[k], sh));
+        }
+        cudaEvent_t e_in[3] = {nullptr, nullptr, nullptr};
+        for (int c = (has0 ? 1 : 0); c < ncomp; ++c) {
             CU(cudaMemcpyAsync(dmap[c], maps[c], map_bytes, cudaMemcpyHostToDevice, sh));
             e_in[c] = next_ev(); CU(cudaEventRecord(e_in[c], sh));
         }
@@ -771,10 +814,16 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
         };
         for (int c = 0; c < ncomp; ++c) CU(cudaMemsetAsync(dalm64[c], 0, (size_t)P->nalm * sizeof(double2), sc));
         if (has0) {
-            CU(cudaStreamWaitEvent(sc, e_in[0], 0));
-            rc = stage_fft(P, PIXSHT_MAP2ALM, ncomp, 0, 1, P->d_phase.p, 0, P->nrings, dmap, sc); if (rc) return rc;
-            const LegJob J = {0, ncomp, 0, 0, P->mmax + 1, nullptr, 0, leg_total_chunks(P, P->R0a), ph};
-            rc = anal_launch(P, J, dalm64[0], nullptr, sc); if (rc) return rc;
+            for (int k = 0; k < K0; ++k) {
+                CU(cudaStreamWaitEvent(sc, e_t[k], 0));
+                for (int h = 0; h < 2; ++h) {
+                    const int r0 = rr0[k][2 * h], r1 = rr0[k][2 * h + 1];
+                    if (r1 <= r0) continue;
+                    rc = stage_fft(P, PIXSHT_MAP2ALM, ncomp, 0, 1, P->d_phase.p + (long long)r0 * ncomp * P->MP, r0, r1 - r0, dmap, sc); if (rc) return rc;
+                }
+                const LegJob J = {0, ncomp, 0, 0, P->mmax + 1, nullptr, cb0[k], cb0[k + 1] - cb0[k], ph};
+                rc = anal_launch(P, J, dalm64[0], nullptr, sc); if (rc) return rc;
+            }
             rc = emit_alm(0, 1, 0, P->mmax + 1); if (rc) return rc;
         }
         if (has2) {

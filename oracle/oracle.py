@@ -15,12 +15,36 @@ _BUILD = os.path.join(_HERE, "_build")
 
 def build(force=False):
     """(Re)build the oracle shared objects with gcc; no-op when up to date."""
-    src = os.path.join(_HERE, "sht_oracle.c")
-    libs = [os.path.join(_BUILD, "liborc_ld.so"), os.path.join(_BUILD, "liborc_d.so")]
-    fresh = all(os.path.exists(p) and os.path.getmtime(p) >= os.path.getmtime(src) for p in libs)
+    srcs = [os.path.join(_HERE, "sht_oracle.c"), os.path.join(_HERE, "sht_cpu.c")]
+    libs = [os.path.join(_BUILD, "liborc_ld.so"), os.path.join(_BUILD, "liborc_d.so"), os.path.join(_BUILD, "libshtcpu.so")]
+    fresh = all(os.path.exists(p) and os.path.getmtime(p) >= max(os.path.getmtime(s) for s in srcs) for p in libs)
+    # libshtcpu.so is compiled with -march=native: rebuild it when the snapshot travelled to a machine with another CPU
+    tag, tag_file = _cpu_tag(), os.path.join(_BUILD, "libshtcpu.host")
+    try:
+        same_host = open(tag_file).read() == tag
+    except OSError:
+        same_host = False
+    if not same_host and os.path.exists(libs[2]):
+        os.remove(libs[2])
+        fresh = False
     if force or not fresh:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    if not same_host:
+        with open(tag_file, "w") as f:
+            f.write(tag)
     return libs
+
+
+def _cpu_tag():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    import hashlib
+                    return hashlib.sha1(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
 
 
 def alm_index(lmax, l, m):
@@ -112,6 +136,74 @@ class Oracle:
         if rc != 0:
             raise ValueError("orc_alm2map: bad arguments")
         return np.stack(maps)
+
+
+class CpuSht:
+    """ctypes front-end of oracle/sht_cpu.c: the libsharp2-style CPU implementation (double, OpenMP, SIMD over rings) that
+    bench.py times as the CPU baseline.  Same conventions as Oracle; sampling is by m in both directions."""
+
+    def __init__(self):
+        build()
+        self.lib = ctypes.CDLL(os.path.join(_BUILD, "libshtcpu.so"))
+        L = self.lib
+        dp = ctypes.POINTER(ctypes.c_double)
+        pp = ctypes.POINTER(ctypes.c_void_p)
+        L.cpu_alm2map.argtypes = [ctypes.c_int, ctypes.c_int, dp, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                  pp, pp, ctypes.c_int, ctypes.c_int, dp]
+        L.cpu_map2alm.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                  pp, pp, ctypes.c_int, ctypes.c_int, dp]
+        L.cpu_num_threads.restype = ctypes.c_int
+        self.last_times = (0.0, 0.0)
+
+    @property
+    def threads(self):
+        return int(self.lib.cpu_num_threads())
+
+    def alm2map(self, alms, theta, phi0, nphi, lmax, mmax=None, spin=0, m_stride=1, m_offset=0):
+        mmax = lmax if mmax is None else mmax
+        alms = np.ascontiguousarray(alms, dtype=np.complex128)
+        if alms.ndim == 1:
+            alms = alms[None]
+        nc = alms.shape[0]
+        assert nc == (1 if spin == 0 else 2) and alms.shape[1] == nalm(lmax, mmax)
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        maps = [np.zeros((theta.shape[0], nphi), dtype=np.float64) for _ in range(nc)]
+        al = [alms[c] for c in range(nc)]
+        t = (ctypes.c_double * 2)()
+        rc = self.lib.cpu_alm2map(spin, theta.shape[0], Oracle._dp(theta), float(phi0), nphi, lmax, mmax, Oracle._ptrs(al),
+                                  Oracle._ptrs(maps), m_stride, m_offset, t)
+        if rc != 0:
+            raise ValueError("cpu_alm2map: bad arguments")
+        self.last_times = (t[0], t[1])
+        return np.stack(maps)
+
+    def map2alm(self, maps, theta, wgt, phi0, lmax, mmax=None, spin=0, m_stride=1, m_offset=0):
+        mmax = lmax if mmax is None else mmax
+        maps = np.ascontiguousarray(maps, dtype=np.float64)
+        if maps.ndim == 2:
+            maps = maps[None]
+        nc, nr, nphi = maps.shape
+        assert nc == (1 if spin == 0 else 2)
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        wgt = np.ascontiguousarray(wgt, dtype=np.float64)
+        alms = [np.zeros(nalm(lmax, mmax), dtype=np.complex128) for _ in range(nc)]
+        mp = [maps[c] for c in range(nc)]
+        t = (ctypes.c_double * 2)()
+        rc = self.lib.cpu_map2alm(spin, nr, Oracle._dp(theta), Oracle._dp(wgt), float(phi0), nphi, lmax, mmax, Oracle._ptrs(mp),
+                                  Oracle._ptrs(alms), m_stride, m_offset, t)
+        if rc != 0:
+            raise ValueError("cpu_map2alm: bad arguments")
+        self.last_times = (t[0], t[1])
+        return np.stack(alms)
+
+
+_CPU = []
+
+
+def get_cpu_sht():
+    if not _CPU:
+        _CPU.append(CpuSht())
+    return _CPU[0]
 
 
 _ORACLES = {}

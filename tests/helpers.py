@@ -59,9 +59,13 @@ def band_to_map(band, b):
 
 
 def oracle_map2alm(m, lmax, mmax=None, spin=0, kind="ld", **kw):
-    """Oracle analysis of an Enmap (2-D, or 3-D with the right ncomp for `spin`)."""
+    """Oracle analysis of an Enmap (2-D, or 3-D with the right ncomp for `spin`).  kind: "ld" / "d" = the naive checker in
+    long double / double; "cpu" = the libsharp2-style CPU implementation (oracle/sht_cpu.c)."""
     band, b = band_copy(m)
     theta, w = cc_geometry(b.nrings_total, b.nphi, b.ring_first, b.nrings)
+    if kind == "cpu":
+        from oracle import get_cpu_sht
+        return get_cpu_sht().map2alm(band, theta, w, b.phi0, lmax, mmax, spin=spin, **kw)
     return get_oracle(kind).map2alm(band, theta, w, b.phi0, lmax, mmax, spin=spin, **kw)
 
 

@@ -1,5 +1,6 @@
-"""Pins the CPU oracle against every SHT golden vector the reference ships:
-test/test_transforms.jl:11-77 with test/data/simple_*.txt.  CPU only."""
+"""Pins the CPU oracle -- the naive checker in both precisions and the libsharp2-style CPU implementation that bench.py times
+-- against every SHT golden vector the reference ships: test/test_transforms.jl:11-77 with
+test/data/simple_*.txt.  CPU only."""
 import numpy as np
 import pytest
 
@@ -14,7 +15,7 @@ def relmax(a, b):
     return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
 
 
-@pytest.mark.parametrize("kind", ["ld", "d"])
+@pytest.mark.parametrize("kind", ["ld", "d", "cpu"])
 def test_spin0_fullsky_lmax18(kind):
     shape, wcs = fullsky_geometry(10.0 * degree)
     assert shape == (36, 19)
@@ -30,7 +31,7 @@ def test_spin0_default_lmax_count():
     assert pixsht.getlmax(wcs) == 18  # -> 190 coefficients (test/test_transforms.jl:21)
 
 
-@pytest.mark.parametrize("kind", ["ld", "d"])
+@pytest.mark.parametrize("kind", ["ld", "d", "cpu"])
 def test_spin0_sliced(kind):
     shape, wcs = fullsky_geometry(10.0 * degree)
     m = Enmap(gen_spin0(shape), wcs)
@@ -40,23 +41,25 @@ def test_spin0_sliced(kind):
     assert relmax(alm, golden_alm("simple_analytic_sht_sliced")) < TOL
 
 
-def test_spin0_box_lmax100():
+@pytest.mark.parametrize("kind", ["ld", "cpu"])
+def test_spin0_box_lmax100(kind):
     box = [[10 * degree, -10 * degree], [-5 * degree, 5 * degree]]
     shape, wcs = geometry(CarClenshawCurtis, box, 1.0 * degree)
     assert shape == (20, 10)
     m = Enmap(gen_spin0(shape, 2.5), wcs)
-    alm = oracle_map2alm(m, 100)[0]
+    alm = oracle_map2alm(m, 100, kind=kind)[0]
     assert relmax(alm, golden_alm("simple_box_analytic_sht")) < TOL
 
 
-def test_spin0_aliased_lmax108():
+@pytest.mark.parametrize("kind", ["ld", "cpu"])
+def test_spin0_aliased_lmax108(kind):
     shape, wcs = fullsky_geometry(10.0 * degree)
     m = Enmap(gen_spin0(shape), wcs)
-    alm = oracle_map2alm(m, 108)[0]
+    alm = oracle_map2alm(m, 108, kind=kind)[0]
     assert relmax(alm, golden_alm("simple_analytic_sht_fullalm")) < TOL
 
 
-@pytest.mark.parametrize("kind", ["ld", "d"])
+@pytest.mark.parametrize("kind", ["ld", "d", "cpu"])
 def test_spin2_lmax108(kind):
     shape, wcs = fullsky_geometry(10.0 * degree, dims=(2,))
     m = Enmap(gen_spin2(shape), wcs)

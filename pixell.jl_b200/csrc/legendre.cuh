@@ -462,22 +462,17 @@ __device__ __forceinline__ void anal_step(RingState<SPIN, R>& S, const double (&
                 part[1] = fma(p0, X[2 * PAR + 1][j], part[1]);
             } else {
                 // a+ += p+ Y+_N + sgn p- Y+_S ;  a- += p- Y-_N + sgn p+ Y-_S   (Y_S pre-multiplied by the base sign)
+                // the four products of one function are adjacent so that its value is fetched once (operand reuse cache)
                 constexpr int NXX = (SPIN == 0 ? 4 : 8), NPP = (SPIN == 0 ? 2 : 4);
+                const double q0 = (PAR == 0) ? p0 : -p0, q1 = (PAR == 0) ? p1 : -p1;
                 part[0] = fma(p0, X[0][j], part[0]);
                 part[1] = fma(p0, X[1][j], part[1]);
+                part[NPP - 2] = fma(q0, X[NXX - 2][j], part[NPP - 2]);
+                part[NPP - 1] = fma(q0, X[NXX - 1][j], part[NPP - 1]);
                 part[NPP - 2] = fma(p1, X[NXX - 4][j], part[NPP - 2]);
                 part[NPP - 1] = fma(p1, X[NXX - 3][j], part[NPP - 1]);
-                if (PAR == 0) {
-                    part[0] = fma(p1, X[2][j], part[0]);
-                    part[1] = fma(p1, X[3][j], part[1]);
-                    part[NPP - 2] = fma(p0, X[NXX - 2][j], part[NPP - 2]);
-                    part[NPP - 1] = fma(p0, X[NXX - 1][j], part[NPP - 1]);
-                } else {
-                    part[0] = fma(-p1, X[2][j], part[0]);
-                    part[1] = fma(-p1, X[3][j], part[1]);
-                    part[NPP - 2] = fma(-p0, X[NXX - 2][j], part[NPP - 2]);
-                    part[NPP - 1] = fma(-p0, X[NXX - 1][j], part[NPP - 1]);
-                }
+                part[0] = fma(q1, X[2][j], part[0]);
+                part[1] = fma(q1, X[3][j], part[1]);
             }
             rec_step<SPIN, R, PAR>(S, j, c.x, c.y);
         }

@@ -1,4 +1,3 @@
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-ncu --set full --clock-control none --import-source on -k regex:"fft_" --launch-skip 2 --launch-count 2 -f -o gpurun_out/prof_fft_c4 python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_fft.log 2>&1
-ncu -i gpurun_out/prof_fft_c4.ncu-rep --page raw --csv > gpurun_out/prof_fft_c4_raw.csv
-ncu -i gpurun_out/prof_fft_c4.ncu-rep --page source --csv --kernel-name regex:fft_phase2map > gpurun_out/prof_fft_c4_src.csv
+python -m pytest tests -m gpu -x -q -k "iqu_f64 or golden_spin2" 2>&1 | tail -2
+python tools/loop_eff.py 3000 12 1.0 | grep "anal spin2"
+python bench.py --workload C4 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['stages'], [ (k['kernel'], round(k['ms'],1)) for k in d['roofline']['kernels']])"

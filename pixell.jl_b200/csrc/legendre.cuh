@@ -336,21 +336,15 @@ __device__ __forceinline__ void synth_step(RingState<SPIN, R>& S, double (&acc)[
             } else {
                 // north: S+ += p+ G+, S- += p- G-;  south: T+ += sgn p- G+, T- += sgn p+ G-  (sgn alternates with l)
                 constexpr int A4 = (SPIN == 0 ? 0 : 4);   // keeps indices in range in the (dead) SPIN == 0 instantiation
+                const double q0 = (PAR == 0) ? p0 : -p0, q1 = (PAR == 0) ? p1 : -p1;
                 acc[0][j] = fma(p0, g0.x, acc[0][j]);
                 acc[1][j] = fma(p0, g0.y, acc[1][j]);
+                acc[A4 + 2][j] = fma(q0, g1.x, acc[A4 + 2][j]);
+                acc[A4 + 3][j] = fma(q0, g1.y, acc[A4 + 3][j]);
                 acc[2][j] = fma(p1, g1.x, acc[2][j]);
                 acc[3][j] = fma(p1, g1.y, acc[3][j]);
-                if (PAR == 0) {
-                    acc[A4 + 0][j] = fma(p1, g0.x, acc[A4 + 0][j]);
-                    acc[A4 + 1][j] = fma(p1, g0.y, acc[A4 + 1][j]);
-                    acc[A4 + 2][j] = fma(p0, g1.x, acc[A4 + 2][j]);
-                    acc[A4 + 3][j] = fma(p0, g1.y, acc[A4 + 3][j]);
-                } else {
-                    acc[A4 + 0][j] = fma(-p1, g0.x, acc[A4 + 0][j]);
-                    acc[A4 + 1][j] = fma(-p1, g0.y, acc[A4 + 1][j]);
-                    acc[A4 + 2][j] = fma(-p0, g1.x, acc[A4 + 2][j]);
-                    acc[A4 + 3][j] = fma(-p0, g1.y, acc[A4 + 3][j]);
-                }
+                acc[A4 + 0][j] = fma(q1, g0.x, acc[A4 + 0][j]);
+                acc[A4 + 1][j] = fma(q1, g0.y, acc[A4 + 1][j]);
             }
             rec_step<SPIN, R, PAR>(S, j, c.x, c.y);
         }

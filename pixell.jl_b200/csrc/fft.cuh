@@ -87,6 +87,30 @@ __device__ __forceinline__ cpx<T> twid(const TwTab<T>& W, int t)
     return r;
 }
 
+// Per-pass twiddle table W_{qL}^{kk}, kk < L, as a product of two conflict-free lookups: lo[kk & 127] * hi[kk >> 7]
+// (consecutive threads have consecutive kk).  Built one pass ahead from the global table, double buffered, so that the
+// barrier that ends a pass also publishes the next pass's table.
+constexpr int FFT_PT = 256;   // 128 lo + up to 128 hi entries
+template <class T>
+__device__ __forceinline__ void pass_table_build(const FftParams& P, cpx<T>* tab, int L, int tstep)
+{
+    const int nlo = L < 128 ? L : 128, nhi = (L + 127) >> 7;
+    for (int i = threadIdx.x; i < nlo + nhi; i += blockDim.x) {
+        const int t = (i < nlo) ? i * tstep : (i - nlo) * 128 * tstep;
+        const double2 w = P.tw[t];
+        cpx<T> v; v.x = (T)w.x; v.y = (T)w.y;
+        tab[(i < nlo) ? i : 128 + (i - nlo)] = v;
+    }
+}
+template <class T, int SIGN>
+__device__ __forceinline__ cpx<T> twp(const cpx<T>* tab, int kk, bool two_level)
+{
+    cpx<T> r = tab[kk & 127];
+    if (two_level) r = cmul(tab[128 + (kk >> 7)], r);
+    if (SIGN > 0) r.y = -r.y;
+    return r;
+}
+
 // host side: position of natural index i in the permuted buffer (mixed-radix digit reversal for the DIT pass order fac[])
 inline int fft_digit_reverse(const int* fac, int nfac, int n, int i)
 {
@@ -134,18 +158,18 @@ __device__ __forceinline__ void dft5(cpx<T>* a)
     a[2] = cadd(r2, i2); a[3] = csub(r2, i2);
 }
 
-// one butterfly of a radix-Q pass at element pointer e (stride L), twiddle exponent base tk = kk * tstep.
+// one butterfly of a radix-Q pass at element pointer e (stride L); tk = kk, the index into the pass's twiddle table.
 // DIF == false: decimation in time (twiddle, then DFT);  DIF == true: the transpose (DFT, then twiddle).
 template <class T, int SIGN, int Q, bool DIF>
-__device__ __forceinline__ void butterfly(const TwTab<T>& W, cpx<T>* e, int L, int tk)
+__device__ __forceinline__ void butterfly(const cpx<T>* ptab, cpx<T>* e, int L, int tk)
 {
     cpx<T> a[Q];
 #pragma unroll
     for (int j = 0; j < Q; ++j) a[j] = e[(size_t)j * L];
     cpx<T> w[5];
     if (tk) {
-        w[1] = twid<T, SIGN>(W, tk);
-        if constexpr (Q > 2) w[2] = twid<T, SIGN>(W, 2 * tk);
+        w[1] = twp<T, SIGN>(ptab, tk, L > 128);
+        if constexpr (Q > 2) w[2] = cmul(w[1], w[1]);   // squaring instead of a second table lookup (shared-memory pipe is the busier one)
         if constexpr (Q > 3) w[3] = cmul(w[1], w[2]);
         if constexpr (Q > 4) w[4] = cmul(w[2], w[2]);
     }
@@ -186,35 +210,42 @@ __device__ void butterfly_generic(const FftParams& P, const TwTab<T>& W, cpx<T>*
 
 // all butterflies of one radix-Q pass (Q a template parameter so that the loop body is straight-line code)
 template <class T, int SIGN, int Q, bool DIF>
-__device__ __forceinline__ void pass_loop(const TwTab<T>& W, cpx<T>* buf, int L, int nb, int tstep, unsigned magic)
+__device__ __forceinline__ void pass_loop(const cpx<T>* ptab, cpx<T>* buf, int L, int nb, unsigned magic)
 {
     for (int b = threadIdx.x; b < nb; b += blockDim.x) {
         const int g = (L == 1) ? b : (int)__umulhi((unsigned)b, magic);
         const int kk = b - g * L;
-        butterfly<T, SIGN, Q, DIF>(W, buf + (size_t)g * Q * L + kk, L, kk * tstep);
+        butterfly<T, SIGN, Q, DIF>(ptab, buf + (size_t)g * Q * L + kk, L, kk);
     }
 }
 
 // in-place mixed-radix passes over buf[0..n).  DIF == false: digit-reversed input -> natural output (pass order 0..nfac-1);
 // DIF == true: natural input -> digit-reversed output (pass order nfac-1..0).  SIGN = -1 forward.
 template <class T, int SIGN, bool DIF>
-__device__ void fft_passes(const FftParams& P, const TwTab<T>& W, cpx<T>* buf)
+__device__ void fft_passes(const FftParams& P, const TwTab<T>& W, cpx<T>* buf, cpx<T>* ptabs)
 {
+    // ptabs: two per-pass twiddle tables; the table of the FIRST pass was built by the caller before its last barrier
     const int n = P.n;
-    int L = 1;
-    if (DIF) L = n;
+    int L = DIF ? n : 1;
     for (int tt = 0; tt < P.nfac; ++tt) {
         const int t = DIF ? (P.nfac - 1 - tt) : tt;
         const int q = P.fac[t];
         if (DIF) L /= q;
         const int nb = n / q;
-        const int tstep = P.nphi / (q * L);   // W_{qL}^{a} = tw[a * tstep]
         const unsigned magic = P.magic[t];
-        if (q == 4) pass_loop<T, SIGN, 4, DIF>(W, buf, L, nb, tstep, magic);
-        else if (q == 3) pass_loop<T, SIGN, 3, DIF>(W, buf, L, nb, tstep, magic);
-        else if (q == 5) pass_loop<T, SIGN, 5, DIF>(W, buf, L, nb, tstep, magic);
-        else if (q == 2) pass_loop<T, SIGN, 2, DIF>(W, buf, L, nb, tstep, magic);
+        const cpx<T>* cur = ptabs + (tt & 1) * FFT_PT;
+        if (tt + 1 < P.nfac) {   // next pass's table (read only after the barrier below)
+            const int t2 = DIF ? (t - 1) : (t + 1);
+            const int q2 = P.fac[t2];
+            const int L2 = DIF ? (L / q2) : (L * q);
+            pass_table_build<T>(P, ptabs + ((tt + 1) & 1) * FFT_PT, L2, P.nphi / (q2 * L2));
+        }
+        if (q == 4) pass_loop<T, SIGN, 4, DIF>(cur, buf, L, nb, magic);
+        else if (q == 3) pass_loop<T, SIGN, 3, DIF>(cur, buf, L, nb, magic);
+        else if (q == 5) pass_loop<T, SIGN, 5, DIF>(cur, buf, L, nb, magic);
+        else if (q == 2) pass_loop<T, SIGN, 2, DIF>(cur, buf, L, nb, magic);
         else {
+            const int tstep = P.nphi / (q * L);   // W_{qL}^{a} = tw[a * tstep]
             for (int b = threadIdx.x; b < nb; b += blockDim.x) {
                 const int g = (L == 1) ? b : (int)__umulhi((unsigned)b, magic);
                 const int kk = b - g * L;
@@ -224,6 +255,16 @@ __device__ void fft_passes(const FftParams& P, const TwTab<T>& W, cpx<T>* buf)
         if (!DIF) L *= q;
         __syncthreads();
     }
+}
+
+// geometry of the first pass in execution order (for the caller's table build)
+template <bool DIF>
+__device__ __forceinline__ void first_pass_geom(const FftParams& P, int& L, int& tstep)
+{
+    const int t = DIF ? (P.nfac - 1) : 0;
+    const int q = P.fac[t];
+    L = DIF ? (P.n / q) : 1;
+    tstep = P.nphi / (q * L);
 }
 
 // phase element (band ring, component c, m): in this launch's local rows, or -- m-sharded -- in the buffer of m's owner
@@ -291,6 +332,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
     PIXSHT_DYN_SMEM(smem_raw);
     cpx<T>* buf = reinterpret_cast<cpx<T>*>(smem_raw);   // n + 1 entries, then the twiddle tables
     const TwTab<T> W = tw_setup<T>(P, buf + P.n + 1);
+    cpx<T>* ptabs = buf + P.n + 1 + fft_tw_entries(P.nphi);   // 2 x FFT_PT per-pass tables
     const int rl = blockIdx.x, c = P.c_begin + blockIdx.y, ring = P.ring_begin + rl;
     const int n = P.n;
     double2* row = P.phase + ((long long)rl * P.ncomp + c) * P.MP;
@@ -339,8 +381,9 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
             buf[k] = cadd(ea, cmuli<T, +1>(oa));
         }
     }
+    { int L1, ts1; first_pass_geom<true>(P, L1, ts1); pass_table_build<T>(P, ptabs, L1, ts1); }
     __syncthreads();
-    fft_passes<T, +1, true>(P, W, buf);
+    fft_passes<T, +1, true>(P, W, buf, ptabs);
 
     // store x[2j] = Re z[j], x[2j+1] = Im z[j] into the caller's array (flips / partial rings by index arithmetic)
     T* out = reinterpret_cast<T*>(P.maps[c]);
@@ -366,6 +409,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams 
     PIXSHT_DYN_SMEM(smem_raw);
     cpx<T>* buf = reinterpret_cast<cpx<T>*>(smem_raw);   // n + 1 entries, then the twiddle tables
     const TwTab<T> W = tw_setup<T>(P, buf + P.n + 1);
+    cpx<T>* ptabs = buf + P.n + 1 + fft_tw_entries(P.nphi);   // 2 x FFT_PT per-pass tables
     const int rl = blockIdx.x, c = P.c_begin + blockIdx.y, ring = P.ring_begin + rl;
     const int n = P.n, N = P.nphi;
     const T* in = reinterpret_cast<const T*>(P.maps[c]);
@@ -383,8 +427,9 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams 
 #pragma unroll
         for (int u = 0; u < FFT_IO_UNROLL; ++u) if ((int)(j0 + u * blockDim.x) < n) buf[pj[u]] = z[u];
     }
+    { int L1, ts1; first_pass_geom<false>(P, L1, ts1); pass_table_build<T>(P, ptabs, L1, ts1); }
     __syncthreads();
-    fft_passes<T, -1, false>(P, W, buf);
+    fft_passes<T, -1, false>(P, W, buf, ptabs);
 
     // post-processing in place: F[k] = ((Z[k] + conj Z[n-k]) - i e^{-2 pi i k/N} (Z[k] - conj Z[n-k])) / 2,  k = 0..n
     for (int k = threadIdx.x; k <= n / 2; k += blockDim.x) {

@@ -273,7 +273,7 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     P->nfft = P->nphi / 2;
     if (factorize(P->nfft, P->fac, P->nfac)) return fail(PIXSHT_ERR_UNSUPPORTED, "nphi/2 has a prime factor > 64");
     const size_t elem = (P->dtype == PIXSHT_F64) ? 16 : 8;
-    P->fft_smem = (size_t)(P->nfft + 1 + fft_tw_entries(P->nphi)) * elem;
+    P->fft_smem = (size_t)(P->nfft + 1 + fft_tw_entries(P->nphi) + 2 * FFT_PT) * elem;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, P->device));
     P->sm_count = prop.multiProcessorCount;

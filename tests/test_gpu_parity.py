@@ -376,3 +376,73 @@ def test_multi_gpu_peer_memory_pipeline_matches_single_gpu(tmp_path):
     for c in range(3):
         assert rel_rms(alm_sum[c], back[c]) < 1e-13
     plan.close()
+
+
+# ---- edge cases: degenerate band limits, tiny and ragged bands, argument errors --------------------------------------------
+@pytest.mark.parametrize("lmax,mmax", [(0, 0), (1, 1), (1, 0), (2, 2), (18, 0), (18, 3), (40, 40)])
+def test_edge_band_limits(lmax, mmax):
+    """lmax / mmax at the low end (spin 2 has nothing below l = 2), mmax < lmax, and lmax > nphi/2 (aliasing) on a 36 x 19 grid."""
+    shape, wcs = fullsky_geometry(10.0 * degree)
+    band = pixsht.sht_band(shape, wcs)
+    plan = Plan(band, lmax, mmax)
+    theta, w = cc_geometry(band.nrings_total, band.nphi)
+    orc = get_oracle("ld")
+    for spin, nc in ((0, 1), (2, 2)):
+        alms = [synth_alm(lmax, mmax, 7 + c, spin2=spin == 2) for c in range(nc)]
+        maps = plan.alm2map(alms)
+        ref = oracle_alm2map(np.stack(alms), shape, wcs, lmax, mmax, spin=spin)
+        scale = max(1.0, float(np.max(np.abs(ref))))
+        for c in range(nc):
+            assert np.max(np.abs(maps[c] - ref[:, :, c])) < 1e-12 * scale
+        rng = np.random.default_rng(5)
+        x = [np.asfortranarray(rng.standard_normal(shape)) for _ in range(nc)]
+        got = plan.map2alm(x)
+        xm = Enmap(x[0], wcs) if nc == 1 else Enmap(np.asfortranarray(np.stack(x, axis=2)), wcs)
+        ref_alm = oracle_map2alm(xm, lmax, mmax, spin=spin)
+        for c in range(nc):
+            assert np.max(np.abs(got[c] - ref_alm[c])) < 1e-12 * max(1.0, float(np.max(np.abs(ref_alm[c]))))
+    plan.close()
+
+
+def test_edge_tiny_and_ragged_bands():
+    """One-ring band, a band that contains only southern rings, a band one column wide (everything else of each ring is
+    zero padding), and the two pole rings alone."""
+    shape0, wcs0 = fullsky_geometry(10.0 * degree)
+    full = Enmap(gen_spin0(shape0), wcs0)
+    lmax = 18
+    for sub in (full[:, 9:10], full[:, 0:4], full[17:18, :], full[3:30, 2:3], full[:, 18:19], full[:, 0:1]):
+        got = map2alm(sub, lmax=lmax).alm
+        ref = oracle_map2alm(sub, lmax)[0]
+        assert np.max(np.abs(got - ref)) < 1e-12 * max(1.0, float(np.max(np.abs(ref))))
+        alm = synth_alm(lmax, lmax, 3)
+        back = alm2map(Alm(lmax, lmax, alm), sub.shape, sub.wcs)
+        refm = oracle_alm2map(alm[None], sub.shape, sub.wcs, lmax)[:, :, 0]
+        assert back.data.shape == sub.shape and np.max(np.abs(back.data - refm)) < 1e-12 * max(1.0, float(np.max(np.abs(refm))))
+
+
+def test_argument_errors_are_reported_not_fatal():
+    lib = get_lib()
+    L = lib.lib
+    h = ctypes.c_void_p()
+    g = _lib.Geom(36, 19, 0, 19, 36, 1, 1, 0, 0.0)
+    assert L.pixsht_plan_create(ctypes.byref(h), ctypes.byref(g), 10, 11, _lib.F64, 0) == _lib.ERR_ARG          # mmax > lmax
+    assert b"mmax" in L.pixsht_last_error()
+    assert L.pixsht_plan_create(ctypes.byref(h), ctypes.byref(g), 10, 10, 7, 0) == _lib.ERR_ARG                 # dtype
+    bad = _lib.Geom(35, 19, 0, 19, 35, 1, 1, 0, 0.0)
+    assert L.pixsht_plan_create(ctypes.byref(h), ctypes.byref(bad), 10, 10, _lib.F64, 0) == _lib.ERR_UNSUPPORTED  # odd ring length
+    assert b"odd" in L.pixsht_last_error()
+    bad = _lib.Geom(36, 19, 5, 19, 36, 1, 1, 0, 0.0)
+    assert L.pixsht_plan_create(ctypes.byref(h), ctypes.byref(bad), 10, 10, _lib.F64, 0) == _lib.ERR_ARG         # band sticks out of the sphere
+    bad = _lib.Geom(36, 19, 0, 19, 40, 1, 1, 0, 0.0)
+    assert L.pixsht_plan_create(ctypes.byref(h), ctypes.byref(bad), 10, 10, _lib.F64, 0) == _lib.ERR_ARG         # map wider than a ring
+    assert L.pixsht_plan_create(ctypes.byref(h), ctypes.byref(g), 10, 10, _lib.F64, 99) == _lib.ERR_ARG          # device index
+    assert L.pixsht_execute(None, 0, 1, None, None, 0) == _lib.ERR_ARG
+    p = Plan(pixsht.sht_band((36, 19), fullsky_geometry(10.0 * degree)[1]), 10)
+    one = (ctypes.c_void_p * 1)(0)
+    assert L.pixsht_execute(p.handle, 0, 1, one, one, 0) == _lib.ERR_ARG                                            # null component pointer
+    assert L.pixsht_execute(p.handle, 5, 1, one, one, 0) == _lib.ERR_ARG                                            # direction
+    with pytest.raises(ValueError):
+        p.alm2map([np.zeros(3, dtype=np.complex128)])                                                              # wrong alm length
+    with pytest.raises(ValueError):
+        p.map2alm([np.zeros((5, 5))])                                                                              # wrong map shape
+    p.close()

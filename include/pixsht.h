@@ -108,6 +108,12 @@ int pixsht_shared_open(int device, const unsigned char handle[64], void **dptr);
 int pixsht_shared_close(void *dptr);
 int pixsht_shared_free(void *dptr);
 
+/* ---- alm2cl ---------------------------------------------------------------------------------------------- */
+/* Healpix.alm2cl as the reference's tests use it (test/test_transforms.jl:104-107): cross (or auto, alm2 = NULL) spectrum
+ * C_l = (a_l0 b_l0* + 2 sum_{m>=1} Re(a_lm b_lm*)) / (2l+1), l = 0..lmax, of two alm in the triangular m-major layout.
+ * dtype: element type of the alm (complex double / complex float); cl: lmax+1 doubles; location as in pixsht_execute. */
+int pixsht_alm2cl(int lmax, int mmax, const void *alm1, const void *alm2, double *cl, int dtype, int location, int device);
+
 /* ---- introspection -------------------------------------------------------------------------------------- */
 int64_t pixsht_nalm(int lmax, int mmax);
 int pixsht_plan_info(const pixsht_plan *plan, int32_t info[16]);

@@ -1165,6 +1165,52 @@ extern "C" int pixsht_plan_work(pixsht_plan* P, int spin, double out[2])
     return PIXSHT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// alm2cl: the first consumer of the alm (Healpix.alm2cl as used at test/test_transforms.jl:104-107 of the reference)
+// ---------------------------------------------------------------------------------------------------------------
+// C_l = (a_l0 b_l0* + 2 sum_{m=1..min(l,mmax)} Re(a_lm b_lm*)) / (2l+1); one thread per l, coalesced in l for every m
+template <class C>
+__global__ void k_alm2cl(int lmax, int mmax, const C* __restrict__ a, const C* __restrict__ b, double* __restrict__ cl)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > lmax) return;
+    double acc = 0.0;
+    const int mtop = l < mmax ? l : mmax;
+    for (int m = 0; m <= mtop; ++m) {
+        const long long k = alm_index(lmax, l, m);
+        const C x = a[k], y = b[k];
+        const double t = (double)x.x * (double)y.x + (double)x.y * (double)y.y;
+        acc += (m == 0) ? t : 2.0 * t;
+    }
+    cl[l] = acc / (2.0 * l + 1.0);
+}
+
+extern "C" int pixsht_alm2cl(int lmax, int mmax, const void* alm1, const void* alm2, double* cl, int dtype, int location, int device)
+{
+    if (!alm1 || !cl || lmax < 0 || mmax < 0 || mmax > lmax) return fail(PIXSHT_ERR_ARG, "bad argument");
+    if (dtype != PIXSHT_F64 && dtype != PIXSHT_F32) return fail(PIXSHT_ERR_ARG, "dtype must be PIXSHT_F64 or PIXSHT_F32");
+    if (location != PIXSHT_HOST && location != PIXSHT_DEVICE) return fail(PIXSHT_ERR_ARG, "bad location");
+    if (!alm2) alm2 = alm1;
+    int rc = check_device(device); if (rc) return rc;
+    const size_t n = (size_t)pixsht_nalm(lmax, mmax), bytes = n * (dtype == PIXSHT_F64 ? 16 : 8);
+    DevBuf<unsigned char> da, db; DevBuf<double> dcl;
+    const void *pa = alm1, *pb = alm2; double* pc = cl;
+    if (location == PIXSHT_HOST) {
+        if (da.alloc(bytes) || dcl.alloc(lmax + 1) || (alm2 != alm1 && db.alloc(bytes))) { da.release(); db.release(); dcl.release(); return fail(PIXSHT_ERR_NOMEM, "allocation failed"); }
+        CU(cudaMemcpy(da.p, alm1, bytes, cudaMemcpyHostToDevice));
+        if (alm2 != alm1) CU(cudaMemcpy(db.p, alm2, bytes, cudaMemcpyHostToDevice));
+        pa = da.p; pb = (alm2 != alm1) ? (const void*)db.p : (const void*)da.p; pc = dcl.p;
+    }
+    const int grid = (lmax + 128) / 128;
+    if (dtype == PIXSHT_F64) PIXSHT_LAUNCH(k_alm2cl<double2>, grid, 128, 0, 0, lmax, mmax, (const double2*)pa, (const double2*)pb, pc);
+    else PIXSHT_LAUNCH(k_alm2cl<float2>, grid, 128, 0, 0, lmax, mmax, (const float2*)pa, (const float2*)pb, pc);
+    CU(cudaGetLastError());
+    if (location == PIXSHT_HOST) CU(cudaMemcpy(cl, dcl.p, sizeof(double) * (lmax + 1), cudaMemcpyDeviceToHost));
+    else CU(cudaStreamSynchronize(0));
+    da.release(); db.release(); dcl.release();
+    return PIXSHT_OK;
+}
+
 extern "C" int pixsht_plan_weights(const pixsht_plan* P, double* weights, double* theta)
 {
     if (!P) return fail(PIXSHT_ERR_ARG, "null argument");

@@ -27,7 +27,7 @@ class Geom(ctypes.Structure):
 EXPORTS = ["pixsht_plan_create", "pixsht_plan_create_rings", "pixsht_plan_destroy", "pixsht_execute", "pixsht_get_timings", "pixsht_plan_set_stream",
            "pixsht_stage_alm2phase", "pixsht_stage_phase2alm", "pixsht_stage_phase2map", "pixsht_stage_map2phase",
            "pixsht_phase_row_len", "pixsht_shared_alloc", "pixsht_shared_open", "pixsht_shared_close", "pixsht_shared_free",
-           "pixsht_nalm", "pixsht_plan_info", "pixsht_plan_weights", "pixsht_plan_work", "pixsht_plan_work_per_m", "pixsht_last_error", "pixsht_version",
+           "pixsht_nalm", "pixsht_alm2cl", "pixsht_plan_info", "pixsht_plan_weights", "pixsht_plan_work", "pixsht_plan_work_per_m", "pixsht_last_error", "pixsht_version",
            "pixsht_device_count", "pixsht_measure_fma_peak",
            "sharp_make_geom_info", "sharp_destroy_geom_info", "sharp_map_size", "sharp_make_triangular_alm_info",
            "sharp_destroy_alm_info", "sharp_alm_count", "sharp_execute", "pixsht_shim_status"]
@@ -57,6 +57,7 @@ class PixshtLib:
         L.pixsht_stage_phase2alm.argtypes = [vp, i32, vp, ctypes.c_int64, i32, vp, pvp, vp]
         L.pixsht_stage_phase2map.argtypes = [vp, i32, vp, i32, i32, pvp, vp]
         L.pixsht_stage_map2phase.argtypes = [vp, i32, pvp, i32, i32, vp, vp]
+        L.pixsht_alm2cl.argtypes = [i32, i32, vp, vp, ctypes.POINTER(dbl), i32, i32, i32]
         L.pixsht_plan_work.argtypes = [vp, i32, ctypes.POINTER(dbl)]
         L.pixsht_plan_work_per_m.argtypes = [vp, i32, ctypes.POINTER(dbl)]
         L.pixsht_phase_row_len.argtypes = [vp]

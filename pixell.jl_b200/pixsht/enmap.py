@@ -88,13 +88,21 @@ class Alm:
         return self.alm.shape[0]
 
 
-def alm2cl(a, b=None):
+def alm2cl(a, b=None, lib=None):
     """Healpix.alm2cl mirror (used by the reference's tests, test/test_transforms.jl:104-107):
-    C_l = (a_l0 b_l0* + 2 sum_{m>=1} Re(a_lm b_lm*)) / (2l+1)."""
+    C_l = (a_l0 b_l0* + 2 sum_{m>=1} Re(a_lm b_lm*)) / (2l+1).
+    With `lib` (a PixshtLib) the sum runs on the GPU through pixsht_alm2cl; without, it is host bookkeeping in numpy."""
     b = a if b is None else b
     if (a.lmax, a.mmax) != (b.lmax, b.mmax):
         raise ValueError("alm geometries differ")
     lmax, mmax = a.lmax, a.mmax
+    if lib is not None:
+        import ctypes
+        x = np.ascontiguousarray(a.alm, dtype=np.complex128)
+        y = np.ascontiguousarray(b.alm, dtype=np.complex128)
+        out = np.empty(lmax + 1)
+        lib.check(lib.lib.pixsht_alm2cl(lmax, mmax, x.ctypes.data, y.ctypes.data, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 0, 0, 0))
+        return out
     cl = np.zeros(lmax + 1)
     for m in range(mmax + 1):
         i0 = a.index(m, m)

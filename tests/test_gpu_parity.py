@@ -446,3 +446,14 @@ def test_argument_errors_are_reported_not_fatal():
     with pytest.raises(ValueError):
         p.map2alm([np.zeros((5, 5))])                                                                              # wrong map shape
     p.close()
+
+
+def test_alm2cl_on_device_matches_host_mirror():
+    """pixsht_alm2cl (the first consumer of the alm) against the numpy mirror of Healpix.alm2cl."""
+    lib = get_lib()
+    for lmax, mmax in ((0, 0), (7, 7), (40, 25), (300, 300)):
+        a = Alm(lmax, mmax, synth_alm(lmax, mmax, 1)); b = Alm(lmax, mmax, synth_alm(lmax, mmax, 2))
+        for x, y in ((a, None), (a, b)):
+            ref = pixsht.alm2cl(x, y)
+            got = pixsht.alm2cl(x, y, lib=lib)
+            assert np.max(np.abs(got - ref)) < 1e-13 * max(1.0, float(np.max(np.abs(ref))))

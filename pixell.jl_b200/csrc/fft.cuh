@@ -25,13 +25,15 @@ namespace pixsht {
 
 constexpr int FFT_MAXFAC = 24;
 constexpr int FFT_MAXRADIX = 64;
-constexpr int FFT_MAXTHREADS = 768;
+constexpr int FFT_MAXTHREADS = 640;
 
 struct FftParams {
     int nphi, n;                // ring length, complex FFT length (nphi/2)
     int nfac;
     int fac[FFT_MAXFAC];        // radices in DIT pass order (pass t works on sub-transforms of length L_t = prod_{u<t} fac[u])
     unsigned magic[FFT_MAXFAC]; // floor(2^32 / L_t) + 1: b / L_t == umulhi(b, magic) for b < 2^16
+    int nsp;                    // super-passes: consecutive radix passes done together in registers (fft.cuh butterfly2)
+    unsigned char sp_first[FFT_MAXFAC], sp_count[FFT_MAXFAC];   // first fine pass and number of fine passes (1 or 2), DIT order
     const double2* tw;          // [nphi] exp(-2 pi i t / nphi)
     const double2* phi0tw;      // [mmax+1] exp(+i m phi0)
     const double* wgt;          // [nrings] quadrature weight per band ring
@@ -84,6 +86,22 @@ __device__ __forceinline__ cpx<T> twid(const TwTab<T>& W, int t)
     const cpx<T> a = W.A[t >> FFT_TWLO_BITS], b = W.B[t & (FFT_TWLO - 1)];
     cpx<T> r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x;
     if (SIGN > 0) r.y = -r.y;
+    return r;
+}
+
+// exp(-2 pi i k / S), k < S, for every S <= FFT_CST_MAX: the twiddles between the two radix stages of a fused super-pass.
+// Constant memory: after unrolling every index is a compile-time constant, so they become constant-bank operands.
+constexpr int FFT_CST_MAX = 25;
+#ifndef PIXSHT_EMU
+__constant__ double2 c_fft_cst[(FFT_CST_MAX + 1) * FFT_CST_MAX];
+#else
+static double2 c_fft_cst[(FFT_CST_MAX + 1) * FFT_CST_MAX];
+#endif
+template <class T, int SIGN>
+__device__ __forceinline__ cpx<T> fft_cst(int S, int k)
+{
+    const double2 w = c_fft_cst[S * FFT_CST_MAX + k];
+    cpx<T> r; r.x = (T)w.x; r.y = (T)(SIGN < 0 ? w.y : -w.y);
     return r;
 }
 
@@ -158,6 +176,14 @@ __device__ __forceinline__ void dft5(cpx<T>* a)
     a[2] = cadd(r2, i2); a[3] = csub(r2, i2);
 }
 
+template <class T, int SIGN, int Q>
+__device__ __forceinline__ void dftq(cpx<T>* a)
+{
+    if constexpr (Q == 2) dft2<T, SIGN>(a);
+    else if constexpr (Q == 3) dft3<T, SIGN>(a);
+    else if constexpr (Q == 4) dft4<T, SIGN>(a);
+    else dft5<T, SIGN>(a);
+}
 // one butterfly of a radix-Q pass at element pointer e (stride L); tk = kk, the index into the pass's twiddle table.
 // DIF == false: decimation in time (twiddle, then DFT);  DIF == true: the transpose (DFT, then twiddle).
 template <class T, int SIGN, int Q, bool DIF>
@@ -166,24 +192,23 @@ __device__ __forceinline__ void butterfly(const cpx<T>* ptab, cpx<T>* e, int L, 
     cpx<T> a[Q];
 #pragma unroll
     for (int j = 0; j < Q; ++j) a[j] = e[(size_t)j * L];
-    cpx<T> w[5];
+    cpx<T> w1, w2, w3, w4;
+    w1.x = w2.x = w3.x = w4.x = (T)1; w1.y = w2.y = w3.y = w4.y = (T)0;
     if (tk) {
-        w[1] = twp<T, SIGN>(ptab, tk, L > 128);
-        if constexpr (Q > 2) w[2] = cmul(w[1], w[1]);   // squaring instead of a second table lookup (shared-memory pipe is the busier one)
-        if constexpr (Q > 3) w[3] = cmul(w[1], w[2]);
-        if constexpr (Q > 4) w[4] = cmul(w[2], w[2]);
+        w1 = twp<T, SIGN>(ptab, tk, L > 128);
+        if (Q > 2) w2 = cmul(w1, w1);   // squaring instead of a second table lookup (shared-memory pipe is the busier one)
+        if (Q > 3) w3 = cmul(w1, w2);
+        if (Q > 4) w4 = cmul(w2, w2);
     }
+    auto WW = [&](int j) { return j == 1 ? w1 : (j == 2 ? w2 : (j == 3 ? w3 : w4)); };
     if (!DIF && tk) {
 #pragma unroll
-        for (int j = 1; j < Q; ++j) a[j] = cmul(a[j], w[j]);
+        for (int j = 1; j < Q; ++j) a[j] = cmul(a[j], WW(j));
     }
-    if constexpr (Q == 2) dft2<T, SIGN>(a);
-    else if constexpr (Q == 3) dft3<T, SIGN>(a);
-    else if constexpr (Q == 4) dft4<T, SIGN>(a);
-    else dft5<T, SIGN>(a);
+    dftq<T, SIGN, Q>(a);
     if (DIF && tk) {
 #pragma unroll
-        for (int j = 1; j < Q; ++j) a[j] = cmul(a[j], w[j]);
+        for (int j = 1; j < Q; ++j) a[j] = cmul(a[j], WW(j));
     }
 #pragma unroll
     for (int j = 0; j < Q; ++j) e[(size_t)j * L] = a[j];
@@ -208,6 +233,111 @@ __device__ void butterfly_generic(const FftParams& P, const TwTab<T>& W, cpx<T>*
     }
 }
 
+// Two consecutive radix passes (Q1 at sub-length L, then Q2 at sub-length Q1*L in DIT order) on Q1*Q2 elements held in
+// registers: one shared-memory round trip and one barrier instead of two.  Element (j2, j1) sits at e[(j2*Q1 + j1)*L].
+//   DIT: x *= WA^{j1};  DFT_Q1 over j1;  y(j2,u1) *= WB^{j2} * W_{Q1Q2}^{j2 u1};  DFT_Q2 over j2;   DIF: the transpose.
+// TA / TB: the pass tables for the roots Q1*L and Q1*Q2*L, both indexed by kk.
+// TW == false: the super-pass at sub-length 1 (kk == 0 everywhere), no pass twiddles at all
+template <class T, int SIGN, int Q1, int Q2, bool DIF, bool TW>
+__device__ __forceinline__ void butterfly2(const cpx<T>* TA, const cpx<T>* TB, cpx<T>* e, int L, int kk)
+{
+    constexpr int S = Q1 * Q2;
+    cpx<T> a[Q2][Q1];
+#pragma unroll
+    for (int j2 = 0; j2 < Q2; ++j2)
+#pragma unroll
+        for (int j1 = 0; j1 < Q1; ++j1) a[j2][j1] = e[(size_t)(j2 * Q1 + j1) * L];
+    // pass twiddles W^kk .. W^{4 kk} of the two roots as scalars (arrays that are only conditionally written end up in
+    // local memory); for kk == 0 they are exactly 1
+    cpx<T> wa1, wa2, wa3, wa4, wb1, wb2, wb3, wb4;
+    wa1.x = wa2.x = wa3.x = wa4.x = wb1.x = wb2.x = wb3.x = wb4.x = (T)1;
+    wa1.y = wa2.y = wa3.y = wa4.y = wb1.y = wb2.y = wb3.y = wb4.y = (T)0;
+    if (TW) {
+        wa1 = twp<T, SIGN>(TA, kk, L > 128); wa2 = cmul(wa1, wa1);
+        if (Q1 > 3) { wa3 = cmul(wa1, wa2); } if (Q1 > 4) { wa4 = cmul(wa2, wa2); }
+        wb1 = twp<T, SIGN>(TB, kk, L > 128); wb2 = cmul(wb1, wb1);
+        if (Q2 > 3) { wb3 = cmul(wb1, wb2); } if (Q2 > 4) { wb4 = cmul(wb2, wb2); }
+    }
+    auto WA = [&](int j) { return j == 1 ? wa1 : (j == 2 ? wa2 : (j == 3 ? wa3 : wa4)); };
+    auto WB = [&](int j) { return j == 1 ? wb1 : (j == 2 ? wb2 : (j == 3 ? wb3 : wb4)); };
+    if (!DIF) {
+#pragma unroll
+        for (int j2 = 0; j2 < Q2; ++j2) {
+            if (TW) {
+#pragma unroll
+                for (int j1 = 1; j1 < Q1; ++j1) a[j2][j1] = cmul(a[j2][j1], WA(j1));
+            }
+            dftq<T, SIGN, Q1>(a[j2]);
+        }
+    } else {
+#pragma unroll
+        for (int u1 = 0; u1 < Q1; ++u1) {
+            cpx<T> col[Q2];
+#pragma unroll
+            for (int u2 = 0; u2 < Q2; ++u2) col[u2] = a[u2][u1];
+            dftq<T, SIGN, Q2>(col);
+#pragma unroll
+            for (int j2 = 0; j2 < Q2; ++j2) a[j2][u1] = col[j2];
+        }
+    }
+    // the stage between the two DFTs: diagonal in (j2, u1)
+#pragma unroll
+    for (int j2 = 1; j2 < Q2; ++j2) {
+#pragma unroll
+        for (int u1 = 0; u1 < Q1; ++u1) {
+            if (u1) a[j2][u1] = cmul(a[j2][u1], fft_cst<T, SIGN>(S, (j2 * u1) % S));
+            if (TW) a[j2][u1] = cmul(a[j2][u1], WB(j2));
+        }
+    }
+    if (!DIF) {
+#pragma unroll
+        for (int u1 = 0; u1 < Q1; ++u1) {
+            cpx<T> col[Q2];
+#pragma unroll
+            for (int j2 = 0; j2 < Q2; ++j2) col[j2] = a[j2][u1];
+            dftq<T, SIGN, Q2>(col);
+#pragma unroll
+            for (int u2 = 0; u2 < Q2; ++u2) a[u2][u1] = col[u2];
+        }
+    } else {
+#pragma unroll
+        for (int j2 = 0; j2 < Q2; ++j2) {
+            dftq<T, SIGN, Q1>(a[j2]);
+            if (TW) {
+#pragma unroll
+                for (int j1 = 1; j1 < Q1; ++j1) a[j2][j1] = cmul(a[j2][j1], WA(j1));
+            }
+        }
+    }
+#pragma unroll
+    for (int j2 = 0; j2 < Q2; ++j2)
+#pragma unroll
+        for (int j1 = 0; j1 < Q1; ++j1) e[(size_t)(j2 * Q1 + j1) * L] = a[j2][j1];
+}
+
+template <class T, int SIGN, int Q1, int Q2, bool DIF>
+__device__ __forceinline__ void pass2_loop(const cpx<T>* TA, const cpx<T>* TB, cpx<T>* buf, int L, int nb, unsigned magic)
+{
+    if (L == 1) {
+        for (int b = threadIdx.x; b < nb; b += blockDim.x) butterfly2<T, SIGN, Q1, Q2, DIF, false>(TA, TB, buf + (size_t)b * (Q1 * Q2), 1, 0);
+    } else {
+        for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+            const int g = (int)__umulhi((unsigned)b, magic);
+            const int kk = b - g * L;
+            butterfly2<T, SIGN, Q1, Q2, DIF, true>(TA, TB, buf + (size_t)g * (Q1 * Q2) * L + kk, L, kk);
+        }
+    }
+}
+constexpr int FFT_FUSE_MAX = 16;   // largest fused super-pass (points held in registers per thread)
+template <class T, int SIGN, int Q1, bool DIF>
+__device__ __forceinline__ void pass2_dispatch(int q2, const cpx<T>* TA, const cpx<T>* TB, cpx<T>* buf, int L, int nb, unsigned magic)
+{
+    if constexpr (Q1 * 2 <= FFT_FUSE_MAX) { if (q2 == 2) { pass2_loop<T, SIGN, Q1, 2, DIF>(TA, TB, buf, L, nb, magic); return; } }
+    if constexpr (Q1 * 3 <= FFT_FUSE_MAX) { if (q2 == 3) { pass2_loop<T, SIGN, Q1, 3, DIF>(TA, TB, buf, L, nb, magic); return; } }
+    if constexpr (Q1 * 4 <= FFT_FUSE_MAX) { if (q2 == 4) { pass2_loop<T, SIGN, Q1, 4, DIF>(TA, TB, buf, L, nb, magic); return; } }
+    if constexpr (Q1 * 5 <= FFT_FUSE_MAX) { if (q2 == 5) { pass2_loop<T, SIGN, Q1, 5, DIF>(TA, TB, buf, L, nb, magic); return; } }
+}
+
 // all butterflies of one radix-Q pass (Q a template parameter so that the loop body is straight-line code)
 template <class T, int SIGN, int Q, bool DIF>
 __device__ __forceinline__ void pass_loop(const cpx<T>* ptab, cpx<T>* buf, int L, int nb, unsigned magic)
@@ -219,52 +349,62 @@ __device__ __forceinline__ void pass_loop(const cpx<T>* ptab, cpx<T>* buf, int L
     }
 }
 
-// in-place mixed-radix passes over buf[0..n).  DIF == false: digit-reversed input -> natural output (pass order 0..nfac-1);
-// DIF == true: natural input -> digit-reversed output (pass order nfac-1..0).  SIGN = -1 forward.
+// tables of one super-pass: slot 0 = root q1*L, slot 1 = root q1*q2*L (pairs only)
+template <class T>
+__device__ __forceinline__ void superpass_tables(const FftParams& P, cpx<T>* tabs, int sp, int L)
+{
+    const int t = P.sp_first[sp], q1 = P.fac[t];
+    pass_table_build<T>(P, tabs, L, P.nphi / (q1 * L));
+    if (P.sp_count[sp] == 2) pass_table_build<T>(P, tabs + FFT_PT, L, P.nphi / (q1 * P.fac[t + 1] * L));
+}
+// sub-length L at which super-pass sp works (product of the radices before it)
+__device__ __forceinline__ int superpass_L(const FftParams& P, int sp)
+{
+    int L = 1;
+    for (int t = 0; t < P.sp_first[sp]; ++t) L *= P.fac[t];
+    return L;
+}
+
+// in-place mixed-radix passes over buf[0..n).  DIF == false: digit-reversed input -> natural output (super-passes in order);
+// DIF == true: natural input -> digit-reversed output (super-passes in reverse order).  SIGN = -1 forward.
+// ptabs: 2 x 2 pass tables, double buffered; the tables of the FIRST super-pass were built by the caller before its last barrier.
 template <class T, int SIGN, bool DIF>
 __device__ void fft_passes(const FftParams& P, const TwTab<T>& W, cpx<T>* buf, cpx<T>* ptabs)
 {
-    // ptabs: two per-pass twiddle tables; the table of the FIRST pass was built by the caller before its last barrier
     const int n = P.n;
-    int L = DIF ? n : 1;
-    for (int tt = 0; tt < P.nfac; ++tt) {
-        const int t = DIF ? (P.nfac - 1 - tt) : tt;
-        const int q = P.fac[t];
-        if (DIF) L /= q;
-        const int nb = n / q;
+    for (int ss = 0; ss < P.nsp; ++ss) {
+        const int sp = DIF ? (P.nsp - 1 - ss) : ss;
+        const int t = P.sp_first[sp], q1 = P.fac[t];
+        const int L = superpass_L(P, sp);
         const unsigned magic = P.magic[t];
-        const cpx<T>* cur = ptabs + (tt & 1) * FFT_PT;
-        if (tt + 1 < P.nfac) {   // next pass's table (read only after the barrier below)
-            const int t2 = DIF ? (t - 1) : (t + 1);
-            const int q2 = P.fac[t2];
-            const int L2 = DIF ? (L / q2) : (L * q);
-            pass_table_build<T>(P, ptabs + ((tt + 1) & 1) * FFT_PT, L2, P.nphi / (q2 * L2));
+        const cpx<T>* cur = ptabs + (ss & 1) * 2 * FFT_PT;
+        if (ss + 1 < P.nsp) {   // next super-pass's tables (read only after the barrier below)
+            const int sp2 = DIF ? (sp - 1) : (sp + 1);
+            superpass_tables<T>(P, ptabs + ((ss + 1) & 1) * 2 * FFT_PT, sp2, superpass_L(P, sp2));
         }
-        if (q == 4) pass_loop<T, SIGN, 4, DIF>(cur, buf, L, nb, magic);
-        else if (q == 3) pass_loop<T, SIGN, 3, DIF>(cur, buf, L, nb, magic);
-        else if (q == 5) pass_loop<T, SIGN, 5, DIF>(cur, buf, L, nb, magic);
-        else if (q == 2) pass_loop<T, SIGN, 2, DIF>(cur, buf, L, nb, magic);
-        else {
-            const int tstep = P.nphi / (q * L);   // W_{qL}^{a} = tw[a * tstep]
-            for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-                const int g = (L == 1) ? b : (int)__umulhi((unsigned)b, magic);
-                const int kk = b - g * L;
-                butterfly_generic<T, SIGN, DIF>(P, W, buf + (size_t)g * q * L + kk, q, L, kk * tstep);
+        if (P.sp_count[sp] == 2) {
+            const int q2 = P.fac[t + 1], nb = n / (q1 * q2);
+            if (q1 == 2) pass2_dispatch<T, SIGN, 2, DIF>(q2, cur, cur + FFT_PT, buf, L, nb, magic);
+            else if (q1 == 3) pass2_dispatch<T, SIGN, 3, DIF>(q2, cur, cur + FFT_PT, buf, L, nb, magic);
+            else if (q1 == 4) pass2_dispatch<T, SIGN, 4, DIF>(q2, cur, cur + FFT_PT, buf, L, nb, magic);
+            else pass2_dispatch<T, SIGN, 5, DIF>(q2, cur, cur + FFT_PT, buf, L, nb, magic);
+        } else {
+            const int nb = n / q1;
+            if (q1 == 4) pass_loop<T, SIGN, 4, DIF>(cur, buf, L, nb, magic);
+            else if (q1 == 3) pass_loop<T, SIGN, 3, DIF>(cur, buf, L, nb, magic);
+            else if (q1 == 5) pass_loop<T, SIGN, 5, DIF>(cur, buf, L, nb, magic);
+            else if (q1 == 2) pass_loop<T, SIGN, 2, DIF>(cur, buf, L, nb, magic);
+            else {
+                const int tstep = P.nphi / (q1 * L);   // W_{qL}^{a} = tw[a * tstep]
+                for (int b = threadIdx.x; b < nb; b += blockDim.x) {
+                    const int g = (L == 1) ? b : (int)__umulhi((unsigned)b, magic);
+                    const int kk = b - g * L;
+                    butterfly_generic<T, SIGN, DIF>(P, W, buf + (size_t)g * q1 * L + kk, q1, L, kk * tstep);
+                }
             }
         }
-        if (!DIF) L *= q;
         __syncthreads();
     }
-}
-
-// geometry of the first pass in execution order (for the caller's table build)
-template <bool DIF>
-__device__ __forceinline__ void first_pass_geom(const FftParams& P, int& L, int& tstep)
-{
-    const int t = DIF ? (P.nfac - 1) : 0;
-    const int q = P.fac[t];
-    L = DIF ? (P.n / q) : 1;
-    tstep = P.nphi / (q * L);
 }
 
 // phase element (band ring, component c, m): in this launch's local rows, or -- m-sharded -- in the buffer of m's owner
@@ -332,7 +472,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
     PIXSHT_DYN_SMEM(smem_raw);
     cpx<T>* buf = reinterpret_cast<cpx<T>*>(smem_raw);   // n + 1 entries, then the twiddle tables
     const TwTab<T> W = tw_setup<T>(P, buf + P.n + 1);
-    cpx<T>* ptabs = buf + P.n + 1 + fft_tw_entries(P.nphi);   // 2 x FFT_PT per-pass tables
+    cpx<T>* ptabs = buf + P.n + 1 + fft_tw_entries(P.nphi);   // 2 x 2 x FFT_PT pass tables
     const int rl = blockIdx.x, c = P.c_begin + blockIdx.y, ring = P.ring_begin + rl;
     const int n = P.n;
     double2* row = P.phase + ((long long)rl * P.ncomp + c) * P.MP;
@@ -381,7 +521,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
             buf[k] = cadd(ea, cmuli<T, +1>(oa));
         }
     }
-    { int L1, ts1; first_pass_geom<true>(P, L1, ts1); pass_table_build<T>(P, ptabs, L1, ts1); }
+    superpass_tables<T>(P, ptabs, P.nsp - 1, superpass_L(P, P.nsp - 1));
     __syncthreads();
     fft_passes<T, +1, true>(P, W, buf, ptabs);
 
@@ -409,7 +549,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams 
     PIXSHT_DYN_SMEM(smem_raw);
     cpx<T>* buf = reinterpret_cast<cpx<T>*>(smem_raw);   // n + 1 entries, then the twiddle tables
     const TwTab<T> W = tw_setup<T>(P, buf + P.n + 1);
-    cpx<T>* ptabs = buf + P.n + 1 + fft_tw_entries(P.nphi);   // 2 x FFT_PT per-pass tables
+    cpx<T>* ptabs = buf + P.n + 1 + fft_tw_entries(P.nphi);   // 2 x 2 x FFT_PT pass tables
     const int rl = blockIdx.x, c = P.c_begin + blockIdx.y, ring = P.ring_begin + rl;
     const int n = P.n, N = P.nphi;
     const T* in = reinterpret_cast<const T*>(P.maps[c]);
@@ -427,7 +567,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams 
 #pragma unroll
         for (int u = 0; u < FFT_IO_UNROLL; ++u) if ((int)(j0 + u * blockDim.x) < n) buf[pj[u]] = z[u];
     }
-    { int L1, ts1; first_pass_geom<false>(P, L1, ts1); pass_table_build<T>(P, ptabs, L1, ts1); }
+    superpass_tables<T>(P, ptabs, 0, 1);
     __syncthreads();
     fft_passes<T, -1, false>(P, W, buf, ptabs);
 

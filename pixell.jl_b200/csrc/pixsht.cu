@@ -57,6 +57,7 @@ struct pixsht_plan {
     // FFT
     int nfft = 0, nfac = 0, fac[FFT_MAXFAC] = {0}, fft_threads = 256;
     unsigned fft_magic[FFT_MAXFAC] = {0};
+    int nsp = 0; unsigned char sp_first[FFT_MAXFAC] = {0}, sp_count[FFT_MAXFAC] = {0};   // fused super-passes (fft.cuh)
     size_t fft_smem = 0;
     long long MP = 0;             // phase row length (mmax+1 rounded up to a multiple of 8 complex = 128 B)
     // geometry (host copies kept for introspection)
@@ -167,7 +168,8 @@ static int factorize(int n, int* fac, int& nfac)
             odd[nodd++] = n; n = 1;
         }
     }
-    for (int i = nodd - 1; i >= 0; --i) fac[nfac++] = odd[i];
+    // odd radices alternate large / small (5,3,5,3,...) so that neighbours fuse into super-passes of <= 16 points
+    for (int lo = 0, hi = nodd - 1; lo <= hi;) { fac[nfac++] = odd[hi--]; if (lo <= hi) fac[nfac++] = odd[lo++]; }
     for (; n2 >= 2; n2 -= 2) { if (nfac >= FFT_MAXFAC) return 1; fac[nfac++] = 4; }
     if (n2 == 1) { if (nfac >= FFT_MAXFAC) return 1; fac[nfac++] = 2; }
     return 0;
@@ -273,7 +275,22 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     P->nfft = P->nphi / 2;
     if (factorize(P->nfft, P->fac, P->nfac)) return fail(PIXSHT_ERR_UNSUPPORTED, "nphi/2 has a prime factor > 64");
     const size_t elem = (P->dtype == PIXSHT_F64) ? 16 : 8;
-    P->fft_smem = (size_t)(P->nfft + 1 + fft_tw_entries(P->nphi) + 2 * FFT_PT) * elem;
+    P->fft_smem = (size_t)(P->nfft + 1 + fft_tw_entries(P->nphi) + 4 * FFT_PT) * elem;
+    {
+        // super-passes: neighbouring radices from {2,3,4,5} whose product is <= PIXSHT_FFT_FUSE (default 16) share one
+        // shared-memory round trip
+        const int lim = std::min(env_int("PIXSHT_FFT_FUSE", FFT_FUSE_MAX), FFT_FUSE_MAX);
+        P->nsp = 0;
+        for (int t = 0; t < P->nfac;) {
+            const bool small = P->fac[t] <= 5 && t + 1 < P->nfac && P->fac[t + 1] <= 5;
+            const int cnt = (small && P->fac[t] * P->fac[t + 1] <= lim && P->fac[t] * P->fac[t + 1] <= FFT_CST_MAX) ? 2 : 1;
+            P->sp_first[P->nsp] = (unsigned char)t; P->sp_count[P->nsp] = (unsigned char)cnt; ++P->nsp; t += cnt;
+        }
+        std::vector<double2> cst((FFT_CST_MAX + 1) * FFT_CST_MAX);
+        for (int S = 1; S <= FFT_CST_MAX; ++S)
+            for (int k = 0; k < S; ++k) { const long double a = 2.0L * LPI * k / S; cst[S * FFT_CST_MAX + k] = make_double2((double)cosl(a), (double)(-sinl(a))); }
+        CU(cudaMemcpyToSymbol(c_fft_cst, cst.data(), sizeof(double2) * cst.size()));
+    }
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, P->device));
     P->sm_count = prop.multiProcessorCount;
@@ -291,7 +308,11 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
         long long best = -1; int bt = tmax;
         for (int t = tmin; t <= tmax; t += 32) {
             long long cost = 0;
-            for (int i = 0; i < P->nfac; ++i) { const int nb = P->nfft / P->fac[i]; cost += (long long)((nb + t - 1) / t) * (P->fac[i] + 2); }
+            for (int i = 0; i < P->nsp; ++i) {
+                int pts = P->fac[P->sp_first[i]]; if (P->sp_count[i] == 2) pts *= P->fac[P->sp_first[i] + 1];
+                const int nb = P->nfft / pts;
+                cost += (long long)((nb + t - 1) / t) * (pts + 2);
+            }
             cost = cost * 64 + (tmax - t) / 32;   // ties: prefer more threads
             if (best < 0 || cost < best) { best = cost; bt = t; }
         }
@@ -602,6 +623,8 @@ static int stage_fft(pixsht_plan* P, int dir, int ncomp, int c_begin, int c_coun
     memset(&F, 0, sizeof(F));
     F.nphi = P->nphi; F.n = P->nfft; F.nfac = P->nfac;
     for (int i = 0; i < P->nfac; ++i) { F.fac[i] = P->fac[i]; F.magic[i] = P->fft_magic[i]; }
+    F.nsp = P->nsp;
+    for (int i = 0; i < P->nsp; ++i) { F.sp_first[i] = P->sp_first[i]; F.sp_count[i] = P->sp_count[i]; }
     F.tw = P->d_tw.p; F.phi0tw = P->d_phi0tw.p; F.wgt = P->d_wgt.p; F.perm = P->d_perm.p; F.mmax = P->mmax;
     F.phase = phase; F.mtab = mtab; F.MP = P->MP; F.ncomp = ncomp; F.c_begin = c_begin;
     F.ring_begin = ring_begin; F.ring_count = ring_count;

@@ -1,8 +1,3 @@
-set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/pytest_gpu_final.log; cat gpurun_out/pytest_gpu_final.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 > gpurun_out/smoke_final.log; cat gpurun_out/smoke_final.log
-python bench.py > gpurun_out/bench_c4_final.log 2>&1; tail -1 gpurun_out/bench_c4_final.log | cut -c1-400
-python bench.py --workload C3 > gpurun_out/bench_c3_final.log 2>&1; tail -1 gpurun_out/bench_c3_final.log | cut -c1-300
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c4_final.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_l.log 2>&1
-M=dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum,sm__cycles_elapsed.max,lts__t_bytes.sum,smsp__warps_active.avg.per_cycle_active
-ncu --metrics $M --clock-control none -k regex:"leg_|fft_" --launch-skip 6 --launch-count 6 --csv --log-file gpurun_out/metrics_c4_final.csv python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_m.log 2>&1
+python -m pytest tests -m gpu -x -q -k "not c4_size and not c3_size" 2>&1 | tail -2
+for f in 16 1; do for w in C3 C4; do PIXSHT_FFT_FUSE=$f python bench.py --workload $w --steps 2 --warmup 1 --no-e2e --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('fuse', $f, d['value'], d['stages'], round(d['roofline_fft']['frac'],3))"; done; done
+python bench.py --workload C2 --steps 3 --warmup 2 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('C2', d['value'], d['stages'], d['e2e']['value'])"

@@ -101,7 +101,12 @@ end
 compute_type(::Type{Float32}) = Float32
 compute_type(::Type) = Float64            # the reference promotes everything to Float64 (src/transforms.jl:71)
 
-dense(m::AbstractArray{T}, ::Type{T}) where {T} = (m isa Array && true) ? m : Array(m)
+# a contiguous column-major plane of eltype T is passed as it is (Array, or a contiguous view such as m[:, :, c]);
+# anything else is copied / converted once
+is_dense(m::Array) = true
+is_dense(m::SubArray) = Base.iscontiguous(m)
+is_dense(m) = false
+dense(m::AbstractArray{T}, ::Type{T}) where {T} = is_dense(m) ? m : Array(m)
 dense(m::AbstractArray, ::Type{T}) where {T} = Array{T}(m)
 
 # ---- map2alm: src/transforms.jl:88-165 -------------------------------------------------------------------------

@@ -106,6 +106,7 @@ def cpu_baseline(wl, target_s=12.0, maps=None, alms=None):
     import pixsht
     from oracle import get_cpu_sht, cc_geometry, nalm as nalm_of
     cpu = get_cpu_sht()
+    cpu.use_all_cores()
     res = wl["res_arcmin"] * pixsht.arcminute
     shape, wcs = pixsht.fullsky_geometry(res)
     band = pixsht.sht_band(shape, wcs)

@@ -153,7 +153,18 @@ class CpuSht:
         L.cpu_map2alm.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                   pp, pp, ctypes.c_int, ctypes.c_int, dp]
         L.cpu_num_threads.restype = ctypes.c_int
+        L.cpu_set_threads.argtypes = [ctypes.c_int]
+        L.cpu_set_threads.restype = None
         self.last_times = (0.0, 0.0)
+
+    def use_all_cores(self):
+        """All host cores, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for its workers)."""
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+        self.lib.cpu_set_threads(n)
+        return n
 
     @property
     def threads(self):

@@ -521,6 +521,16 @@ int cpu_map2alm(int spin, int nrings, const double *theta, const double *wgt, do
     return 0;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the timed baseline must use the cores it claims */
+void cpu_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int cpu_num_threads(void)
 {
 #ifdef _OPENMP

@@ -20,7 +20,6 @@ import os
 import subprocess
 import sys
 import threading
-import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for _p in (ROOT, os.path.join(ROOT, "pixell.jl_b200"), os.path.join(ROOT, "tests")):

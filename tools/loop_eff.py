@@ -1,10 +1,10 @@
 #!/usr/bin/env python
 """Inner-loop efficiency probe: time the Legendre kernels on the NM lowest m and the CHUNKS equator-most chunks only
 (PIXSHT_DBG_NM / PIXSHT_DBG_CHUNKS), where every ring is active over ~the whole l range, and compare with the DFMA peak."""
-import os, sys, ctypes
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "pixell.jl_b200")]
-import numpy as np, torch, pixsht
+import torch, pixsht
 from pixsht.transforms import Plan, get_lib, MAP2ALM, ALM2MAP, DEVICE
 nm, nch = int(sys.argv[1]), int(sys.argv[2])
 res = float(sys.argv[3]) if len(sys.argv) > 3 else 2.0

@@ -36,9 +36,10 @@ typedef struct pixsht_plan pixsht_plan;
 enum { PIXSHT_OK = 0, PIXSHT_ERR_ARG = 1, PIXSHT_ERR_CUDA = 2, PIXSHT_ERR_UNSUPPORTED = 3, PIXSHT_ERR_NOMEM = 4, PIXSHT_ERR_NODEVICE = 5 };
 enum { PIXSHT_F64 = 0, PIXSHT_F32 = 1 };             /* element type of maps and alm at the boundary */
 enum { PIXSHT_MAP2ALM = 0, PIXSHT_ALM2MAP = 1 };     /* numerically equal to libsharp2's SHARP_MAP2ALM / SHARP_ALM2MAP */
-enum { PIXSHT_HOST = 0, PIXSHT_DEVICE = 1 };         /* where the alm / map pointers passed to pixsht_execute live */
+enum { PIXSHT_HOST = 0, PIXSHT_DEVICE = 1 };
+enum { PIXSHT_RINGS_CC = 0, PIXSHT_RINGS_FEJER1 = 1 };  /* ring scheme of pixsht_geom */         /* where the alm / map pointers passed to pixsht_execute live */
 
-/* How the caller's (nx, ny) map sits on the full-sky Clenshaw-Curtis ring grid. */
+/* How the caller's (nx, ny) map sits on the full-sky ring grid. */
 typedef struct pixsht_geom {
     int32_t nphi;          /* pixels of a full ring           = fullringsize(wcs)   (src/transforms.jl:3-4)   */
     int32_t nrings_total;  /* rings of the full-sky grid      = fullringnum(wcs)    (src/transforms.jl:7-8)   */
@@ -47,7 +48,9 @@ typedef struct pixsht_geom {
     int32_t nx;            /* columns in the map (<= nphi); band columns nx..nphi-1 are zeros (:70-75)          */
     int32_t flipx;         /* 1: band column i is map column nx-1-i  (cdelt1 < 0, :25-30)                       */
     int32_t flipy;         /* 1: band ring r is map row ny-1-r       (cdelt2 > 0, :25-30)                       */
-    int32_t reserved;
+    int32_t ring_scheme;   /* PIXSHT_RINGS_CC: theta_k = pi k/(N-1), Clenshaw-Curtis weights (the reference's only SHT grid,
+                              src/transforms.jl:44-46); PIXSHT_RINGS_FEJER1: theta_k = pi (k+1/2)/N, Fejer-1 weights (the
+                              CarFejer1 grid of src/projections/car_proj.jl:14-19, which has no SHT path upstream)   */
     double phi0;           /* RA (radians) of band column 0 (:41)                                                */
 } pixsht_geom;
 

@@ -182,7 +182,8 @@ static int env_int(const char* name, int dflt)
     return atoi(s);
 }
 
-static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const std::vector<double>& wgt_or_empty, int N_cc, int ring_first)
+static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const std::vector<double>& wgt_or_empty, int N_cc, int ring_first,
+                      int ring_scheme = 0)
 {
     const int nr = P->nrings, lmax = P->lmax, mmax = P->mmax;
     P->nalm = pixsht_nalm(lmax, mmax);
@@ -351,7 +352,8 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
 
     // ---- device-side precompute ----
     if (wgt_or_empty.empty()) {
-        PIXSHT_LAUNCH(k_cc_weights, (nr + 127) / 128, 128, 0, P->stream, N_cc, P->nphi, ring_first, nr, P->d_wgt.p);
+        if (ring_scheme == PIXSHT_RINGS_FEJER1) PIXSHT_LAUNCH(k_fejer1_weights, (nr + 127) / 128, 128, 0, P->stream, N_cc, P->nphi, ring_first, nr, P->d_wgt.p);
+        else PIXSHT_LAUNCH(k_cc_weights, (nr + 127) / 128, 128, 0, P->stream, N_cc, P->nphi, ring_first, nr, P->d_wgt.p);
     } else {
         CU(cudaMemcpyAsync(P->d_wgt.p, wgt_or_empty.data(), sizeof(double) * nr, cudaMemcpyHostToDevice, P->stream));
     }
@@ -401,16 +403,20 @@ extern "C" int pixsht_plan_create(pixsht_plan** out, const pixsht_geom* g, int l
     if (dtype != PIXSHT_F64 && dtype != PIXSHT_F32) return fail(PIXSHT_ERR_ARG, "dtype must be PIXSHT_F64 or PIXSHT_F32");
     if (g->nphi < 2 || g->nrings_total < 2 || g->nrings < 1 || g->ring_first < 0 || g->ring_first + g->nrings > g->nrings_total)
         return fail(PIXSHT_ERR_ARG, "inconsistent ring geometry");
+    if (g->ring_scheme != PIXSHT_RINGS_CC && g->ring_scheme != PIXSHT_RINGS_FEJER1) return fail(PIXSHT_ERR_ARG, "unknown ring scheme");
     if (g->nx < 1 || g->nx > g->nphi) return fail(PIXSHT_ERR_ARG, "need 1 <= nx <= nphi");
     int rc = check_device(device); if (rc) return rc;
     pixsht_plan* P = new pixsht_plan();
     P->device = device; P->dtype = dtype; P->nphi = g->nphi; P->nrings = g->nrings; P->lmax = lmax; P->mmax = mmax;
     P->nx = g->nx; P->ny = g->nrings; P->flipx = g->flipx != 0; P->flipy = g->flipy != 0; P->phi0 = g->phi0;
     // theta_k = pi k/(N-1) rounded to double, as range(0, pi, length=N)[k] gives the reference (src/transforms.jl:46)
+    // Fejer-1: theta_k = pi (k + 1/2)/N, no ring on the poles
     std::vector<double> theta(g->nrings);
     for (int i = 0; i < g->nrings; ++i)
-        theta[i] = (double)(LPI * (long double)(g->ring_first + i) / (long double)(g->nrings_total - 1));
-    rc = plan_build(P, theta, std::vector<double>(), g->nrings_total, g->ring_first);
+        theta[i] = g->ring_scheme == PIXSHT_RINGS_FEJER1
+                       ? (double)(LPI * ((long double)(g->ring_first + i) + 0.5L) / (long double)g->nrings_total)
+                       : (double)(LPI * (long double)(g->ring_first + i) / (long double)(g->nrings_total - 1));
+    rc = plan_build(P, theta, std::vector<double>(), g->nrings_total, g->ring_first, g->ring_scheme);
     if (rc) { std::string keep = g_err; pixsht_plan_destroy(P); g_err = keep; return rc; }
     *out = P;
     return PIXSHT_OK;

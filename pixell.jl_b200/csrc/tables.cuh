@@ -27,6 +27,23 @@ __global__ void k_cc_weights(int N, int nphi, int ring_first, int nrings, double
     w[i] = (2.0 / (double)n) * (1.0 - s) * scale;
 }
 
+// Fejer's first rule on the N interior nodes theta_k = pi (k + 1/2)/N (no ring on the poles): ring weights
+// w_k = f_k * 2pi/nphi,  f_k = (2/N) [1 - 2 sum_{q=1}^{floor(N/2)} cos(2 q theta_k)/(4 q^2 - 1)]  (exact for polynomials in
+// cos(theta) of degree < N).  The reference declares the CarFejer1 type but has no SHT path for it.
+__global__ void k_fejer1_weights(int N, int nphi, int ring_first, int nrings, double* __restrict__ w)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrings) return;
+    const int k = ring_first + i;
+    const double scale = 2.0 * 3.14159265358979323846 / (double)nphi;
+    double s = 0.0;
+    for (int q = N / 2; q >= 1; --q) {
+        const long long t = ((long long)q * (2 * k + 1)) % (2LL * N);   // 2 q theta_k = pi q (2k+1)/N, reduced mod 2 pi
+        s += cospi((double)t / (double)N) / (4.0 * (double)q * (double)q - 1.0);
+    }
+    w[i] = (2.0 / (double)N) * (1.0 - 2.0 * s) * scale;
+}
+
 // A_l of lambda_{l+1} = A_l (x - mu_l) lambda_l - (A_l/A_{l-1}) lambda_{l-1}   (normalised d-functions)
 __device__ __forceinline__ double coefA(int l, int m, int s)
 {

@@ -29,7 +29,7 @@ struct PixshtGeom
     nx::Int32
     flipx::Int32
     flipy::Int32
-    reserved::Int32
+    ring_scheme::Int32     # 0: Clenshaw-Curtis rings (the reference's SHT grid), 1: Fejer-1
     phi0::Float64
 end
 

@@ -20,7 +20,7 @@ class PixshtError(RuntimeError):
 class Geom(ctypes.Structure):
     _fields_ = [("nphi", ctypes.c_int32), ("nrings_total", ctypes.c_int32), ("ring_first", ctypes.c_int32),
                 ("nrings", ctypes.c_int32), ("nx", ctypes.c_int32), ("flipx", ctypes.c_int32), ("flipy", ctypes.c_int32),
-                ("reserved", ctypes.c_int32), ("phi0", ctypes.c_double)]
+                ("ring_scheme", ctypes.c_int32), ("phi0", ctypes.c_double)]
 
 
 # every symbol include/pixsht.h and include/pixsht_sharp_shim.h declare

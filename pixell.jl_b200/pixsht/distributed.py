@@ -85,7 +85,7 @@ class ShardedSHT:
         self.mmax = int(lmax if mmax is None else mmax)
         self.device = torch.device(device if device is not None else "cuda")
         self.dev_index = self.device.index if self.device.type == "cuda" and self.device.index is not None else 0
-        g = Geom(band.nphi, band.nrings_total, band.ring_first, band.nrings, band.nx, int(band.flipx), int(band.flipy), 0, band.phi0)
+        g = Geom(band.nphi, band.nrings_total, band.ring_first, band.nrings, band.nx, int(band.flipx), int(band.flipy), int(getattr(band, "ring_scheme", 0)), band.phi0)
         h = ctypes.c_void_p()
         self.dtype = dtype
         if dtype not in (torch.float64, torch.float32):

@@ -67,10 +67,20 @@ def _julia_round(x):
 
 
 def fullsky_geometry(res, W=CarClenshawCurtis, shape=None, dims=()):
-    """Full-sky CAR geometry with pixels on the poles (src/enmap_geom.jl:47-73). `res` in radians (number or pair)."""
+    """Full-sky CAR geometry with pixels on the poles (src/enmap_geom.jl:47-73). `res` in radians (number or pair).
+    W = CarFejer1 (extension: the reference has the type but no constructor) gives the Fejer-1 grid: ny =
+    pi/res rings at colatitudes (k + 1/2) res, none on the poles."""
     if not isinstance(res, (tuple, list)):
         res = (res, res)
     resx, resy = float(res[0]), float(res[1])
+    if W is CarFejer1:
+        if shape is None:
+            shape = (_julia_round(2 * math.pi / resx), _julia_round(math.pi / resy))
+        nx, ny = shape
+        if not abs(resx * nx - 2 * math.pi) < 1e-8 or not abs(resy * ny - math.pi) < 1e-8:
+            raise AssertionError("Resolution does not evenly divide the sky; this is required for SHTs.")
+        wcs = create_car_wcs(W, (-360.0 / nx, 180.0 / ny), (math.floor(nx / 2) + 0.5, (ny + 1) / 2), (resy * 90 / math.pi, 0.0))
+        return (nx, ny) + tuple(dims), wcs
     if shape is None:
         shape = (_julia_round(2 * math.pi / resx), _julia_round(math.pi / resy + 1))
     nx, ny = shape
@@ -160,8 +170,9 @@ def fullringsize(wcs):
 
 
 def fullringnum(wcs):
-    """Number of rings of the full-sky version of this WCS (src/transforms.jl:7-8)."""
-    return 1 + _julia_round(abs(math.pi / (getunit(wcs) * getcdelt(wcs)[1])))
+    """Number of rings of the full-sky version of this WCS (src/transforms.jl:7-8); Fejer-1 grids have no pole rings."""
+    n = _julia_round(abs(math.pi / (getunit(wcs) * getcdelt(wcs)[1])))
+    return n if isinstance(wcs, CarFejer1) else 1 + n
 
 
 def getlmax(wcs):
@@ -174,8 +185,9 @@ def first_last_rings_in_fullsky(shape, wcs):
     dth = abs(getcdelt(wcs)[1] * getunit(wcs))
     d1 = pix2sky(shape, wcs, 1, 1)[1]
     d2 = pix2sky(shape, wcs, 1, shape[1])[1]
-    i1 = _julia_round((math.pi / 2 - d1) / dth) + 1
-    i2 = _julia_round((math.pi / 2 - d2) / dth) + 1
+    half = 0.5 if isinstance(wcs, CarFejer1) else 0.0      # Fejer-1 rings sit at (k + 1/2) dtheta
+    i1 = _julia_round((math.pi / 2 - d1) / dth - half) + 1
+    i2 = _julia_round((math.pi / 2 - d2) / dth - half) + 1
     return i1, i2
 
 
@@ -199,6 +211,7 @@ class ShtBand:
     flipx: bool        # band column i  <-> map column nx-1-i
     flipy: bool        # band ring r    <-> map row ny-1-r
     phi0: float        # RA of band column 0, radians, in [-pi, pi]
+    ring_scheme: int = 0   # 0: Clenshaw-Curtis rings (poles included), 1: Fejer-1 rings
 
 
 def sht_band(shape, wcs):
@@ -214,4 +227,4 @@ def sht_band(shape, wcs):
     if i2 - i1 + 1 != shape[1]:
         raise ValueError("map rows do not align with the full-sky ring grid")
     return ShtBand(nphi=nphi, nrings_total=fullringnum(w2), ring_first=i1 - 1, nrings=shape[1], nx=shape[0],
-                   flipx=fx.step == -1, flipy=fy.step == -1, phi0=phi0)
+                   flipx=fx.step == -1, flipy=fy.step == -1, phi0=phi0, ring_scheme=1 if isinstance(wcs, CarFejer1) else 0)

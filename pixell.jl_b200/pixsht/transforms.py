@@ -28,7 +28,7 @@ class Plan:
         if self.dtype not in (np.dtype(np.float64), np.dtype(np.float32)):
             raise TypeError("maps must be Float64 or Float32")
         self.cdtype = np.dtype(np.complex128 if self.dtype == np.float64 else np.complex64)
-        g = Geom(band.nphi, band.nrings_total, band.ring_first, band.nrings, band.nx, int(band.flipx), int(band.flipy), 0,
+        g = Geom(band.nphi, band.nrings_total, band.ring_first, band.nrings, band.nx, int(band.flipx), int(band.flipy), int(getattr(band, "ring_scheme", 0)),
                  band.phi0)
         h = ctypes.c_void_p()
         self.lib.check(self.lib.lib.pixsht_plan_create(ctypes.byref(h), ctypes.byref(g), self.lmax, self.mmax,

@@ -93,3 +93,18 @@ def synth_alm(lmax, mmax, seed, spin2=False):
             i0 = m * (2 * lmax + 1 - m) // 2
             a[i0 + m:i0 + 2] = 0  # l = m .. 1
     return a
+
+
+def fejer1_geometry(nrings_total, nphi, ring_first=0, nrings=None):
+    """Colatitudes and ring weights (x 2pi/nphi) of the Fejer-1 grid theta_k = pi (k + 1/2)/N (test-side restatement, independent
+    of the device kernel: the weights come from the moment equations sum_k f_k T_j(cos theta_k) = int T_j, solved through the
+    orthogonality of the Chebyshev polynomials on these nodes)."""
+    N = nrings_total
+    k = np.arange(N)
+    theta = np.pi * (k + 0.5) / N
+    f = np.full(N, 2.0 / N)                                  # j = 0 term: int T_0 = 2
+    for j in range(2, N, 2):                                 # int_{-1}^{1} T_j = 2/(1 - j^2) for even j, 0 for odd j
+        f += (2.0 / N) * 2.0 / (1.0 - j * j) * np.cos(j * theta)
+    w = f * 2.0 * np.pi / nphi
+    nrings = N - ring_first if nrings is None else nrings
+    return theta[ring_first:ring_first + nrings], w[ring_first:ring_first + nrings]

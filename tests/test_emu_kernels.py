@@ -116,3 +116,4 @@ def test_emu_replay_edge_cases(emu_default):
     g.test_edge_tiny_and_ragged_bands()
     g.test_argument_errors_are_reported_not_fatal()
     g.test_alm2cl_on_device_matches_host_mirror()
+    g.test_fejer1_rings()

@@ -136,3 +136,19 @@ def test_library_refuses_to_compute_without_a_device():
     with pytest.raises(_lib.PixshtError) as e:
         pixsht.Plan(sht_band(shape, wcs), 18)
     assert e.value.code == _lib.ERR_NODEVICE and "no CPU fallback" in str(e.value)
+
+
+def test_fejer1_geometry_extension():
+    """CarFejer1 full-sky grid (extension; the reference has the type but no constructor / SHT path)."""
+    from pixsht import CarFejer1
+    shape, wcs = fullsky_geometry(math.radians(1.0), W=CarFejer1)
+    assert shape == (360, 180) and isinstance(wcs, CarFejer1)
+    assert fullringnum(wcs) == 180 and fullringsize(wcs) == 360
+    # ring centres at (k + 1/2) degrees of colatitude, none on the poles
+    assert abs(pix2sky(shape, wcs, 1, 1)[1] - math.radians(-89.5)) < 1e-12
+    assert abs(pix2sky(shape, wcs, 1, 180)[1] - math.radians(89.5)) < 1e-12
+    b = sht_band(shape, wcs)
+    assert (b.nrings_total, b.ring_first, b.nrings, b.ring_scheme) == (180, 0, 180, 1)
+    sub_shape, sub_wcs = slice_geometry(shape, wcs, slice(0, 360), slice(10, 50))
+    bs = sht_band(sub_shape, sub_wcs)
+    assert (bs.ring_first, bs.nrings, bs.ring_scheme) == (130, 40, 1)      # rows 10..49 from the south = rings 130..169 from the north

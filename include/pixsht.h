@@ -70,6 +70,11 @@ void pixsht_plan_destroy(pixsht_plan *plan);
  * Outputs are overwritten (SHARP_ADD is never used by the reference). */
 int pixsht_execute(pixsht_plan *plan, int direction, int ncomp, void *const *alms, void *const *maps, int location);
 
+/* Batch of nbatch independent spin-0 transforms on one geometry (simulation sweeps; no counterpart in the reference, which
+ * transforms one map per libsharp job).  alms[b] / maps[b] as for ncomp = 1.  Up to four maps share one recurrence per
+ * (m, ring pair): 2 + 2 NB FP64 ops per (l, m, ring pair) instead of 4 NB. */
+int pixsht_execute_batch(pixsht_plan *plan, int direction, int nbatch, void *const *alms, void *const *maps, int location);
+
 /* Run pixsht_execute on the caller's CUDA stream (cudaStream_t passed as void*; NULL is the legacy default stream) when
  * use_caller_stream != 0, or go back to the plan's own stream.  The call still synchronises that stream before returning. */
 int pixsht_plan_set_stream(pixsht_plan *plan, void *stream, int use_caller_stream);

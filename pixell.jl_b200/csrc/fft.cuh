@@ -46,7 +46,7 @@ struct FftParams {
     int ncomp, c_begin;         // components per ring in the phase buffer; first component handled by this launch (grid.y of them)
     int ring_begin, ring_count; // band rings handled by this launch; ringlocal = ring - ring_begin
     int nx, ny, flipx, flipy;   // caller's map layout (column-major nx x ny), see pixsht_geom
-    void* maps[3];
+    void* maps[4];              // up to 3 Stokes components, or a batch of up to 4 spin-0 maps
 };
 
 template <class T> struct cpx { T x, y; };

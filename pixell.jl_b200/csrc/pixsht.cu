@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "tables.cuh"
 #include "legendre.cuh"
+#include "legendre_batch.cuh"
 #include "fft.cuh"
 #include "../../include/pixsht.h"
 
@@ -76,8 +77,8 @@ struct pixsht_plan {
     DevBuf<unsigned short> d_perm;
     // work buffers (grown on demand)
     DevBuf<double2> d_phase; int phase_ncomp = 0;
-    DevBuf<unsigned char> d_map[3], d_alm[3];
-    DevBuf<double2> d_alm64[3];
+    DevBuf<unsigned char> d_map[4], d_alm[4];
+    DevBuf<double2> d_alm64[4];
     cudaStream_t stream = nullptr, own_stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t dep[48] = {nullptr};   // dependency events of the pipelined host path
     std::vector<int> h_ringN, h_ringS;
@@ -454,7 +455,7 @@ extern "C" void pixsht_plan_destroy(pixsht_plan* P)
     P->d_ad0.release(); P->d_gamma0.release(); P->d_ad2.release(); P->d_gamma2.release(); P->d_rec0.release(); P->d_rec2.release();
     P->d_tw.release(); P->d_phi0tw.release(); P->d_phase.release(); P->d_perm.release();
     P->d_lact0.release(); P->d_lact2.release(); P->d_st0.release(); P->d_st2.release();
-    for (int c = 0; c < 3; ++c) { P->d_map[c].release(); P->d_alm[c].release(); P->d_alm64[c].release(); }
+    for (int c = 0; c < 4; ++c) { P->d_map[c].release(); P->d_alm[c].release(); P->d_alm64[c].release(); }
     for (auto& e : P->ev) if (e) cudaEventDestroy(e);
     for (auto& e : P->kev) if (e) cudaEventDestroy(e);
     for (auto& e : P->dep) if (e) cudaEventDestroy(e);
@@ -955,6 +956,109 @@ extern "C" int pixsht_execute(pixsht_plan* P, int direction, int ncomp, void* co
     P->timings[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     if (ncomp != 2) { float k; CU(cudaEventElapsedTime(&k, P->kev[0], P->kev[1])); P->timings[6] = k; }
     if (ncomp >= 2) { float k; CU(cudaEventElapsedTime(&k, P->kev[2], P->kev[3])); P->timings[7] = k; }
+    return PIXSHT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// batched spin-0 transforms (legendre_batch.cuh): nbatch independent T maps / alm on one geometry, NB at a time
+// ---------------------------------------------------------------------------------------------------------------
+template <int NB>
+static int batch_group(pixsht_plan* P, int direction, double2* const* alm64, void* const* dmap, cudaStream_t st)
+{
+    constexpr int R = (NB == 4) ? 2 : 4;
+    const int prep_grid = P->sm_count > 0 ? P->sm_count * 8 : 256;
+    int rc = ensure_seek(P, 0, st); if (rc) return rc;
+    const LegJob J = {0, NB, 0, 0, P->mmax + 1, nullptr, 0, leg_total_chunks(P, R), {P->d_phase.p, 0, 0}};
+    LegParams L = leg_params(P, J, R);
+    BatchPtrs A;
+    memset(&A, 0, sizeof(A));
+    for (int b = 0; b < NB; ++b) { A.in[b] = alm64[b]; A.out[b] = alm64[b]; }
+    const int grid = L.nm * L.nchunks;
+    if (direction == PIXSHT_ALM2MAP) {
+        const size_t need = (size_t)P->nalm * BatchRec<NB>::ND;
+        if (P->d_rec0.n < need && P->d_rec0.alloc(need)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
+        L.rec = P->d_rec0.p;
+        PIXSHT_LAUNCH((k_prep_synth_b<NB>), prep_grid, 256, 0, st, 0LL, (long long)P->nalm, P->lmax, P->d_ad0.p, P->d_gamma0.p, A, P->d_rec0.p);
+        PIXSHT_LAUNCH((leg_synth_b<R, NB>), grid, LEG_NT, 0, st, L);
+        P->launches += 2;
+        CU(cudaGetLastError());
+        return stage_fft(P, PIXSHT_ALM2MAP, NB, 0, NB, P->d_phase.p, 0, P->nrings, dmap, st);
+    }
+    rc = stage_fft(P, PIXSHT_MAP2ALM, NB, 0, NB, P->d_phase.p, 0, P->nrings, dmap, st); if (rc) return rc;
+    for (int b = 0; b < NB; ++b) CU(cudaMemsetAsync(alm64[b], 0, (size_t)P->nalm * sizeof(double2), st));
+    PIXSHT_LAUNCH((leg_anal_b<R, NB>), grid, LEG_NT, 0, st, L, A);
+    P->launches++;
+    CU(cudaGetLastError());
+    return PIXSHT_OK;
+}
+
+extern "C" int pixsht_execute_batch(pixsht_plan* P, int direction, int nbatch, void* const* alms, void* const* maps, int location)
+{
+    if (!P || !alms || !maps) return fail(PIXSHT_ERR_ARG, "null argument");
+    if (direction != PIXSHT_MAP2ALM && direction != PIXSHT_ALM2MAP) return fail(PIXSHT_ERR_ARG, "bad direction");
+    if (nbatch < 1) return fail(PIXSHT_ERR_ARG, "need nbatch >= 1");
+    if (location != PIXSHT_HOST && location != PIXSHT_DEVICE) return fail(PIXSHT_ERR_ARG, "bad location");
+    for (int b = 0; b < nbatch; ++b) if (!alms[b] || !maps[b]) return fail(PIXSHT_ERR_ARG, "null map or alm pointer");
+    std::lock_guard<std::mutex> lock(P->mu);
+    int rc = check_device(P->device); if (rc) return rc;
+    const auto t_begin = std::chrono::steady_clock::now();
+    P->launches = 0;
+    // the phase rows of a group hold NB "components"; make room for the largest group
+    rc = ensure_phase(P, LEG_MAXBATCH); if (rc) return rc;
+    cudaStream_t st = P->stream;
+    const bool f32 = P->dtype == PIXSHT_F32;
+    const size_t esz = f32 ? 4 : 8;
+    const size_t map_bytes = (size_t)P->nx * P->ny * esz, alm_bytes = (size_t)P->nalm * 2 * esz;
+    const int cvt_grid = P->sm_count > 0 ? P->sm_count * 8 : 256;
+    for (int b0 = 0; b0 < nbatch;) {
+        const int left = nbatch - b0, nb = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
+        void* dmap[4] = {nullptr, nullptr, nullptr, nullptr};
+        void* dalm[4] = {nullptr, nullptr, nullptr, nullptr};
+        double2* alm64[4] = {nullptr, nullptr, nullptr, nullptr};
+        for (int b = 0; b < nb; ++b) {
+            if (location == PIXSHT_HOST) {
+                if (P->d_map[b].n < map_bytes && P->d_map[b].alloc(map_bytes)) return fail(PIXSHT_ERR_NOMEM, "map staging allocation failed");
+                if (P->d_alm[b].n < alm_bytes && P->d_alm[b].alloc(alm_bytes)) return fail(PIXSHT_ERR_NOMEM, "alm staging allocation failed");
+                dmap[b] = P->d_map[b].p; dalm[b] = P->d_alm[b].p;
+                if (direction == PIXSHT_ALM2MAP) CU(cudaMemcpyAsync(dalm[b], alms[b0 + b], alm_bytes, cudaMemcpyHostToDevice, st));
+                else CU(cudaMemcpyAsync(dmap[b], maps[b0 + b], map_bytes, cudaMemcpyHostToDevice, st));
+            } else { dmap[b] = maps[b0 + b]; dalm[b] = alms[b0 + b]; }
+            if (f32) {
+                if (P->d_alm64[b].n < (size_t)P->nalm && P->d_alm64[b].alloc(P->nalm)) return fail(PIXSHT_ERR_NOMEM, "alm work buffer allocation failed");
+                alm64[b] = P->d_alm64[b].p;
+                if (direction == PIXSHT_ALM2MAP) { PIXSHT_LAUNCH(k_cvt_f32_to_f64, cvt_grid, 256, 0, st, (const float*)dalm[b], (double*)alm64[b], 2 * P->nalm); P->launches++; }
+            } else alm64[b] = reinterpret_cast<double2*>(dalm[b]);
+        }
+        if (nb == 4) rc = batch_group<4>(P, direction, alm64, dmap, st);
+        else if (nb == 2) rc = batch_group<2>(P, direction, alm64, dmap, st);
+        else {
+            // a single map: the ordinary spin-0 kernels
+            if (direction == PIXSHT_ALM2MAP) {
+                const double2* a1[3] = {alm64[0], nullptr, nullptr};
+                rc = stage_alm2phase(P, 1, a1, P->mmax + 1, nullptr, {P->d_phase.p, 0, 0}, st);
+                if (!rc) rc = stage_fft(P, PIXSHT_ALM2MAP, 1, 0, 1, P->d_phase.p, 0, P->nrings, dmap, st);
+            } else {
+                rc = stage_fft(P, PIXSHT_MAP2ALM, 1, 0, 1, P->d_phase.p, 0, P->nrings, dmap, st);
+                if (!rc) rc = cudaMemsetAsync(alm64[0], 0, (size_t)P->nalm * sizeof(double2), st) == cudaSuccess ? PIXSHT_OK : PIXSHT_ERR_CUDA;
+                double2* a1[3] = {alm64[0], nullptr, nullptr};
+                if (!rc) rc = stage_phase2alm(P, 1, {P->d_phase.p, 0, 0}, P->mmax + 1, nullptr, a1, st);
+            }
+        }
+        if (rc) return rc;
+        for (int b = 0; b < nb; ++b) {
+            if (direction == PIXSHT_MAP2ALM && f32) { PIXSHT_LAUNCH(k_cvt_f64_to_f32, cvt_grid, 256, 0, st, (const double*)alm64[b], (float*)dalm[b], 2 * P->nalm); P->launches++; }
+            if (location == PIXSHT_HOST) {
+                if (direction == PIXSHT_ALM2MAP) CU(cudaMemcpyAsync(maps[b0 + b], dmap[b], map_bytes, cudaMemcpyDeviceToHost, st));
+                else CU(cudaMemcpyAsync(alms[b0 + b], dalm[b], alm_bytes, cudaMemcpyDeviceToHost, st));
+            }
+        }
+        if (location == PIXSHT_HOST) CU(cudaStreamSynchronize(st));   // the staging slots are reused by the next group
+        b0 += nb;
+    }
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    for (auto& t : P->timings) t = 0;
+    P->timings[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     return PIXSHT_OK;
 }
 

@@ -52,6 +52,26 @@ class Plan:
         self.lib.check(self.lib.lib.pixsht_execute(self.handle, direction, n, _ptr_array(alm_ptrs), _ptr_array(map_ptrs),
                                                    location))
 
+    def execute_batch_ptrs(self, direction, alm_ptrs, map_ptrs, location=HOST):
+        self.lib.check(self.lib.lib.pixsht_execute_batch(self.handle, direction, len(alm_ptrs), _ptr_array(alm_ptrs), _ptr_array(map_ptrs),
+                                                         location))
+
+    def alm2map_batch(self, alms):
+        """Independent spin-0 syntheses of a list of alm vectors on this plan's geometry (pixsht_execute_batch)."""
+        alms = [np.ascontiguousarray(a, dtype=self.cdtype) for a in alms]
+        for a in alms:
+            if a.shape != (self.nalm,):
+                raise ValueError("alm has %d entries, expected %d" % (a.size, self.nalm))
+        maps = [np.zeros((self.band.nx, self.band.nrings), dtype=self.dtype, order="F") for _ in alms]
+        self.execute_batch_ptrs(ALM2MAP, [a.ctypes.data for a in alms], [m.ctypes.data for m in maps])
+        return maps
+
+    def map2alm_batch(self, maps):
+        maps = [self._as_map(m) for m in maps]
+        alms = [np.zeros(self.nalm, dtype=self.cdtype) for _ in maps]
+        self.execute_batch_ptrs(MAP2ALM, [a.ctypes.data for a in alms], [m.ctypes.data for m in maps])
+        return alms
+
     def timings(self):
         t = (ctypes.c_double * 8)()
         self.lib.check(self.lib.lib.pixsht_get_timings(self.handle, t))

@@ -117,3 +117,10 @@ def test_emu_replay_edge_cases(emu_default):
     g.test_argument_errors_are_reported_not_fatal()
     g.test_alm2cl_on_device_matches_host_mirror()
     g.test_fejer1_rings()
+
+
+def test_emu_replay_batched(emu_default):
+    import test_gpu_parity as g
+    import numpy as np
+    g.test_batched_spin0_equals_single_transforms(7, np.float64, res_deg=7.5, lmax=24)
+    g.test_batched_spin0_equals_single_transforms(3, np.float32, res_deg=7.5, lmax=24)

@@ -122,5 +122,5 @@ def test_emu_replay_edge_cases(emu_default):
 def test_emu_replay_batched(emu_default):
     import test_gpu_parity as g
     import numpy as np
-    g.test_batched_spin0_equals_single_transforms(7, np.float64, res_deg=7.5, lmax=24)
+    g.test_batched_spin0_equals_single_transforms(6, np.float64, res_deg=7.5, lmax=24)
     g.test_batched_spin0_equals_single_transforms(3, np.float32, res_deg=7.5, lmax=24)

@@ -34,6 +34,8 @@ WORKLOADS = {
     "C3": dict(res_arcmin=2.0, lmax=5400, ncomp=3, dtype="f64", desc="full-sky CAR 2' (10800x5401) Float64 IQU, lmax=5400"),
     "C4": dict(res_arcmin=1.0, lmax=10800, ncomp=3, dtype="f64", desc="full-sky CAR 1' (21600x10801) Float64 IQU, lmax=10800"),
     "C5": dict(res_arcmin=0.5, lmax=21600, ncomp=1, dtype="f32", desc="full-sky CAR 0.5' (43200x21601) Float32 T-only, lmax=21600"),
+    "C2x64": dict(res_arcmin=4.0, lmax=2700, ncomp=1, dtype="f32", batch=64,
+                  desc="64-sim batched sweep: full-sky CAR 4' (5400x2701) Float32 T-only, lmax=2700 (configs[4], second part)"),
 }
 METRIC = "alm2map+map2alm wall time"
 
@@ -229,6 +231,9 @@ def main():
     esz = 8 if f64 else 4
     seed0 = 1000 * int(args.workload[1])
     stream = torch.cuda.current_stream(device)
+    if "batch" in wl:
+        return bench_batch(args, wl, config, torch, pixsht, Plan, lib, band, lmax, device, stream, rdt, cdt, npdt, local_rank,
+                           MAP2ALM, ALM2MAP, DEVICE)
     l2_scratch = None if args.workload in ("C3", "C4", "C5") else torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=device)
 
     def flush_l2():
@@ -461,6 +466,56 @@ def main():
     print(json.dumps(line))
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
+
+
+def bench_batch(args, wl, config, torch, pixsht, Plan, lib, band, lmax, device, stream, rdt, cdt, npdt, local_rank, MAP2ALM, ALM2MAP, DEVICE):
+    """Simulation sweep: B independent T transforms on one geometry, batched (pixsht_execute_batch: four maps per recurrence)
+    against the same B transforms issued one by one.  Device-resident, one GPU."""
+    B = wl["batch"]
+    plan = Plan(band, lmax, dtype=npdt)
+    lib.check(lib.lib.pixsht_plan_set_stream(plan.handle, ctypes.c_void_p(stream.cuda_stream), 1))
+    nalm = plan.nalm
+    alm = [synth_alm_device(torch, nalm, lmax, 5000 + i, False, device, cdt) for i in range(B)]
+    out = [torch.empty_like(a) for a in alm]
+    mp = [torch.empty(band.nx * band.nrings, dtype=rdt, device=device) for _ in range(B)]
+
+    def run(fn):
+        for _ in range(args.warmup):
+            fn()
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize(device)
+        return e0.elapsed_time(e1) / args.steps
+
+    def batched():
+        plan.execute_batch_ptrs(ALM2MAP, [a.data_ptr() for a in alm], [m.data_ptr() for m in mp], DEVICE)
+        plan.execute_batch_ptrs(MAP2ALM, [a.data_ptr() for a in out], [m.data_ptr() for m in mp], DEVICE)
+
+    def one_by_one():
+        for i in range(B):
+            plan.execute_ptrs(ALM2MAP, [alm[i].data_ptr()], [mp[i].data_ptr()], DEVICE)
+            plan.execute_ptrs(MAP2ALM, [out[i].data_ptr()], [mp[i].data_ptr()], DEVICE)
+
+    clk = ClockSampler(local_rank); clk.start()
+    ms_b = run(batched)
+    clocks = clk.stop()
+    ms_s = run(one_by_one)
+    fp64_peak, _ = lib.measure_fma_peak(local_rank)
+    nom = 2.0 * 2.0 * 4 * nalm * math.ceil(band.nrings / 2) * B      # flop the B single transforms would take, both directions
+    print(json.dumps({"metric": METRIC, "value": ms_b, "unit": "ms", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": ms_b, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": wl["dtype"],
+                      "data": "synthetic", "config": dict(config, batch=B, step="alm2map + map2alm of all %d maps" % B), "clocks": clocks,
+                      "sims_per_s": 1e3 * B / ms_b, "one_by_one_ms": ms_s, "one_by_one_sims_per_s": 1e3 * B / ms_s,
+                      "batch_speedup": ms_s / ms_b,
+                      "roofline": {"bound": "fp64_fma", "kernel": "leg_synth_b + leg_anal_b (+ ring FFTs) of the whole sweep",
+                                   "achieved": nom / (ms_b * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                                   "frac": nom / (ms_b * 1e-3) / 1e12 / fp64_peak, "traffic": None,
+                                   "note": "algorithmic = 4 FP64 ops per (l, m, ring pair) and map, as for single transforms; the batched "
+                                           "kernels execute 2 + 2 NB per NB maps, so frac can exceed 1"}}))
 
 
 if __name__ == "__main__":

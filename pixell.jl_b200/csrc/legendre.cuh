@@ -33,8 +33,19 @@ namespace pixsht {
 //   spin 2: { alpha, delta, G+re, G+im, G-re, G-im },  G+- = -gamma (E +- iB)/2   6 doubles
 // the analysis kernels stream the static (alpha, delta) table (2 doubles per l).
 template <int SPIN> struct SynthRec { static constexpr int ND = (SPIN == 0) ? 4 : 6; static constexpr int STEPS = (SPIN == 0) ? 128 : 64; };
+// Analysis: every l-step leaves NV double2 partial sums per lane; groups of G steps are summed over the 32 lanes through a
+// warp-private shared-memory transpose (row = (value, step), column = source lane, rows padded to 33 so that row-wise stores
+// and column-wise loads are conflict-free).  NV*G rows are shared out over the 32 lanes: LPP lanes per row, one shuffle level
+// when LPP == 2.  STEPS = records per TMA stage; spin 2 keeps it small so that 12 one-warp CTAs fit the shared memory of an SM.
 constexpr int ANAL_STEPS = 128;
-template <int SPIN> struct RedT { static constexpr int G = (SPIN == 0) ? 16 : 8; static constexpr int NV = (SPIN == 0) ? 1 : 2; };   // G: l-steps per reduction group; NV: double2 values per l
+template <int SPIN> struct RedT {
+    static constexpr int G = 16, NV = (SPIN == 0) ? 1 : 2;
+    static constexpr int STEPS = (SPIN == 0) ? ANAL_STEPS : 32;
+};
+template <int NV, int G> struct RedMap {
+    static constexpr int ROWS = NV * G, LPP = 32 / ROWS, SL = 32 / LPP;
+    static_assert(ROWS * LPP == 32 && (LPP == 1 || LPP == 2), "rows must tile the warp");
+};
 constexpr int L_NEVER = 0x3fffffff;
 
 struct LegParams {
@@ -473,13 +484,32 @@ __device__ __forceinline__ void anal_step(RingState<SPIN, R>& S, const double (&
     }
 }
 
+// Sum of row (lane % ROWS) over the 32 source lanes; every lane of the LPP sharing a row returns the full sum.
+template <int NV, int G>
+__device__ __forceinline__ double2 red_sum(const double2* red, int lane)
+{
+    using M = RedMap<NV, G>;
+    const double2* src = red + (lane % M::ROWS) * 33 + (lane / M::ROWS) * M::SL;
+    double2 a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = src[i];
+#pragma unroll
+    for (int k = 4; k < M::SL; k += 4)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const double2 q = src[k + i]; a[i].x += q.x; a[i].y += q.y; }
+    double2 t = make_double2((a[0].x + a[1].x) + (a[2].x + a[3].x), (a[0].y + a[1].y) + (a[2].y + a[3].y));
+    if (M::LPP == 2) { t.x += __shfl_xor_sync(0xffffffffu, t.x, 16); t.y += __shfl_xor_sync(0xffffffffu, t.y, 16); }
+    return t;
+}
+
 template <int SPIN, int R>
 __global__ void __launch_bounds__(LEG_NT) leg_anal(const LegParams P)
 {
     constexpr int NX = (SPIN == 0) ? 4 : 8;
     constexpr int NPART = (SPIN == 0) ? 2 : 4;
     constexpr int G = RedT<SPIN>::G, NV = RedT<SPIN>::NV;
-    constexpr int STEPS = ANAL_STEPS;
+    constexpr int STEPS = RedT<SPIN>::STEPS;
+    using M = RedMap<NV, G>;
     __shared__ __align__(16) double sbuf[2 * STEPS * 2];
     __shared__ __align__(16) double2 red[NV * G * 33];
     __shared__ __align__(8) unsigned long long sbar[2];
@@ -536,6 +566,10 @@ __global__ void __launch_bounds__(LEG_NT) leg_anal(const LegParams P)
         for (int g0 = 0; g0 < cnt; g0 += G) {
             int gcnt = cnt - g0; if (gcnt > G) gcnt = G;
             const int t0 = c * STEPS + g0;
+            // this lane's output element of the group and its normalisation, fetched ahead of the arithmetic that hides the latency
+            const bool mine = (lane % G) < gcnt;
+            const long long gk = abase + lstart + t0 + (lane % G);
+            const double g = mine ? P.gamma[gk] : 0.0;
             if (t0 >= nmixed && gcnt == G) {
                 // fast path: every live ring is active for the whole group -> straight-line code
 #pragma unroll
@@ -569,47 +603,24 @@ __global__ void __launch_bounds__(LEG_NT) leg_anal(const LegParams P)
                 }
             }
             __syncwarp();
-            // transpose-reduce: lane -> (step lq = lane % G, source slice = lane / G of 32/G slices)
             {
-                constexpr int NSL = 32 / G, SL = 32 / NSL;
-                const int lq = lane % G, slice = lane / G;
-                double t[NPART], t2[NPART];
-#pragma unroll
-                for (int k = 0; k < NPART; ++k) { t[k] = 0.0; t2[k] = 0.0; }
-                const bool mine = lq < gcnt;
-                if (mine) {
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-#pragma unroll
-                        for (int k = 0; k < SL; k += 2) {
-                            const double2 q = red[(v * G + lq) * 33 + slice * SL + k];
-                            const double2 q2 = red[(v * G + lq) * 33 + slice * SL + k + 1];
-                            t[2 * v] += q.x; t[2 * v + 1] += q.y;
-                            t2[2 * v] += q2.x; t2[2 * v + 1] += q2.y;
-                        }
+                const double2 t = red_sum<NV, G>(red, lane);
+                if (SPIN == 0) {
+                    if (mine && lane < M::ROWS) {
+                        atomicAdd(&P.alm_out0[gk].x, g * t.x);
+                        if (m != 0) atomicAdd(&P.alm_out0[gk].y, g * t.y);
                     }
-                }
-#pragma unroll
-                for (int k = 0; k < NPART; ++k) t[k] += t2[k];
-#pragma unroll
-                for (int off = G; off < 32; off <<= 1)
-#pragma unroll
-                    for (int q = 0; q < NPART; ++q) t[q] += __shfl_xor_sync(0xffffffffu, t[q], off);
-                if (slice == 0 && mine) {
-                    const long long k = abase + lstart + t0 + lq;
-                    const double g = P.gamma[k];
-                    if (SPIN == 0) {
-                        if (t[0] != 0.0) atomicAdd(&P.alm_out0[k].x, g * t[0]);
-                        if (t[1] != 0.0 && m != 0) atomicAdd(&P.alm_out0[k].y, g * t[1]);
-                    } else {
-                        // E = -(a+ + a-)/2 ; B = i (a+ - a-)/2
-                        const double h = 0.5 * g;
-                        const double er = -h * (t[0] + t[NPART - 2]), ei = -h * (t[1] + t[NPART - 1]);
-                        const double br = -h * (t[1] - t[NPART - 1]), bi = h * (t[0] - t[NPART - 2]);
-                        if (er != 0.0) atomicAdd(&P.alm_out0[k].x, er);
-                        if (ei != 0.0 && m != 0) atomicAdd(&P.alm_out0[k].y, ei);
-                        if (br != 0.0) atomicAdd(&P.alm_out1[k].x, br);
-                        if (bi != 0.0 && m != 0) atomicAdd(&P.alm_out1[k].y, bi);
+                } else {
+                    // row v = 0 holds a+, v = 1 holds a-:  E = -(a+ + a-)/2 ; B = i (a+ - a-)/2.  The v = 0 lane of a step writes E, the v = 1 lane B.
+                    const double ox = __shfl_xor_sync(0xffffffffu, t.x, G), oy = __shfl_xor_sync(0xffffffffu, t.y, G);
+                    // g enters last: a product of g alone would be hoisted to the prefetch and stall on it
+                    const bool isB = lane >= G;
+                    const double re = 0.5 * ((isB ? (t.y - oy) : -(t.x + ox)) * g);
+                    const double im = 0.5 * ((isB ? (ox - t.x) : -(t.y + oy)) * g);
+                    if (mine) {
+                        double2* out = (isB ? P.alm_out1 : P.alm_out0) + gk;
+                        atomicAdd(&out->x, re);
+                        if (m != 0) atomicAdd(&out->y, im);
                     }
                 }
                 __syncwarp();

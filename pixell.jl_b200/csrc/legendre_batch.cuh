@@ -10,7 +10,7 @@ namespace pixsht {
 
 constexpr int LEG_MAXBATCH = 4;
 template <int NB> struct BatchRec { static constexpr int ND = 2 + 2 * NB; static constexpr int STEPS = 64; };   // { alpha, 0, (gamma a_b).re, .im ... }
-template <int NB> struct BatchRed { static constexpr int G = 8; };   // l-steps per reduction group (NB double2 values per l)
+template <int NB> struct BatchRed { static constexpr int G = 32 / NB; };   // l-steps per reduction group: NB double2 values per l, one (map, step) row per lane
 
 struct BatchPtrs { const double2* in[LEG_MAXBATCH]; double2* out[LEG_MAXBATCH]; };
 
@@ -182,6 +182,9 @@ __global__ void __launch_bounds__(LEG_NT) leg_anal_b(const LegParams P, const Ba
     if (lane == 0) { mbar_init(&sbar[0], 1); mbar_init(&sbar[1], 1); mbar_init_fence(); }
     __syncwarp();
     const long long abase = alm_index(P.lmax, 0, m);
+    double2* outb = A.out[0];   // the map this lane reduces into (lane = (map, step) in the reduction)
+#pragma unroll
+    for (int b = 1; b < NB; ++b) if (lane / G == b) outb = A.out[b];
     RecStream<2, STEPS> rs;
     rs.src = reinterpret_cast<const double*>(P.ad + abase + lstart); rs.nrec = nl; rs.buf = sbuf; rs.bar = sbar;
     const int nchunk = (nl + STEPS - 1) / STEPS;
@@ -193,6 +196,9 @@ __global__ void __launch_bounds__(LEG_NT) leg_anal_b(const LegParams P, const Ba
         for (int g0 = 0; g0 < cnt; g0 += G) {
             int gcnt = cnt - g0; if (gcnt > G) gcnt = G;
             const int t0 = c * STEPS + g0;
+            const bool mine = (lane % G) < gcnt;
+            const long long gk = abase + lstart + t0 + (lane % G);
+            const double g = mine ? P.gamma[gk] : 0.0;
             if (t0 >= nmixed && gcnt == G) {
 #pragma unroll
                 for (int s = 0; s < G; s += 2) {
@@ -226,34 +232,11 @@ __global__ void __launch_bounds__(LEG_NT) leg_anal_b(const LegParams P, const Ba
             }
             __syncwarp();
             {
-                constexpr int NSL = 32 / G, SL = 32 / NSL;
-                const int lq = lane % G, slice = lane / G;
-                double t[NPART];
-#pragma unroll
-                for (int k = 0; k < NPART; ++k) t[k] = 0.0;
-                const bool mine = lq < gcnt;
+                const double2 t = red_sum<NV, G>(red, lane);   // lane = (map b = lane / G, step lane % G)
                 if (mine) {
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-#pragma unroll
-                        for (int k = 0; k < SL; ++k) {
-                            const double2 q = red[(v * G + lq) * 33 + slice * SL + k];
-                            t[2 * v] += q.x; t[2 * v + 1] += q.y;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int off = G; off < 32; off <<= 1)
-#pragma unroll
-                    for (int q = 0; q < NPART; ++q) t[q] += __shfl_xor_sync(0xffffffffu, t[q], off);
-                if (slice == 0 && mine) {
-                    const long long k = abase + lstart + t0 + lq;
-                    const double g = P.gamma[k];
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) {
-                        if (t[2 * b] != 0.0) atomicAdd(&A.out[b][k].x, g * t[2 * b]);
-                        if (t[2 * b + 1] != 0.0 && m != 0) atomicAdd(&A.out[b][k].y, g * t[2 * b + 1]);
-                    }
+                    double2* out = outb + gk;
+                    atomicAdd(&out->x, g * t.x);
+                    if (m != 0) atomicAdd(&out->y, g * t.y);
                 }
                 __syncwarp();
             }

@@ -965,7 +965,10 @@ extern "C" int pixsht_execute(pixsht_plan* P, int direction, int ncomp, void* co
 template <int NB>
 static int batch_group(pixsht_plan* P, int direction, double2* const* alm64, void* const* dmap, cudaStream_t st)
 {
-    constexpr int R = (NB == 4) ? 2 : 4;
+    // ring pairs per thread: synthesis keeps 4 NB accumulators per ring (R = 2 at NB = 4); analysis wants many rings per
+    // lane because its per-step cross-lane reduction grows with NB
+    constexpr int RS = (NB == 4) ? 2 : 4, RA = 4;
+    const int R = direction == PIXSHT_ALM2MAP ? RS : RA;
     const int prep_grid = P->sm_count > 0 ? P->sm_count * 8 : 256;
     int rc = ensure_seek(P, 0, st); if (rc) return rc;
     const LegJob J = {0, NB, 0, 0, P->mmax + 1, nullptr, 0, leg_total_chunks(P, R), {P->d_phase.p, 0, 0}};
@@ -979,14 +982,14 @@ static int batch_group(pixsht_plan* P, int direction, double2* const* alm64, voi
         if (P->d_rec0.n < need && P->d_rec0.alloc(need)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
         L.rec = P->d_rec0.p;
         PIXSHT_LAUNCH((k_prep_synth_b<NB>), prep_grid, 256, 0, st, 0LL, (long long)P->nalm, P->lmax, P->d_ad0.p, P->d_gamma0.p, A, P->d_rec0.p);
-        PIXSHT_LAUNCH((leg_synth_b<R, NB>), grid, LEG_NT, 0, st, L);
+        PIXSHT_LAUNCH((leg_synth_b<RS, NB>), grid, LEG_NT, 0, st, L);
         P->launches += 2;
         CU(cudaGetLastError());
         return stage_fft(P, PIXSHT_ALM2MAP, NB, 0, NB, P->d_phase.p, 0, P->nrings, dmap, st);
     }
     rc = stage_fft(P, PIXSHT_MAP2ALM, NB, 0, NB, P->d_phase.p, 0, P->nrings, dmap, st); if (rc) return rc;
     for (int b = 0; b < NB; ++b) CU(cudaMemsetAsync(alm64[b], 0, (size_t)P->nalm * sizeof(double2), st));
-    PIXSHT_LAUNCH((leg_anal_b<R, NB>), grid, LEG_NT, 0, st, L, A);
+    PIXSHT_LAUNCH((leg_anal_b<RA, NB>), grid, LEG_NT, 0, st, L, A);
     P->launches++;
     CU(cudaGetLastError());
     return PIXSHT_OK;

@@ -1,4 +1,4 @@
-python -m pytest tests -m gpu -x -q -k "multi_gpu" 2>&1 | tail -2
-for n in 8 4 2; do python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 3 --warmup 3 > gpurun_out/bench_c4_n$n.log 2>&1; tail -1 gpurun_out/bench_c4_n$n.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['n_gpus'], d['value'], d['stages']['legendre_ms'], d['stages']['fft_ms'], d['stages']['exchange_ms'], d['e2e']['value'])" || tail -5 gpurun_out/bench_c4_n$n.log; done
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29520 bench.py --gpus 8 --workload C3 --steps 3 --warmup 3 > gpurun_out/bench_c3_n8.log 2>&1; tail -1 gpurun_out/bench_c3_n8.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('C3', d['n_gpus'], d['value'], d['stages']['legendre_ms'], d['stages']['fft_ms'])"
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --impl reference --steps 1 --warmup 0 2>&1 | tail -1 | cut -c1-300
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "not size" 2>&1 | tail -2
+python bench.py --workload C4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c4_new.log 2>&1
+tail -1 gpurun_out/bench_c4_new.log | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value']); print([(k['kernel'], round(k['ms'],1), round(k['fp64_pipe_utilisation'],3)) for k in d['roofline']['kernels']])"

@@ -42,6 +42,9 @@ enum { PIXSHT_RINGS_CC = 0, PIXSHT_RINGS_FEJER1 = 1 };  /* ring scheme of pixsht
 /* How the caller's (nx, ny) map sits on the full-sky ring grid. */
 typedef struct pixsht_geom {
     int32_t nphi;          /* pixels of a full ring           = fullringsize(wcs)   (src/transforms.jl:3-4)   */
+                           /* any length libsharp2 takes: even or odd, any prime factors (2/3/5-smooth even lengths whose
+                              nphi/2 complex samples fit 227 KB of shared memory take the fast path; the rest use global
+                              work buffers); limit nphi <= 131070 (even) / 65535 (odd) -> PIXSHT_ERR_UNSUPPORTED      */
     int32_t nrings_total;  /* rings of the full-sky grid      = fullringnum(wcs)    (src/transforms.jl:7-8)   */
     int32_t ring_first;    /* 0-based full-sky index of the band's first ring, rings ascending in theta (:11-22) */
     int32_t nrings;        /* rings in the map (= ny)                                                            */

@@ -24,11 +24,16 @@
 namespace pixsht {
 
 constexpr int FFT_MAXFAC = 24;
-constexpr int FFT_MAXRADIX = 64;
+constexpr int FFT_MAXRADIX = 64;       // largest radix done in registers / local memory; larger primes take pass_direct
 constexpr int FFT_MAXTHREADS = 640;
 
 struct FftParams {
-    int nphi, n;                // ring length, complex FFT length (nphi/2)
+    int nphi, n;                // ring length, complex FFT length: nphi/2 (even nphi, two real samples per complex), else nphi
+    int packed;                 // 1: even nphi, real ring packed into n = nphi/2 complex samples; 0: odd nphi, n = nphi, imaginary part zero
+    int pt;                     // entries per pass table (128 lo + hi), FFT_PT unless the work buffer is in global memory
+    void* gbuf;                 // nullptr: the ring lives in shared memory.  Else per-CTA work buffers in global memory (L2-resident):
+    long long gslot;            //   rings too long for shared memory, or a prime factor > FFT_MAXRADIX; gslot entries per buffer,
+    int galt;                   //   galt = 1: two buffers per CTA (pass_direct works out of place)
     int nfac;
     int fac[FFT_MAXFAC];        // radices in DIT pass order (pass t works on sub-transforms of length L_t = prod_{u<t} fac[u])
     unsigned magic[FFT_MAXFAC]; // floor(2^32 / L_t) + 1: b / L_t == umulhi(b, magic) for b < 2^16
@@ -354,8 +359,9 @@ template <class T>
 __device__ __forceinline__ void superpass_tables(const FftParams& P, cpx<T>* tabs, int sp, int L)
 {
     const int t = P.sp_first[sp], q1 = P.fac[t];
+    if (q1 > 5) return;   // generic radices take their twiddles from the two-level root table
     pass_table_build<T>(P, tabs, L, P.nphi / (q1 * L));
-    if (P.sp_count[sp] == 2) pass_table_build<T>(P, tabs + FFT_PT, L, P.nphi / (q1 * P.fac[t + 1] * L));
+    if (P.sp_count[sp] == 2) pass_table_build<T>(P, tabs + P.pt, L, P.nphi / (q1 * P.fac[t + 1] * L));
 }
 // sub-length L at which super-pass sp works (product of the radices before it)
 __device__ __forceinline__ int superpass_L(const FftParams& P, int sp)
@@ -365,11 +371,38 @@ __device__ __forceinline__ int superpass_L(const FftParams& P, int sp)
     return L;
 }
 
-// in-place mixed-radix passes over buf[0..n).  DIF == false: digit-reversed input -> natural output (super-passes in order);
-// DIF == true: natural input -> digit-reversed output (super-passes in reverse order).  SIGN = -1 forward.
+// One radix-q pass for a large prime q, computed directly (O(n q) per ring) and out of place:
+//   DIT: out(g,u,kk) = sum_j in(g,j,kk) W_{qL}^{j kk} W_q^{j u};   DIF: out(g,u,kk) = W_{qL}^{u kk} sum_j in(g,j,kk) W_q^{j u}
+// with element (g, j, kk) at (g q + j) L + kk.  One thread per output element.
+template <class T, int SIGN, bool DIF>
+__device__ void pass_direct(const FftParams& P, const TwTab<T>& W, const cpx<T>* src, cpx<T>* dst, int q, int L, unsigned magic)
+{
+    const int N = P.nphi;
+    const int tstep = N / (q * L), qstep = N / q;
+    for (int o = threadIdx.x; o < P.n; o += blockDim.x) {
+        const int gu = (L == 1) ? o : (int)__umulhi((unsigned)o, magic);
+        const int kk = o - gu * L;
+        const int g = gu / q, u = gu - g * q;
+        int s = u * qstep + (DIF ? 0 : kk * tstep);   // exponent step per input, < 2 N
+        if (s >= N) s -= N;
+        const cpx<T>* in = src + (size_t)g * q * L + kk;
+        cpx<T> acc = in[0];
+        int e = 0;
+        for (int j = 1; j < q; ++j) {
+            e += s; if (e >= N) e -= N;
+            acc = cadd(acc, cmul(in[(size_t)j * L], twid<T, SIGN>(W, e)));
+        }
+        if (DIF && kk && u) acc = cmul(acc, twid<T, SIGN>(W, u * kk * tstep));
+        dst[o] = acc;
+    }
+}
+
+// mixed-radix passes over buf[0..n), in place except for pass_direct (which alternates between buf and alt).
+// DIF == false: digit-reversed input -> natural output (super-passes in order); DIF == true: natural input -> digit-reversed
+// output (super-passes in reverse order).  SIGN = -1 forward.  Returns the buffer that holds the result.
 // ptabs: 2 x 2 pass tables, double buffered; the tables of the FIRST super-pass were built by the caller before its last barrier.
 template <class T, int SIGN, bool DIF>
-__device__ void fft_passes(const FftParams& P, const TwTab<T>& W, cpx<T>* buf, cpx<T>* ptabs)
+__device__ cpx<T>* fft_passes(const FftParams& P, const TwTab<T>& W, cpx<T>* buf, cpx<T>* alt, cpx<T>* ptabs)
 {
     const int n = P.n;
     for (int ss = 0; ss < P.nsp; ++ss) {
@@ -377,33 +410,55 @@ __device__ void fft_passes(const FftParams& P, const TwTab<T>& W, cpx<T>* buf, c
         const int t = P.sp_first[sp], q1 = P.fac[t];
         const int L = superpass_L(P, sp);
         const unsigned magic = P.magic[t];
-        const cpx<T>* cur = ptabs + (ss & 1) * 2 * FFT_PT;
+        const cpx<T>* cur = ptabs + (ss & 1) * 2 * P.pt;
         if (ss + 1 < P.nsp) {   // next super-pass's tables (read only after the barrier below)
             const int sp2 = DIF ? (sp - 1) : (sp + 1);
-            superpass_tables<T>(P, ptabs + ((ss + 1) & 1) * 2 * FFT_PT, sp2, superpass_L(P, sp2));
+            superpass_tables<T>(P, ptabs + ((ss + 1) & 1) * 2 * P.pt, sp2, superpass_L(P, sp2));
         }
         if (P.sp_count[sp] == 2) {
             const int q2 = P.fac[t + 1], nb = n / (q1 * q2);
-            if (q1 == 2) pass2_dispatch<T, SIGN, 2, DIF>(q2, cur, cur + FFT_PT, buf, L, nb, magic);
-            else if (q1 == 3) pass2_dispatch<T, SIGN, 3, DIF>(q2, cur, cur + FFT_PT, buf, L, nb, magic);
-            else if (q1 == 4) pass2_dispatch<T, SIGN, 4, DIF>(q2, cur, cur + FFT_PT, buf, L, nb, magic);
-            else pass2_dispatch<T, SIGN, 5, DIF>(q2, cur, cur + FFT_PT, buf, L, nb, magic);
+            if (q1 == 2) pass2_dispatch<T, SIGN, 2, DIF>(q2, cur, cur + P.pt, buf, L, nb, magic);
+            else if (q1 == 3) pass2_dispatch<T, SIGN, 3, DIF>(q2, cur, cur + P.pt, buf, L, nb, magic);
+            else if (q1 == 4) pass2_dispatch<T, SIGN, 4, DIF>(q2, cur, cur + P.pt, buf, L, nb, magic);
+            else pass2_dispatch<T, SIGN, 5, DIF>(q2, cur, cur + P.pt, buf, L, nb, magic);
         } else {
             const int nb = n / q1;
             if (q1 == 4) pass_loop<T, SIGN, 4, DIF>(cur, buf, L, nb, magic);
             else if (q1 == 3) pass_loop<T, SIGN, 3, DIF>(cur, buf, L, nb, magic);
             else if (q1 == 5) pass_loop<T, SIGN, 5, DIF>(cur, buf, L, nb, magic);
             else if (q1 == 2) pass_loop<T, SIGN, 2, DIF>(cur, buf, L, nb, magic);
-            else {
+            else if (q1 <= FFT_MAXRADIX) {
                 const int tstep = P.nphi / (q1 * L);   // W_{qL}^{a} = tw[a * tstep]
                 for (int b = threadIdx.x; b < nb; b += blockDim.x) {
                     const int g = (L == 1) ? b : (int)__umulhi((unsigned)b, magic);
                     const int kk = b - g * L;
                     butterfly_generic<T, SIGN, DIF>(P, W, buf + (size_t)g * q1 * L + kk, q1, L, kk * tstep);
                 }
+            } else {
+                pass_direct<T, SIGN, DIF>(P, W, buf, alt, q1, L, magic);
+                cpx<T>* sw = buf; buf = alt; alt = sw;
             }
         }
         __syncthreads();
+    }
+    return buf;
+}
+
+// work buffers of this CTA: shared memory (ring + tables; GLOBAL == false keeps the pointers provably shared so that the passes
+// compile to LDS/STS), or a global-memory slot with the tables alone in shared memory
+template <class T, bool GLOBAL>
+__device__ __forceinline__ void fft_buffers(const FftParams& P, unsigned char* smem_raw, cpx<T>*& buf, cpx<T>*& alt, cpx<T>*& tabs)
+{
+    cpx<T>* sm = reinterpret_cast<cpx<T>*>(smem_raw);
+    alt = nullptr;
+    if (GLOBAL) {
+        const long long slot = (long long)blockIdx.y * gridDim.x + blockIdx.x;
+        buf = reinterpret_cast<cpx<T>*>(P.gbuf) + slot * P.gslot * (P.galt ? 2 : 1);
+        if (P.galt) alt = buf + P.gslot;
+        tabs = sm;
+    } else {
+        buf = sm;
+        tabs = sm + P.n + 1;
     }
 }
 
@@ -465,150 +520,186 @@ __device__ __forceinline__ void store_pair(const FftParams& P, T* orow, int j, c
 }
 constexpr int FFT_IO_UNROLL = 4;   // independent global accesses in flight per thread in the load / store loops
 
-// phase -> map  (synthesis).  grid = (ring_count, ncomp)
-template <class T>
+// phase -> map  (synthesis).  grid = (rows, ncomp): CTA x handles band rings ring_begin + x, x + gridDim.x, ...
+template <class T, bool GLOBAL>
 __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams P)
 {
     PIXSHT_DYN_SMEM(smem_raw);
-    cpx<T>* buf = reinterpret_cast<cpx<T>*>(smem_raw);   // n + 1 entries, then the twiddle tables
-    const TwTab<T> W = tw_setup<T>(P, buf + P.n + 1);
-    cpx<T>* ptabs = buf + P.n + 1 + fft_tw_entries(P.nphi);   // 2 x 2 x FFT_PT pass tables
-    const int rl = blockIdx.x, c = P.c_begin + blockIdx.y, ring = P.ring_begin + rl;
-    const int n = P.n;
-    double2* row = P.phase + ((long long)rl * P.ncomp + c) * P.MP;
-
-    // X[k], k = 0..n, natural order (coalesced row read)
-    if (P.mmax <= n) {
-        for (int k0 = threadIdx.x; k0 <= n; k0 += FFT_IO_UNROLL * blockDim.x) {
-            double2 a[FFT_IO_UNROLL], r[FFT_IO_UNROLL];
-#pragma unroll
-            for (int u = 0; u < FFT_IO_UNROLL; ++u) {
-                const int k = k0 + u * blockDim.x;
-                a[u] = make_double2(0.0, 0.0); r[u] = a[u];
-                if (k <= P.mmax) { a[u] = *phase_elem(P, row, ring, c, k); r[u] = P.phi0tw[k]; }
-            }
-#pragma unroll
-            for (int u = 0; u < FFT_IO_UNROLL; ++u) {
-                const int k = k0 + u * blockDim.x;
-                if (k > n) break;
-                const double sx = a[u].x * r[u].x - a[u].y * r[u].y, sy = a[u].x * r[u].y + a[u].y * r[u].x;
-                cpx<T> v;
-                if (k == n) { v.x = (T)(2.0 * sx); v.y = (T)0; }          // m = nphi/2: the ring carries only the (doubled) real part
-                else { v.x = (T)sx; v.y = (T)sy; }
-                buf[k] = v;
-            }
-        }
-    } else {
-        for (int k = threadIdx.x; k <= n; k += blockDim.x) buf[k] = load_X<T>(P, row, ring, c, k);
-    }
-    __syncthreads();
-
-    // pre-processing in place: Z[k] = (X[k] + conj X[n-k]) + i (X[k] - conj X[n-k]) e^{+2 pi i k/nphi}
-    for (int k = threadIdx.x; k <= n / 2; k += blockDim.x) {
-        if (k == 0) {
-            const cpx<T> x0 = buf[0], xn = buf[n];
-            cpx<T> z; z.x = x0.x + xn.x; z.y = x0.x - xn.x;
-            buf[0] = z;
-        } else {
-            const cpx<T> xa = buf[k], xb = buf[n - k];
-            const cpx<T> wa = twid<T, +1>(W, k);
-            const cpx<T> ea = cadd(xa, cconj(xb)), oa = cmul(csub(xa, cconj(xb)), wa);
-            if (k != n - k) {
-                const cpx<T> wb = twid<T, +1>(W, n - k);
-                const cpx<T> eb = cadd(xb, cconj(xa)), ob = cmul(csub(xb, cconj(xa)), wb);
-                buf[n - k] = cadd(eb, cmuli<T, +1>(ob));
-            }
-            buf[k] = cadd(ea, cmuli<T, +1>(oa));
-        }
-    }
-    superpass_tables<T>(P, ptabs, P.nsp - 1, superpass_L(P, P.nsp - 1));
-    __syncthreads();
-    fft_passes<T, +1, true>(P, W, buf, ptabs);
-
-    // store x[2j] = Re z[j], x[2j+1] = Im z[j] into the caller's array (flips / partial rings by index arithmetic)
+    cpx<T>*buf, *alt, *tabs;
+    fft_buffers<T, GLOBAL>(P, smem_raw, buf, alt, tabs);   // buf: n + 1 entries
+    const TwTab<T> W = tw_setup<T>(P, tabs);
+    cpx<T>* ptabs = tabs + fft_tw_entries(P.nphi);   // 2 x 2 pass tables
+    const int c = P.c_begin + blockIdx.y;
+    const int n = P.n, N = P.nphi;
     T* out = reinterpret_cast<T*>(P.maps[c]);
-    const int rowy = P.flipy ? (P.ny - 1 - ring) : ring;
-    T* orow = out + (size_t)rowy * P.nx;
-    const bool vec = (P.nx == P.nphi);
-    for (int j0 = threadIdx.x; j0 < n; j0 += FFT_IO_UNROLL * blockDim.x) {
-        int pj[FFT_IO_UNROLL];
+    const bool vec = (P.nx == P.nphi) && P.packed;
+
+    for (int rl = blockIdx.x; rl < P.ring_count; rl += gridDim.x) {
+        const int ring = P.ring_begin + rl;
+        double2* row = P.phase + ((long long)rl * P.ncomp + c) * P.MP;
+        if (P.packed) {
+            // X[k], k = 0..n, natural order (coalesced row read)
+            if (P.mmax <= n) {
+                for (int k0 = threadIdx.x; k0 <= n; k0 += FFT_IO_UNROLL * blockDim.x) {
+                    double2 a[FFT_IO_UNROLL], r[FFT_IO_UNROLL];
 #pragma unroll
-        for (int u = 0; u < FFT_IO_UNROLL; ++u) { const int j = j0 + u * blockDim.x; pj[u] = (j < n) ? (int)P.perm[j] : 0; }
+                    for (int u = 0; u < FFT_IO_UNROLL; ++u) {
+                        const int k = k0 + u * blockDim.x;
+                        a[u] = make_double2(0.0, 0.0); r[u] = a[u];
+                        if (k <= P.mmax) { a[u] = *phase_elem(P, row, ring, c, k); r[u] = P.phi0tw[k]; }
+                    }
 #pragma unroll
-        for (int u = 0; u < FFT_IO_UNROLL; ++u) {
-            const int j = j0 + u * blockDim.x;
-            if (j < n) store_pair<T>(P, orow, j, buf[pj[u]], vec);
+                    for (int u = 0; u < FFT_IO_UNROLL; ++u) {
+                        const int k = k0 + u * blockDim.x;
+                        if (k > n) break;
+                        const double sx = a[u].x * r[u].x - a[u].y * r[u].y, sy = a[u].x * r[u].y + a[u].y * r[u].x;
+                        cpx<T> v;
+                        if (k == n) { v.x = (T)(2.0 * sx); v.y = (T)0; }          // m = nphi/2: the ring carries only the (doubled) real part
+                        else { v.x = (T)sx; v.y = (T)sy; }
+                        buf[k] = v;
+                    }
+                }
+            } else {
+                for (int k = threadIdx.x; k <= n; k += blockDim.x) buf[k] = load_X<T>(P, row, ring, c, k);
+            }
+            __syncthreads();
+
+            // pre-processing in place: Z[k] = (X[k] + conj X[n-k]) + i (X[k] - conj X[n-k]) e^{+2 pi i k/nphi}
+            for (int k = threadIdx.x; k <= n / 2; k += blockDim.x) {
+                if (k == 0) {
+                    const cpx<T> x0 = buf[0], xn = buf[n];
+                    cpx<T> z; z.x = x0.x + xn.x; z.y = x0.x - xn.x;
+                    buf[0] = z;
+                } else {
+                    const cpx<T> xa = buf[k], xb = buf[n - k];
+                    const cpx<T> wa = twid<T, +1>(W, k);
+                    const cpx<T> ea = cadd(xa, cconj(xb)), oa = cmul(csub(xa, cconj(xb)), wa);
+                    if (k != n - k) {
+                        const cpx<T> wb = twid<T, +1>(W, n - k);
+                        const cpx<T> eb = cadd(xb, cconj(xa)), ob = cmul(csub(xb, cconj(xa)), wb);
+                        buf[n - k] = cadd(eb, cmuli<T, +1>(ob));
+                    }
+                    buf[k] = cadd(ea, cmuli<T, +1>(oa));
+                }
+            }
+        } else {
+            // odd ring length: the full Hermitian spectrum Z[k] = X[k], Z[N-k] = conj X[k] of the real ring
+            for (int k = threadIdx.x; k <= N / 2; k += blockDim.x) {
+                cpx<T> x = load_X<T>(P, row, ring, c, k);
+                if (k == 0) { x.y = (T)0; buf[0] = x; }
+                else { buf[k] = x; buf[N - k] = cconj(x); }
+            }
         }
+        superpass_tables<T>(P, ptabs, P.nsp - 1, superpass_L(P, P.nsp - 1));
+        __syncthreads();
+        const cpx<T>* res = fft_passes<T, +1, true>(P, W, buf, alt, ptabs);
+        if (!GLOBAL) res = buf;   // no out-of-place pass without the global buffers: keeps the pointer provably shared
+
+        // store into the caller's array (flips / partial rings by index arithmetic): packed x[2j] = Re z[j], x[2j+1] = Im z[j]
+        const int rowy = P.flipy ? (P.ny - 1 - ring) : ring;
+        T* orow = out + (size_t)rowy * P.nx;
+        if (P.packed) {
+            for (int j0 = threadIdx.x; j0 < n; j0 += FFT_IO_UNROLL * blockDim.x) {
+                int pj[FFT_IO_UNROLL];
+#pragma unroll
+                for (int u = 0; u < FFT_IO_UNROLL; ++u) { const int j = j0 + u * blockDim.x; pj[u] = (j < n) ? (int)P.perm[j] : 0; }
+#pragma unroll
+                for (int u = 0; u < FFT_IO_UNROLL; ++u) {
+                    const int j = j0 + u * blockDim.x;
+                    if (j < n) store_pair<T>(P, orow, j, res[pj[u]], vec);
+                }
+            }
+        } else {
+            for (int j = threadIdx.x; j < P.nx; j += blockDim.x) orow[P.flipx ? (P.nx - 1 - j) : j] = res[P.perm[j]].x;
+        }
+        __syncthreads();   // the buffer is reused by this CTA's next ring
     }
 }
 
-// map -> weighted phase  (analysis).  grid = (ring_count, ncomp)
-template <class T>
+// map -> weighted phase  (analysis).  grid as above
+template <class T, bool GLOBAL>
 __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams P)
 {
     PIXSHT_DYN_SMEM(smem_raw);
-    cpx<T>* buf = reinterpret_cast<cpx<T>*>(smem_raw);   // n + 1 entries, then the twiddle tables
-    const TwTab<T> W = tw_setup<T>(P, buf + P.n + 1);
-    cpx<T>* ptabs = buf + P.n + 1 + fft_tw_entries(P.nphi);   // 2 x 2 x FFT_PT pass tables
-    const int rl = blockIdx.x, c = P.c_begin + blockIdx.y, ring = P.ring_begin + rl;
+    cpx<T>*buf, *alt, *tabs;
+    fft_buffers<T, GLOBAL>(P, smem_raw, buf, alt, tabs);   // buf: n + 1 entries
+    const TwTab<T> W = tw_setup<T>(P, tabs);
+    cpx<T>* ptabs = tabs + fft_tw_entries(P.nphi);   // 2 x 2 pass tables
+    const int c = P.c_begin + blockIdx.y;
     const int n = P.n, N = P.nphi;
     const T* in = reinterpret_cast<const T*>(P.maps[c]);
-    const int rowy = P.flipy ? (P.ny - 1 - ring) : ring;
-    const T* irow = in + (size_t)rowy * P.nx;
-    const bool vec = (P.nx == P.nphi);
-    for (int j0 = threadIdx.x; j0 < n; j0 += FFT_IO_UNROLL * blockDim.x) {
-        cpx<T> z[FFT_IO_UNROLL]; int pj[FFT_IO_UNROLL];
-#pragma unroll
-        for (int u = 0; u < FFT_IO_UNROLL; ++u) {
-            const int j = j0 + u * blockDim.x;
-            pj[u] = 0; z[u].x = (T)0; z[u].y = (T)0;
-            if (j < n) { pj[u] = (int)P.perm[j]; z[u] = load_pair<T>(P, irow, j, vec); }
-        }
-#pragma unroll
-        for (int u = 0; u < FFT_IO_UNROLL; ++u) if ((int)(j0 + u * blockDim.x) < n) buf[pj[u]] = z[u];
-    }
-    superpass_tables<T>(P, ptabs, 0, 1);
-    __syncthreads();
-    fft_passes<T, -1, false>(P, W, buf, ptabs);
+    const bool vec = (P.nx == P.nphi) && P.packed;
 
-    // post-processing in place: F[k] = ((Z[k] + conj Z[n-k]) - i e^{-2 pi i k/N} (Z[k] - conj Z[n-k])) / 2,  k = 0..n
-    for (int k = threadIdx.x; k <= n / 2; k += blockDim.x) {
-        if (k == 0) {
-            const cpx<T> z0 = buf[0];
-            cpx<T> f0, fn; f0.x = z0.x + z0.y; f0.y = 0; fn.x = z0.x - z0.y; fn.y = 0;
-            buf[0] = f0; buf[n] = fn;
-        } else {
-            const cpx<T> za = buf[k], zb = buf[n - k];
-            const cpx<T> ea = cadd(za, cconj(zb)), oa = cmul(csub(za, cconj(zb)), twid<T, -1>(W, k));
-            const cpx<T> fa = cadd(ea, cmuli<T, -1>(oa));
-            cpx<T> r; r.x = (T)0.5 * fa.x; r.y = (T)0.5 * fa.y;
-            if (k != n - k) {
-                const cpx<T> eb = cadd(zb, cconj(za)), ob = cmul(csub(zb, cconj(za)), twid<T, -1>(W, n - k));
-                const cpx<T> fb = cadd(eb, cmuli<T, -1>(ob));
-                cpx<T> rb; rb.x = (T)0.5 * fb.x; rb.y = (T)0.5 * fb.y;
-                buf[n - k] = rb;
+    for (int rl = blockIdx.x; rl < P.ring_count; rl += gridDim.x) {
+        const int ring = P.ring_begin + rl;
+        const int rowy = P.flipy ? (P.ny - 1 - ring) : ring;
+        const T* irow = in + (size_t)rowy * P.nx;
+        if (P.packed) {
+            for (int j0 = threadIdx.x; j0 < n; j0 += FFT_IO_UNROLL * blockDim.x) {
+                cpx<T> z[FFT_IO_UNROLL]; int pj[FFT_IO_UNROLL];
+#pragma unroll
+                for (int u = 0; u < FFT_IO_UNROLL; ++u) {
+                    const int j = j0 + u * blockDim.x;
+                    pj[u] = 0; z[u].x = (T)0; z[u].y = (T)0;
+                    if (j < n) { pj[u] = (int)P.perm[j]; z[u] = load_pair<T>(P, irow, j, vec); }
+                }
+#pragma unroll
+                for (int u = 0; u < FFT_IO_UNROLL; ++u) if ((int)(j0 + u * blockDim.x) < n) buf[pj[u]] = z[u];
             }
-            buf[k] = r;
+        } else {
+            for (int j = threadIdx.x; j < N; j += blockDim.x) {
+                cpx<T> z; z.y = (T)0;
+                z.x = (j < P.nx) ? irow[P.flipx ? (P.nx - 1 - j) : j] : (T)0;
+                buf[P.perm[j]] = z;
+            }
         }
-    }
-    __syncthreads();
+        superpass_tables<T>(P, ptabs, 0, 1);
+        __syncthreads();
+        cpx<T>* res = fft_passes<T, -1, false>(P, W, buf, alt, ptabs);
+        if (!GLOBAL) res = buf;   // no out-of-place pass without the global buffers: keeps the pointer provably shared
 
-    // phase_m = w * e^{-i m phi0} * F[m mod N]  (conjugate symmetric upper half); coalesced row write
-    const double w = P.wgt[ring];
-    double2* row = P.phase + ((long long)rl * P.ncomp + c) * P.MP;
-    for (int m0 = threadIdx.x; m0 <= P.mmax; m0 += FFT_IO_UNROLL * blockDim.x) {
-        double2 r[FFT_IO_UNROLL];
-#pragma unroll
-        for (int u = 0; u < FFT_IO_UNROLL; ++u) { const int m = m0 + u * blockDim.x; r[u] = (m <= P.mmax) ? P.phi0tw[m] : make_double2(0.0, 0.0); }
-#pragma unroll
-        for (int u = 0; u < FFT_IO_UNROLL; ++u) {
-            const int m = m0 + u * blockDim.x;
-            if (m > P.mmax) break;
-            const int kk = (m < N) ? m : (m % N);
-            const cpx<T> f = (kk <= n) ? buf[kk] : cconj(buf[N - kk]);
-            const double fx = (double)f.x, fy = (double)f.y;
-            *phase_elem(P, row, ring, c, m) = make_double2(w * (fx * r[u].x + fy * r[u].y), w * (fy * r[u].x - fx * r[u].y));
+        if (P.packed) {
+            // post-processing in place: F[k] = ((Z[k] + conj Z[n-k]) - i e^{-2 pi i k/N} (Z[k] - conj Z[n-k])) / 2,  k = 0..n
+            for (int k = threadIdx.x; k <= n / 2; k += blockDim.x) {
+                if (k == 0) {
+                    const cpx<T> z0 = res[0];
+                    cpx<T> f0, fn; f0.x = z0.x + z0.y; f0.y = 0; fn.x = z0.x - z0.y; fn.y = 0;
+                    res[0] = f0; res[n] = fn;
+                } else {
+                    const cpx<T> za = res[k], zb = res[n - k];
+                    const cpx<T> ea = cadd(za, cconj(zb)), oa = cmul(csub(za, cconj(zb)), twid<T, -1>(W, k));
+                    const cpx<T> fa = cadd(ea, cmuli<T, -1>(oa));
+                    cpx<T> r; r.x = (T)0.5 * fa.x; r.y = (T)0.5 * fa.y;
+                    if (k != n - k) {
+                        const cpx<T> eb = cadd(zb, cconj(za)), ob = cmul(csub(zb, cconj(za)), twid<T, -1>(W, n - k));
+                        const cpx<T> fb = cadd(eb, cmuli<T, -1>(ob));
+                        cpx<T> rb; rb.x = (T)0.5 * fb.x; rb.y = (T)0.5 * fb.y;
+                        res[n - k] = rb;
+                    }
+                    res[k] = r;
+                }
+            }
+            __syncthreads();
         }
+
+        // phase_m = w * e^{-i m phi0} * F[m mod N]  (packed: conjugate symmetric upper half); coalesced row write
+        const double w = P.wgt[ring];
+        double2* row = P.phase + ((long long)rl * P.ncomp + c) * P.MP;
+        for (int m0 = threadIdx.x; m0 <= P.mmax; m0 += FFT_IO_UNROLL * blockDim.x) {
+            double2 r[FFT_IO_UNROLL];
+#pragma unroll
+            for (int u = 0; u < FFT_IO_UNROLL; ++u) { const int m = m0 + u * blockDim.x; r[u] = (m <= P.mmax) ? P.phi0tw[m] : make_double2(0.0, 0.0); }
+#pragma unroll
+            for (int u = 0; u < FFT_IO_UNROLL; ++u) {
+                const int m = m0 + u * blockDim.x;
+                if (m > P.mmax) break;
+                const int kk = (m < N) ? m : (m % N);
+                const cpx<T> f = (kk <= n) ? res[kk] : cconj(res[N - kk]);
+                const double fx = (double)f.x, fy = (double)f.y;
+                *phase_elem(P, row, ring, c, m) = make_double2(w * (fx * r[u].x + fy * r[u].y), w * (fy * r[u].x - fx * r[u].y));
+            }
+        }
+        __syncthreads();   // the buffer is reused by this CTA's next ring
     }
 }
 

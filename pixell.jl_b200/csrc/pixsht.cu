@@ -60,6 +60,10 @@ struct pixsht_plan {
     unsigned fft_magic[FFT_MAXFAC] = {0};
     int nsp = 0; unsigned char sp_first[FFT_MAXFAC] = {0}, sp_count[FFT_MAXFAC] = {0};   // fused super-passes (fft.cuh)
     size_t fft_smem = 0;
+    int fft_packed = 1, fft_pt = FFT_PT;   // even nphi: real ring packed into nphi/2 complex samples; entries per pass table
+    int fft_rows = 0;                      // > 0: ring work buffers in global memory, this many CTAs per component (fft.cuh FftParams::gbuf)
+    long long fft_gslot = 0; int fft_galt = 0;
+    DevBuf<unsigned char> d_fftbuf;
     long long MP = 0;             // phase row length (mmax+1 rounded up to a multiple of 8 complex = 128 B)
     // geometry (host copies kept for introspection)
     std::vector<double> h_theta, h_wgt;
@@ -161,11 +165,11 @@ static int factorize(int n, int* fac, int& nfac)
     int odd[FFT_MAXFAC], nodd = 0;
     for (int p = 3; n > 1; p += 2) {
         while (n % p == 0) {
-            if (p > FFT_MAXRADIX || nodd >= FFT_MAXFAC) return 1;
+            if (nodd >= FFT_MAXFAC) return 1;
             odd[nodd++] = p; n /= p;
         }
         if ((long long)p * p > n && n > 1) {
-            if (n > FFT_MAXRADIX || nodd >= FFT_MAXFAC) return 1;
+            if (nodd >= FFT_MAXFAC) return 1;
             odd[nodd++] = n; n = 1;
         }
     }
@@ -273,11 +277,13 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     }
 
     // ---- FFT plan ----
-    if (P->nphi % 2 != 0) return fail(PIXSHT_ERR_UNSUPPORTED, "odd ring length nphi is not supported");
-    P->nfft = P->nphi / 2;
-    if (factorize(P->nfft, P->fac, P->nfac)) return fail(PIXSHT_ERR_UNSUPPORTED, "nphi/2 has a prime factor > 64");
+    // even nphi: the real ring is one complex FFT of nphi/2 packed samples; odd nphi: a complex FFT of nphi samples with
+    // zero imaginary part (no Nyquist mode, no even/odd split)
+    P->fft_packed = (P->nphi % 2 == 0) ? 1 : 0;
+    P->nfft = P->fft_packed ? P->nphi / 2 : P->nphi;
+    if (P->nfft > 65535) return fail(PIXSHT_ERR_UNSUPPORTED, "ring too long: the FFT index tables are 16 bit (nphi <= 131070 even, <= 65535 odd)");
+    if (factorize(P->nfft, P->fac, P->nfac)) return fail(PIXSHT_ERR_UNSUPPORTED, "ring length has too many prime factors");
     const size_t elem = (P->dtype == PIXSHT_F64) ? 16 : 8;
-    P->fft_smem = (size_t)(P->nfft + 1 + fft_tw_entries(P->nphi) + 4 * FFT_PT) * elem;
     {
         // super-passes: neighbouring radices from {2,3,4,5} whose product is <= PIXSHT_FFT_FUSE (default 16) share one
         // shared-memory round trip
@@ -296,14 +302,31 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, P->device));
     P->sm_count = prop.multiProcessorCount;
-    if (P->fft_smem > prop.sharedMemPerBlockOptin || P->nfft > 65535)
-        return fail(PIXSHT_ERR_UNSUPPORTED, "ring too long for the single-CTA shared-memory FFT (nphi/2 complex samples must fit in 227 KB)");
+    {
+        // Where the ring lives during its FFT.  Default: shared memory (n + 1 samples + tables).  Rings that do not fit, or
+        // lengths with a prime factor > FFT_MAXRADIX (whose direct pass works out of place), use per-CTA work buffers in
+        // global memory instead: one CTA per SM loops over the rings, the buffers stay L2-resident.
+        bool big_prime = false; int Lmax = 1, L = 1;
+        for (int i = 0; i < P->nfac; ++i) { if (P->fac[i] > FFT_MAXRADIX) big_prime = true; if (P->fac[i] <= 5) Lmax = std::max(Lmax, L); L *= P->fac[i]; }
+        P->fft_smem = (size_t)(P->nfft + 1 + fft_tw_entries(P->nphi) + 4 * FFT_PT) * elem;
+        const bool in_smem = !big_prime && P->fft_smem <= prop.sharedMemPerBlockOptin && Lmax <= 128 * (FFT_PT - 128) && !env_int("PIXSHT_FFT_GLOBAL", 0);
+        if (!in_smem) {
+            P->fft_pt = 128 + std::max(FFT_PT - 128, (Lmax + 127) / 128);
+            P->fft_smem = (size_t)(fft_tw_entries(P->nphi) + 4 * P->fft_pt) * elem;
+            P->fft_rows = std::max(1, std::min(nr, P->sm_count));
+            P->fft_gslot = ((long long)P->nfft + 1 + 7) / 8 * 8;
+            P->fft_galt = big_prime ? 1 : 0;
+            const size_t bytes = (size_t)P->fft_rows * 4 * P->fft_gslot * (P->fft_galt ? 2 : 1) * elem;   // up to 4 components per launch
+            if (P->d_fftbuf.alloc(bytes)) return fail(PIXSHT_ERR_NOMEM, "FFT work buffer allocation failed");
+        }
+    }
     {
         // threads per CTA: the multiple of 32 that wastes the fewest thread-iterations over the passes
         // as many CTAs per SM as the shared memory allows (their load / compute / store phases then overlap), threads per CTA
         // scaled down accordingly; among the candidates the multiple of 32 that wastes the fewest thread-iterations
         int ctas = (int)(prop.sharedMemPerMultiprocessor / (P->fft_smem + 1024));
         ctas = std::max(1, std::min(ctas, 4));
+        if (P->fft_rows) ctas = 1;   // global-memory work buffers: one large CTA per SM
         const int tcap = std::max(64, std::min(FFT_MAXTHREADS, (FFT_MAXTHREADS / ctas) / 32 * 32));
         const int tmax = std::max(64, std::min(tcap, (P->nfft / 2 + 31) / 32 * 32));
         const int tmin = std::max(64, tmax * 3 / 4 / 32 * 32);
@@ -369,11 +392,21 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
 #ifndef PIXSHT_EMU
     // opt in to large dynamic shared memory
     if (P->dtype == PIXSHT_F64) {
-        CU(cudaFuncSetAttribute(fft_phase2map<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
-        CU(cudaFuncSetAttribute(fft_map2phase<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
+        if (P->fft_rows) {
+            CU(cudaFuncSetAttribute(fft_phase2map<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
+            CU(cudaFuncSetAttribute(fft_map2phase<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
+        } else {
+            CU(cudaFuncSetAttribute(fft_phase2map<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
+            CU(cudaFuncSetAttribute(fft_map2phase<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
+        }
     } else {
-        CU(cudaFuncSetAttribute(fft_phase2map<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
-        CU(cudaFuncSetAttribute(fft_map2phase<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
+        if (P->fft_rows) {
+            CU(cudaFuncSetAttribute(fft_phase2map<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
+            CU(cudaFuncSetAttribute(fft_map2phase<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
+        } else {
+            CU(cudaFuncSetAttribute(fft_phase2map<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
+            CU(cudaFuncSetAttribute(fft_map2phase<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
+        }
     }
 #endif
     return PIXSHT_OK;
@@ -453,7 +486,7 @@ extern "C" void pixsht_plan_destroy(pixsht_plan* P)
     P->d_mlim.release(); P->d_wgt.release(); P->d_ringN.release(); P->d_ringS.release();
     P->d_lg0_hi.release(); P->d_lg0_lo.release(); P->d_lg2_hi.release(); P->d_lg2_lo.release();
     P->d_ad0.release(); P->d_gamma0.release(); P->d_ad2.release(); P->d_gamma2.release(); P->d_rec0.release(); P->d_rec2.release();
-    P->d_tw.release(); P->d_phi0tw.release(); P->d_phase.release(); P->d_perm.release();
+    P->d_tw.release(); P->d_phi0tw.release(); P->d_phase.release(); P->d_perm.release(); P->d_fftbuf.release();
     P->d_lact0.release(); P->d_lact2.release(); P->d_st0.release(); P->d_st2.release();
     for (int c = 0; c < 4; ++c) { P->d_map[c].release(); P->d_alm[c].release(); P->d_alm64[c].release(); }
     for (auto& e : P->ev) if (e) cudaEventDestroy(e);
@@ -637,13 +670,19 @@ static int stage_fft(pixsht_plan* P, int dir, int ncomp, int c_begin, int c_coun
     F.ring_begin = ring_begin; F.ring_count = ring_count;
     F.nx = P->nx; F.ny = P->ny; F.flipx = P->flipx; F.flipy = P->flipy;
     for (int c = 0; c < ncomp; ++c) F.maps[c] = maps[c];
-    dim3 grid(ring_count, c_count);
+    F.packed = P->fft_packed; F.pt = P->fft_pt;
+    if (P->fft_rows) {
+        if (c_count > 4) return fail(PIXSHT_ERR_ARG, "at most 4 components per FFT launch");
+        F.gbuf = P->d_fftbuf.p; F.gslot = P->fft_gslot; F.galt = P->fft_galt;
+    }
+    dim3 grid(P->fft_rows ? std::min(ring_count, P->fft_rows) : ring_count, c_count);
+    const bool glob = P->fft_rows > 0, fwd = dir != PIXSHT_ALM2MAP;
     if (P->dtype == PIXSHT_F64) {
-        if (dir == PIXSHT_ALM2MAP) PIXSHT_LAUNCH(fft_phase2map<double>, grid, P->fft_threads, P->fft_smem, st, F);
-        else PIXSHT_LAUNCH(fft_map2phase<double>, grid, P->fft_threads, P->fft_smem, st, F);
+        if (!glob) { if (!fwd) PIXSHT_LAUNCH((fft_phase2map<double, false>), grid, P->fft_threads, P->fft_smem, st, F); else PIXSHT_LAUNCH((fft_map2phase<double, false>), grid, P->fft_threads, P->fft_smem, st, F); }
+        else { if (!fwd) PIXSHT_LAUNCH((fft_phase2map<double, true>), grid, P->fft_threads, P->fft_smem, st, F); else PIXSHT_LAUNCH((fft_map2phase<double, true>), grid, P->fft_threads, P->fft_smem, st, F); }
     } else {
-        if (dir == PIXSHT_ALM2MAP) PIXSHT_LAUNCH(fft_phase2map<float>, grid, P->fft_threads, P->fft_smem, st, F);
-        else PIXSHT_LAUNCH(fft_map2phase<float>, grid, P->fft_threads, P->fft_smem, st, F);
+        if (!glob) { if (!fwd) PIXSHT_LAUNCH((fft_phase2map<float, false>), grid, P->fft_threads, P->fft_smem, st, F); else PIXSHT_LAUNCH((fft_map2phase<float, false>), grid, P->fft_threads, P->fft_smem, st, F); }
+        else { if (!fwd) PIXSHT_LAUNCH((fft_phase2map<float, true>), grid, P->fft_threads, P->fft_smem, st, F); else PIXSHT_LAUNCH((fft_map2phase<float, true>), grid, P->fft_threads, P->fft_smem, st, F); }
     }
     P->launches++;
     CU(cudaGetLastError());

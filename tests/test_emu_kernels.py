@@ -124,3 +124,9 @@ def test_emu_replay_batched(emu_default):
     import numpy as np
     g.test_batched_spin0_equals_single_transforms(6, np.float64, res_deg=7.5, lmax=24)
     g.test_batched_spin0_equals_single_transforms(3, np.float32, res_deg=7.5, lmax=24)
+
+
+@pytest.mark.parametrize("nphi,force_global", [(45, 0), (71, 0), (134, 0), (72, 1)])
+def test_emu_replay_general_ring_lengths(emu_default, monkeypatch, nphi, force_global):
+    import test_gpu_parity as g
+    g.test_general_ring_lengths(nphi, force_global, monkeypatch)

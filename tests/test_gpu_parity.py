@@ -404,6 +404,66 @@ def test_edge_band_limits(lmax, mmax):
     plan.close()
 
 
+@pytest.mark.parametrize("nphi,force_global", [(45, 0), (71, 0), (134, 0), (154, 0), (72, 1), (50, 1)])
+def test_general_ring_lengths(nphi, force_global, monkeypatch):
+    """Ring lengths outside the 2/3/5-smooth even case, which libsharp2 (pocketfft) accepts just the same: odd nphi (complex FFT
+    of the real ring, no Nyquist mode), prime factors above the in-register radices (71 odd, 134 = 2 x 67: direct pass), a
+    generic small odd radix (154 = 2 x 7 x 11), and -- forced here on small rings -- the global-memory work buffers that rings
+    too long for shared memory use.  Checked against the oracle in both directions, spin 0 and spin 2, partial width included."""
+    import math
+    if force_global:
+        monkeypatch.setenv("PIXSHT_FFT_GLOBAL", "1")
+    ny = 19
+    shape, wcs = fullsky_geometry((2 * math.pi / nphi, math.pi / (ny - 1)))
+    assert shape == (nphi, ny)
+    band = pixsht.sht_band(shape, wcs)
+    lmax = 18 if nphi > 45 else 30          # 30 > 45/2: aliased m on the odd ring as well
+    plan = Plan(band, lmax)
+    for spin, nc in ((0, 1), (2, 2)):
+        alms = [synth_alm(lmax, lmax, 21 + c, spin2=spin == 2) for c in range(nc)]
+        maps = plan.alm2map(alms)
+        ref = oracle_alm2map(np.stack(alms), shape, wcs, lmax, spin=spin)
+        for c in range(nc):
+            assert rel_rms(maps[c], ref[:, :, c]) < 1e-12
+        rng = np.random.default_rng(nphi)
+        x = [np.asfortranarray(rng.standard_normal(shape)) for _ in range(nc)]
+        got = plan.map2alm(x)
+        xm = Enmap(x[0], wcs) if nc == 1 else Enmap(np.asfortranarray(np.stack(x, axis=2)), wcs)
+        ref_alm = oracle_map2alm(xm, lmax, spin=spin)
+        for c in range(nc):
+            assert rel_rms(got[c], ref_alm[c]) < 1e-12
+    plan.close()
+    # a band narrower than the ring (zero padding) on the same grid
+    m = Enmap(gen_spin0(shape), wcs)
+    sub = m[2:-3, 3:-2]
+    assert rel_rms(map2alm(sub, lmax=lmax).alm, oracle_map2alm(sub, lmax)[0]) < 1e-12
+
+
+def test_long_ring_f64_uses_global_work_buffers():
+    """A 0.5' Float64 ring (nphi = 43200: 21600 complex samples = 346 KB) does not fit the 227 KB of shared memory; the FFT
+    kernels then keep the ring in per-CTA global-memory work buffers.  19 rings (10 degree steps in declination) keep the
+    check cheap; IQU, both directions, against the oracle."""
+    shape, wcs = fullsky_geometry((0.5 * pixsht.arcminute, 10.0 * degree))
+    assert shape == (43200, 19)
+    lmax = 18
+    band = pixsht.sht_band(shape, wcs)
+    plan = Plan(band, lmax)
+    for spin, nc in ((0, 1), (2, 2)):
+        alms = [synth_alm(lmax, lmax, 31 + c, spin2=spin == 2) for c in range(nc)]
+        maps = plan.alm2map(alms)
+        ref = oracle_alm2map(np.stack(alms), shape, wcs, lmax, spin=spin, kind="d")
+        for c in range(nc):
+            assert rel_rms(maps[c], ref[:, :, c]) < 1e-12
+        rng = np.random.default_rng(12)
+        x = [np.asfortranarray(rng.standard_normal(shape)) for _ in range(nc)]
+        got = plan.map2alm(x)
+        xm = Enmap(x[0], wcs) if nc == 1 else Enmap(np.asfortranarray(np.stack(x, axis=2)), wcs)
+        ref_alm = oracle_map2alm(xm, lmax, spin=spin, kind="d")
+        for c in range(nc):
+            assert rel_rms(got[c], ref_alm[c]) < 1e-12
+    plan.close()
+
+
 def test_edge_tiny_and_ragged_bands():
     """One-ring band, a band that contains only southern rings, a band one column wide (everything else of each ring is
     zero padding), and the two pole rings alone."""
@@ -428,9 +488,9 @@ def test_argument_errors_are_reported_not_fatal():
     assert L.pixsht_plan_create(ctypes.byref(h), ctypes.byref(g), 10, 11, _lib.F64, 0) == _lib.ERR_ARG          # mmax > lmax
     assert b"mmax" in L.pixsht_last_error()
     assert L.pixsht_plan_create(ctypes.byref(h), ctypes.byref(g), 10, 10, 7, 0) == _lib.ERR_ARG                 # dtype
-    bad = _lib.Geom(35, 19, 0, 19, 35, 1, 1, 0, 0.0)
-    assert L.pixsht_plan_create(ctypes.byref(h), ctypes.byref(bad), 10, 10, _lib.F64, 0) == _lib.ERR_UNSUPPORTED  # odd ring length
-    assert b"odd" in L.pixsht_last_error()
+    bad = _lib.Geom(140000, 70001, 0, 2, 140000, 1, 1, 0, 0.0)
+    assert L.pixsht_plan_create(ctypes.byref(h), ctypes.byref(bad), 10, 10, _lib.F64, 0) == _lib.ERR_UNSUPPORTED  # beyond the 16-bit FFT index tables
+    assert b"too long" in L.pixsht_last_error()
     bad = _lib.Geom(36, 19, 5, 19, 36, 1, 1, 0, 0.0)
     assert L.pixsht_plan_create(ctypes.byref(h), ctypes.byref(bad), 10, 10, _lib.F64, 0) == _lib.ERR_ARG         # band sticks out of the sphere
     bad = _lib.Geom(36, 19, 0, 19, 40, 1, 1, 0, 0.0)

@@ -318,6 +318,9 @@ def main():
             d2h = sum(m.numel() * m.element_size() for m in h_map) + sum(a.numel() * a.element_size() for a in h_out)
             e2e = {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "api": "pixsht_execute(..., PIXSHT_HOST) on pinned host buffers"}
+            # the two directions on their own (same buffers): shows where the copies are not hidden
+            e2e["alm2map_ms"] = timed(lambda: plan.execute_ptrs(ALM2MAP, [a.data_ptr() for a in h_alm], [m.data_ptr() for m in h_map], HOST), 1, max(1, min(args.steps, 3)))
+            e2e["map2alm_ms"] = timed(lambda: plan.execute_ptrs(MAP2ALM, [a.data_ptr() for a in h_out], [m.data_ptr() for m in h_map], HOST), 1, max(1, min(args.steps, 3)))
             # sanity: device-resident and host paths agree
             chk = float((h_out[0].to(device) - d_out[0]).abs().max().item())
             e2e["host_vs_device_maxabs"] = chk

@@ -860,10 +860,32 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
             }
             e_t[k] = next_ev(); CU(cudaEventRecord(e_t[k], sh));
         }
-        cudaEvent_t e_in[3] = {nullptr, nullptr, nullptr};
-        for (int c = (has0 ? 1 : 0); c < ncomp; ++c) {
-            CU(cudaMemcpyAsync(dmap[c], maps[c], map_bytes, cudaMemcpyHostToDevice, sh));
-            e_in[c] = next_ev(); CU(cudaEventRecord(e_in[c], sh));
+        // The polarisation maps follow in two parts: the equatorial third of the rings (half of the spin-2 Legendre work), then
+        // the polar rest.  The analysis of the first part (all m) starts as soon as it has arrived -- about when the spin-0 work
+        // ends -- and covers the arrival of the second, which is then analysed in m ranges whose alm columns leave one by one.
+        const int R2a = P->R2a, nch2 = leg_total_chunks(P, R2a);
+        int cA = has2 ? (int)std::lround(nch2 * (2.0 / 3.0)) : 0;      // chunks [cA, nch2): the equatorial part
+        int rA[2][2] = {{0, 0}, {0, 0}}, rB[2][2] = {{0, 0}, {0, 0}};
+        bool two_part = has2 && cA > 0 && cA < nch2 &&
+                        pair_range_rings(P, std::min(P->npairs, cA * 32 * R2a), P->npairs, rA) && pair_range_rings(P, 0, std::min(P->npairs, cA * 32 * R2a), rB);
+        cudaEvent_t e_in[3] = {nullptr, nullptr, nullptr}, e_partA = nullptr;
+        if (two_part) {
+            for (int part = 0; part < 2; ++part) {
+                for (int c = c0; c < c0 + 2; ++c)
+                    for (int h = 0; h < 2; ++h) {
+                        const int r0 = part == 0 ? rA[h][0] : rB[h][0], r1 = part == 0 ? rA[h][1] : rB[h][1];
+                        if (r1 <= r0) continue;
+                        size_t off, nb; ring_rows(P, r0, r1, esz, off, nb);
+                        CU(cudaMemcpyAsync((char*)dmap[c] + off, (const char*)maps[c] + off, nb, cudaMemcpyHostToDevice, sh));
+                    }
+                cudaEvent_t e = next_ev(); CU(cudaEventRecord(e, sh));
+                if (part == 0) e_partA = e; else e_in[c0] = e_in[c0 + 1] = e;
+            }
+        } else {
+            for (int c = (has0 ? 1 : 0); c < ncomp; ++c) {
+                CU(cudaMemcpyAsync(dmap[c], maps[c], map_bytes, cudaMemcpyHostToDevice, sh));
+                e_in[c] = next_ev(); CU(cudaEventRecord(e_in[c], sh));
+            }
         }
         // conversion + D2H of the alm columns of m in [m0, m1) for components [cb, cb+cn)
         auto emit_alm = [&](int cb, int cn, int m0, int m1) -> int {
@@ -896,9 +918,23 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
             rc = emit_alm(0, 1, 0, P->mmax + 1); if (rc) return rc;
         }
         if (has2) {
+            int chunksB = nch2;   // chunks left for the m-range launches below
+            if (two_part) {
+                CU(cudaStreamWaitEvent(sc, e_partA, 0));
+                for (int h = 0; h < 2; ++h)
+                    if (rA[h][1] > rA[h][0]) { rc = stage_fft(P, PIXSHT_MAP2ALM, ncomp, c0, 2, P->d_phase.p + (long long)rA[h][0] * ncomp * P->MP, rA[h][0], rA[h][1] - rA[h][0], dmap, sc); if (rc) return rc; }
+                const LegJob JA = {2, ncomp, c0, 0, P->mmax + 1, nullptr, cA, nch2 - cA, ph};
+                rc = anal_launch(P, JA, dalm64[c0], dalm64[c0 + 1], sc); if (rc) return rc;
+                chunksB = cA;
+            }
             CU(cudaStreamWaitEvent(sc, e_in[c0], 0));
             CU(cudaStreamWaitEvent(sc, e_in[c0 + 1], 0));
-            rc = stage_fft(P, PIXSHT_MAP2ALM, ncomp, c0, 2, P->d_phase.p, 0, P->nrings, dmap, sc); if (rc) return rc;
+            if (two_part) {
+                for (int h = 0; h < 2; ++h)
+                    if (rB[h][1] > rB[h][0]) { rc = stage_fft(P, PIXSHT_MAP2ALM, ncomp, c0, 2, P->d_phase.p + (long long)rB[h][0] * ncomp * P->MP, rB[h][0], rB[h][1] - rB[h][0], dmap, sc); if (rc) return rc; }
+            } else {
+                rc = stage_fft(P, PIXSHT_MAP2ALM, ncomp, c0, 2, P->d_phase.p, 0, P->nrings, dmap, sc); if (rc) return rc;
+            }
             // splits of m with equal Legendre work (work per m ~ lmax - m + 1), ascending: the last piece is the smallest
             const int K = std::min(P->nsplit, P->mmax + 1);
             std::vector<int> mb(K + 1);
@@ -906,7 +942,7 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
             mb[0] = 0; mb[K] = P->mmax + 1;
             for (int k = 1; k <= K; ++k) mb[k] = std::max(mb[k], mb[k - 1]);
             for (int k = 0; k < K; ++k) {
-                const LegJob J = {2, ncomp, c0, mb[k], mb[k + 1] - mb[k], nullptr, 0, leg_total_chunks(P, P->R2a), ph};
+                const LegJob J = {2, ncomp, c0, mb[k], mb[k + 1] - mb[k], nullptr, 0, chunksB, ph};
                 rc = anal_launch(P, J, dalm64[c0], dalm64[c0 + 1], sc); if (rc) return rc;
                 rc = emit_alm(c0, 2, mb[k], mb[k + 1]); if (rc) return rc;
             }

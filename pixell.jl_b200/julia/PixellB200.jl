@@ -164,6 +164,42 @@ function alm2map(alms::Vector{<:Alm}, shape, wcs)
     throw(ArgumentError("1, 2 or 3 Alm are supported"))
 end
 
-export map2alm, alm2map
+# ---- simulation sweeps: many spin-0 maps on one geometry (no counterpart upstream, where this is a loop over map2alm) ----
+# Up to four maps share one Legendre recurrence inside the library (pixsht_execute_batch).
+function execute_batch!(p::Plan, dir::Cint, alms::Vector{<:AbstractVector}, maps::Vector{<:AbstractArray})
+    GC.@preserve alms maps begin
+        aptr = Ptr{Cvoid}[pointer(a) for a in alms]
+        mptr = Ptr{Cvoid}[pointer(m) for m in maps]
+        check(ccall((:pixsht_execute_batch, libpixsht), Cint,
+                    (Ptr{Cvoid}, Cint, Cint, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Cint),
+                    p.ptr, dir, length(alms), aptr, mptr, PIXSHT_HOST))
+    end
+end
+
+"map2alm of every map of `ms` (same shape and WCS, spin 0); equals `[map2alm(m; lmax, mmax) for m in ms]`."
+function map2alm_batch(ms::Vector{<:Enmap{T,2}}; lmax=nothing, mmax=lmax) where {T}
+    wcs, shape = getwcs(ms[1]), size(ms[1])
+    if isnothing(lmax)
+        lmax = getlmax(wcs); mmax = lmax
+    end
+    C = compute_type(T)
+    p = plan_for(shape, wcs, lmax, mmax, C)
+    planes = [dense(parent(m), C) for m in ms]
+    alms = [zeros(Complex{C}, p.nalm) for _ in planes]
+    execute_batch!(p, PIXSHT_MAP2ALM, alms, planes)
+    [Alm(lmax, mmax, ComplexF64.(a)) for a in alms]
+end
+
+"alm2map of every Alm of `alms` (same lmax, mmax) onto the same geometry; equals `[alm2map(a, shape, wcs) for a in alms]`."
+function alm2map_batch(alms::Vector{<:Alm}, shape, wcs)
+    lmax, mmax = alms[1].lmax, alms[1].mmax
+    p = plan_for(shape[1:2], wcs, lmax, mmax, Float64)
+    vecs = [ComplexF64.(a.alm) for a in alms]
+    maps = [zeros(Float64, shape[1], shape[2]) for _ in alms]
+    execute_batch!(p, PIXSHT_ALM2MAP, vecs, maps)
+    [Enmap(m, wcs) for m in maps]
+end
+
+export map2alm, alm2map, map2alm_batch, alm2map_batch
 
 end # module

@@ -100,6 +100,10 @@ int pixsht_get_timings(const pixsht_plan *plan, double ms[8]);
  * Element types: phase rows and the alm of the Legendre stages are always complex double (a Float32 plan converts at the
  * pixsht_execute boundary only); the maps of the FFT stages are of the plan's dtype. */
 int64_t pixsht_phase_row_len(const pixsht_plan *plan);   /* row length of the single-GPU layout (mmax+1 rounded up to 8) */
+/* Which spin families the following pixsht_stage_* calls on this plan process: the T component (spin0), the Q/U <-> E/B pair
+ * (spin2), or both (the default).  Component arrays and the phase layout stay those of the full ncomp set; a caller uses this
+ * to pipeline an IQU transform per family (T on the device while Q/U are still on the wire: pixsht/distributed.py). */
+int pixsht_plan_set_stage_families(pixsht_plan *plan, int spin0, int spin2);
 /* Legendre stage over the m values m_list[0..nm) (device array of int32, or NULL for m = 0..nm-1). */
 int pixsht_stage_alm2phase(pixsht_plan *plan, int ncomp, const void *const *d_alms, int nm, const int32_t *d_m_list,
                            void *d_phase, int64_t row_len, void *stream);

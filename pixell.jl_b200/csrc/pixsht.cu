@@ -64,6 +64,7 @@ struct pixsht_plan {
     int fft_rows = 0;                      // > 0: ring work buffers in global memory, this many CTAs per component (fft.cuh FftParams::gbuf)
     long long fft_gslot = 0; int fft_galt = 0;
     DevBuf<unsigned char> d_fftbuf;
+    bool stage_fam0 = true, stage_fam2 = true;   // spin families the pixsht_stage_* calls process (pixsht_plan_set_stage_families)
     long long MP = 0;             // phase row length (mmax+1 rounded up to a multiple of 8 complex = 128 B)
     // geometry (host copies kept for introspection)
     std::vector<double> h_theta, h_wgt;
@@ -623,14 +624,15 @@ static int anal_launch(pixsht_plan* P, const LegJob& J, double2* out0, double2* 
 }
 
 // alm component layout per ncomp: ncomp 1: [T]; 2: [E,B]; 3: [T,E,B].  phase/map components likewise [T] / [Q,U] / [T,Q,U].
-static int stage_alm2phase(pixsht_plan* P, int ncomp, const double2* const* alm, int nm, const int* d_m_list, PhaseRef ph, cudaStream_t st)
+static int stage_alm2phase(pixsht_plan* P, int ncomp, const double2* const* alm, int nm, const int* d_m_list, PhaseRef ph, cudaStream_t st,
+                           bool fam0 = true, bool fam2 = true)
 {
-    if (ncomp == 1 || ncomp == 3) {
+    if ((ncomp == 1 || ncomp == 3) && fam0) {
         int rc = synth_prep(P, 0, alm[0], alm[0], st); if (rc) return rc;
         const LegJob J = {0, ncomp, 0, 0, nm, d_m_list, 0, leg_total_chunks(P, P->R0), ph};
         rc = synth_launch(P, J, st); if (rc) return rc;
     }
-    if (ncomp >= 2) {
+    if (ncomp >= 2 && fam2) {
         const int c0 = ncomp == 3 ? 1 : 0;
         int rc = synth_prep(P, 2, alm[c0], alm[c0 + 1], st); if (rc) return rc;
         const LegJob J = {2, ncomp, c0, 0, nm, d_m_list, 0, leg_total_chunks(P, P->R2), ph};
@@ -639,13 +641,14 @@ static int stage_alm2phase(pixsht_plan* P, int ncomp, const double2* const* alm,
     return PIXSHT_OK;
 }
 
-static int stage_phase2alm(pixsht_plan* P, int ncomp, PhaseRef ph, int nm, const int* d_m_list, double2* const* alm, cudaStream_t st)
+static int stage_phase2alm(pixsht_plan* P, int ncomp, PhaseRef ph, int nm, const int* d_m_list, double2* const* alm, cudaStream_t st,
+                           bool fam0 = true, bool fam2 = true)
 {
-    if (ncomp == 1 || ncomp == 3) {
+    if ((ncomp == 1 || ncomp == 3) && fam0) {
         const LegJob J = {0, ncomp, 0, 0, nm, d_m_list, 0, leg_total_chunks(P, P->R0a), ph};
         int rc = anal_launch(P, J, alm[0], nullptr, st); if (rc) return rc;
     }
-    if (ncomp >= 2) {
+    if (ncomp >= 2 && fam2) {
         const int c0 = ncomp == 3 ? 1 : 0;
         const LegJob J = {2, ncomp, c0, 0, nm, d_m_list, 0, leg_total_chunks(P, P->R2a), ph};
         int rc = anal_launch(P, J, alm[c0], alm[c0 + 1], st); if (rc) return rc;
@@ -1167,6 +1170,25 @@ static int stage_common(pixsht_plan* P, int ncomp)
 
 extern "C" int64_t pixsht_phase_row_len(const pixsht_plan* P) { return P ? (int64_t)P->MP : 0; }
 
+// components [cb, cb + cn) of an ncomp-component set that the selected spin families cover
+static void stage_components(const pixsht_plan* P, int ncomp, int& cb, int& cn)
+{
+    const bool h0 = ncomp != 2 && P->stage_fam0, h2 = ncomp >= 2 && P->stage_fam2;
+    const int c0 = ncomp == 3 ? 1 : 0;
+    if (h0 && h2) { cb = 0; cn = ncomp; }
+    else if (h0) { cb = 0; cn = 1; }
+    else if (h2) { cb = c0; cn = 2; }
+    else { cb = 0; cn = 0; }
+}
+
+extern "C" int pixsht_plan_set_stage_families(pixsht_plan* P, int spin0, int spin2)
+{
+    if (!P) return fail(PIXSHT_ERR_ARG, "null plan");
+    std::lock_guard<std::mutex> lock(P->mu);
+    P->stage_fam0 = spin0 != 0; P->stage_fam2 = spin2 != 0;
+    return PIXSHT_OK;
+}
+
 extern "C" int pixsht_stage_alm2phase(pixsht_plan* P, int ncomp, const void* const* d_alms, int nm, const int32_t* d_m_list,
                                       void* d_phase, int64_t row_len, void* stream)
 {
@@ -1176,7 +1198,7 @@ extern "C" int pixsht_stage_alm2phase(pixsht_plan* P, int ncomp, const void* con
     const double2* alm[3] = {nullptr, nullptr, nullptr};
     for (int c = 0; c < ncomp; ++c) alm[c] = (const double2*)d_alms[c];
     const PhaseRef ph = {(double2*)d_phase, (long long)row_len, 1};
-    return stage_alm2phase(P, ncomp, alm, nm, d_m_list, ph, (cudaStream_t)stream);
+    return stage_alm2phase(P, ncomp, alm, nm, d_m_list, ph, (cudaStream_t)stream, P->stage_fam0, P->stage_fam2);
 }
 
 extern "C" int pixsht_stage_phase2alm(pixsht_plan* P, int ncomp, const void* d_phase, int64_t row_len, int nm, const int32_t* d_m_list,
@@ -1188,7 +1210,7 @@ extern "C" int pixsht_stage_phase2alm(pixsht_plan* P, int ncomp, const void* d_p
     double2* alm[3] = {nullptr, nullptr, nullptr};
     for (int c = 0; c < ncomp; ++c) alm[c] = (double2*)d_alms[c];
     const PhaseRef ph = {(double2*)d_phase, (long long)row_len, 1};
-    return stage_phase2alm(P, ncomp, ph, nm, d_m_list, alm, (cudaStream_t)stream);
+    return stage_phase2alm(P, ncomp, ph, nm, d_m_list, alm, (cudaStream_t)stream, P->stage_fam0, P->stage_fam2);
 }
 
 extern "C" int pixsht_stage_phase2map(pixsht_plan* P, int ncomp, const int64_t* d_mtab, int ring_begin, int ring_count,
@@ -1196,7 +1218,8 @@ extern "C" int pixsht_stage_phase2map(pixsht_plan* P, int ncomp, const int64_t* 
 {
     int rc = stage_common(P, ncomp); if (rc) return rc;
     if (!d_maps || !d_mtab || ring_begin < 0 || ring_count < 0 || ring_begin + ring_count > P->nrings) return fail(PIXSHT_ERR_ARG, "bad argument");
-    return stage_fft(P, PIXSHT_ALM2MAP, ncomp, 0, ncomp, nullptr, ring_begin, ring_count, d_maps, (cudaStream_t)stream, (const long long*)d_mtab);
+    int cb, cn; stage_components(P, ncomp, cb, cn);
+    return stage_fft(P, PIXSHT_ALM2MAP, ncomp, cb, cn, nullptr, ring_begin, ring_count, d_maps, (cudaStream_t)stream, (const long long*)d_mtab);
 }
 
 extern "C" int pixsht_stage_map2phase(pixsht_plan* P, int ncomp, const void* const* d_maps, int ring_begin, int ring_count,
@@ -1204,7 +1227,8 @@ extern "C" int pixsht_stage_map2phase(pixsht_plan* P, int ncomp, const void* con
 {
     int rc = stage_common(P, ncomp); if (rc) return rc;
     if (!d_maps || !d_mtab || ring_begin < 0 || ring_count < 0 || ring_begin + ring_count > P->nrings) return fail(PIXSHT_ERR_ARG, "bad argument");
-    return stage_fft(P, PIXSHT_MAP2ALM, ncomp, 0, ncomp, nullptr, ring_begin, ring_count, (void* const*)d_maps, (cudaStream_t)stream, (const long long*)d_mtab);
+    int cb, cn; stage_components(P, ncomp, cb, cn);
+    return stage_fft(P, PIXSHT_MAP2ALM, ncomp, cb, cn, nullptr, ring_begin, ring_count, (void* const*)d_maps, (cudaStream_t)stream, (const long long*)d_mtab);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -269,6 +269,124 @@ class ShardedSHT:
         ev.append(self._ev())
         self._record("map2alm", ev)
 
+    # ---- host-resident data: the same pipelines with the PCIe copies overlapped, one spin family at a time ----------------
+    def _families(self, nc):
+        """[(spin0, spin2, components)] in processing order: T first, so that its stages run while Q/U (E/B) are on the wire."""
+        return {1: [(1, 0, [0])], 2: [(0, 1, [0, 1])], 3: [(1, 0, [0]), (0, 1, [1, 2])]}[nc]
+
+    def _host_state(self, nc):
+        if getattr(self, "_hs", None) is None or self._hs["nc"] < nc:
+            cuda = self.device.type == "cuda"
+            idx = torch.cat([torch.arange(s, e, device=self.device) for (s, e) in self.alm_columns()]) if self.nm else torch.zeros(0, dtype=torch.long, device=self.device)
+            self._hs = {"nc": nc, "idx": idx,
+                        "pin": [torch.empty(idx.numel(), dtype=self.cdtype, device=self.device) for _ in range(nc)],
+                        "pout": [torch.empty(idx.numel(), dtype=self.cdtype, device=self.device) for _ in range(nc)],
+                        "sh": torch.cuda.Stream(self.device) if cuda else None, "sd": torch.cuda.Stream(self.device) if cuda else None}
+        return self._hs
+
+    def _on(self, stream):
+        import contextlib
+        return torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+
+    def _set_families(self, f0, f2):
+        self.lib.check(self.lib.lib.pixsht_plan_set_stage_families(self.handle, int(f0), int(f2)))
+
+    def alm2map_host(self, h_alm_cols, h_map_slabs, d_alms, d_map_slabs):
+        """alm2map from / to (pinned) host memory.  h_alm_cols[c]: this rank's alm columns, packed in the order of
+        alm_columns(); h_map_slabs[c]: receives this rank's map rows.  d_alms / d_map_slabs: device work tensors as for
+        alm2map().  T is synthesised and transformed while E/B are still arriving, its rows leave while E/B compute."""
+        nc = len(d_alms)
+        hs = self._host_state(nc)
+        L = self.lib.lib
+        cuda = self.device.type == "cuda"
+        sc = torch.cuda.current_stream(self.device) if cuda else None
+        sh, sd = hs["sh"], hs["sd"]
+        if cuda:
+            sh.wait_stream(sc); sd.wait_stream(sc)
+        fams = self._families(nc)
+        ev_in = []
+        for (_, _, comps) in fams:
+            with self._on(sh):
+                for c in comps:
+                    hs["pin"][c].copy_(h_alm_cols[c], non_blocking=True)
+                    d_alms[c].index_copy_(0, hs["idx"], hs["pin"][c])
+                ev_in.append(sh.record_event() if cuda else None)
+        mtab = self._m_table()
+        st = self._stream_ptr()
+        self._barrier()          # every rank is done reading the previous contents of my phase buffer
+        try:
+            for k, (f0, f2, comps) in enumerate(fams):
+                if cuda:
+                    sc.wait_event(ev_in[k])
+                src = list(d_alms)
+                if self.dtype != torch.float64:
+                    for c in comps:
+                        src[c] = d_alms[c].to(torch.complex128)
+                self._set_families(f0, f2)
+                self.lib.check(L.pixsht_stage_alm2phase(self.handle, nc, self._ptrs(src), self.nm, ctypes.c_void_p(self.d_m_list.data_ptr()),
+                                                        ctypes.c_void_p(self.own_ptr), self.row_len, st))
+                self._barrier()      # every rank's m columns of this family are complete
+                self.lib.check(L.pixsht_stage_phase2map(self.handle, nc, ctypes.c_void_p(mtab.data_ptr()), self.r0, self.nloc,
+                                                        self._slab_base_ptrs(d_map_slabs), st))
+                if cuda:
+                    sd.wait_event(sc.record_event())
+                with self._on(sd):
+                    for c in comps:
+                        h_map_slabs[c].copy_(d_map_slabs[c], non_blocking=True)
+        finally:
+            self._set_families(1, 1)
+        if cuda:
+            sc.wait_stream(sd)   # a synchronize on the caller's stream covers the copies
+
+    def map2alm_host(self, h_map_slabs, h_alm_cols, d_map_slabs, d_alms):
+        """map2alm from / to (pinned) host memory; arguments as for alm2map_host (h_alm_cols receives this rank's columns)."""
+        nc = len(d_alms)
+        hs = self._host_state(nc)
+        L = self.lib.lib
+        cuda = self.device.type == "cuda"
+        sc = torch.cuda.current_stream(self.device) if cuda else None
+        sh, sd = hs["sh"], hs["sd"]
+        if cuda:
+            sh.wait_stream(sc); sd.wait_stream(sc)
+        fams = self._families(nc)
+        ev_in = []
+        for (_, _, comps) in fams:
+            with self._on(sh):
+                for c in comps:
+                    d_map_slabs[c].copy_(h_map_slabs[c], non_blocking=True)
+                ev_in.append(sh.record_event() if cuda else None)
+        mtab = self._m_table()
+        st = self._stream_ptr()
+        self._barrier()          # every rank is done with the previous contents of the phase buffers I am about to write
+        try:
+            for k, (f0, f2, comps) in enumerate(fams):
+                if cuda:
+                    sc.wait_event(ev_in[k])
+                self._set_families(f0, f2)
+                self.lib.check(L.pixsht_stage_map2phase(self.handle, nc, self._slab_base_ptrs(d_map_slabs), self.r0, self.nloc,
+                                                        ctypes.c_void_p(mtab.data_ptr()), st))
+                self._barrier()      # all rings of my m columns of this family have arrived
+                outs = list(d_alms)
+                for c in comps:
+                    if self.dtype != torch.float64:
+                        outs[c] = torch.empty(d_alms[c].shape, dtype=torch.complex128, device=d_alms[c].device)
+                    outs[c].zero_()
+                self.lib.check(L.pixsht_stage_phase2alm(self.handle, nc, ctypes.c_void_p(self.own_ptr), self.row_len, self.nm,
+                                                        ctypes.c_void_p(self.d_m_list.data_ptr()), self._ptrs(outs), st))
+                for c in comps:
+                    if outs[c] is not d_alms[c]:
+                        d_alms[c].copy_(outs[c])
+                    torch.index_select(d_alms[c], 0, hs["idx"], out=hs["pout"][c])
+                if cuda:
+                    sd.wait_event(sc.record_event())
+                with self._on(sd):
+                    for c in comps:
+                        h_alm_cols[c].copy_(hs["pout"][c], non_blocking=True)
+        finally:
+            self._set_families(1, 1)
+        if cuda:
+            sc.wait_stream(sd)
+
     def _record(self, name, ev):
         self.last_ms[name] = ev
 

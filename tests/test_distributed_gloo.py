@@ -36,6 +36,24 @@ def _worker(rank, world, port, lmax, res_deg, out_dir):
     sht.map2alm(slabs, out)
     np.save(os.path.join(out_dir, "alm_%d.npy" % rank), np.stack([o.numpy() for o in out]))
     np.save(os.path.join(out_dir, "rows_%d.npy" % rank), np.array([a, b]))
+    # host-resident variants (per-family pipelines through pixsht_plan_set_stage_families): same numbers as the device-tensor calls
+    idx = torch.cat([torch.arange(s, e) for (s, e) in sht.alm_columns()])
+    h_cols = [x.index_select(0, idx).clone() for x in alms]
+    work = [torch.zeros(sht.nalm, dtype=torch.complex128) for _ in range(nc)]
+    d_slabs = [torch.zeros_like(x) for x in slabs]
+    h_slabs = [torch.zeros_like(x) for x in slabs]
+    sht.alm2map_host(h_cols, h_slabs, work, d_slabs)
+    ok = all(torch.equal(x, y) for x, y in zip(h_slabs, slabs))
+    h_out = [torch.zeros_like(x) for x in h_cols]
+    sht.map2alm_host(h_slabs, h_out, d_slabs, work)
+    ok = ok and all(torch.allclose(x, o.index_select(0, idx), rtol=0, atol=1e-13) for x, o in zip(h_out, out))
+    # two components (spin 2 alone) and one (T alone) take the other family tables
+    for comps in ([1, 2], [0]):
+        w2 = [torch.zeros(sht.nalm, dtype=torch.complex128) for _ in comps]
+        hs2 = [torch.zeros_like(slabs[0]) for _ in comps]
+        sht.alm2map_host([h_cols[c] for c in comps], hs2, w2, [torch.zeros_like(slabs[0]) for _ in comps])
+        ok = ok and all(torch.equal(x, slabs[c]) for x, c in zip(hs2, comps))
+    np.save(os.path.join(out_dir, "hostok_%d.npy" % rank), np.array([int(ok)]))
     dist.barrier()
     sht.close()
     # Float32 maps / complex64 alm through the same pipeline (T only)
@@ -101,6 +119,7 @@ def test_sharded_pipeline_matches_oracle(world, tmp_path):
     assert rel_rms(got32.T.astype(np.float64), ref[:, :, 0]) < 1e-5            # Float32 tolerance of north_star
     alm32 = sum(np.load(tmp_path / ("alm32_%d.npy" % r)) for r in range(world)).astype(np.complex128)
     assert rel_rms(alm32, oracle_map2alm(pixsht.Enmap(np.asfortranarray(got32.T.astype(np.float64)), wcs), lmax)[0]) < 1e-5
+    assert all(int(np.load(tmp_path / ("hostok_%d.npy" % r))[0]) == 1 for r in range(world))   # host-path variants = device-tensor calls
     alm_sum = sum(np.load(tmp_path / ("alm_%d.npy" % r)) for r in range(world))
     rt = oracle_map2alm(pixsht.Enmap(ref[:, :, 0], wcs), lmax)[0]
     reb = oracle_map2alm(pixsht.Enmap(ref[:, :, 1:], wcs), lmax, spin=2)

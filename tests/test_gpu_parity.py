@@ -341,6 +341,20 @@ def _mgpu_worker(rank, world, port, out_dir):
         out = [torch.full((sht.nalm,), 7.0, dtype=torch.complex128, device=dev) for _ in range(3)]
         sht.map2alm(slabs, out)
     torch.cuda.synchronize(dev)
+    # host-resident variant (copies overlapped with the stages, one spin family at a time): same numbers
+    idx = torch.cat([torch.arange(s, e, device=dev) for (s, e) in sht.alm_columns()])
+    h_cols = [x.index_select(0, idx).cpu().pin_memory() for x in alms]
+    h_slabs = [torch.zeros(x.numel(), dtype=x.dtype).pin_memory() for x in slabs]
+    h_out = [torch.zeros_like(x).pin_memory() for x in h_cols]
+    w_alm = [torch.zeros(sht.nalm, dtype=torch.complex128, device=dev) for _ in range(3)]
+    w_slab = [torch.zeros_like(x) for x in slabs]
+    for _ in range(2):
+        sht.alm2map_host(h_cols, h_slabs, w_alm, w_slab)
+        sht.map2alm_host(h_slabs, h_out, w_slab, w_alm)
+    torch.cuda.synchronize(dev)
+    host_ok = all(torch.equal(h.to(dev), x) for h, x in zip(h_slabs, slabs))
+    host_ok = host_ok and all(float((h.to(dev) - o.index_select(0, idx)).abs().max()) <= 1e-13 * float(o.abs().max()) for h, o in zip(h_out, out))
+    np.save(os.path.join(out_dir, "hostok_%d.npy" % rank), np.array([int(host_ok)]))
     np.save(os.path.join(out_dir, "slab_%d.npy" % rank), np.stack([s.cpu().numpy() for s in slabs]))
     np.save(os.path.join(out_dir, "alm_%d.npy" % rank), np.stack([o.cpu().numpy() for o in out]))
     np.save(os.path.join(out_dir, "rows_%d.npy" % rank), np.array([a, b]))
@@ -375,6 +389,7 @@ def test_multi_gpu_peer_memory_pipeline_matches_single_gpu(tmp_path):
     alm_sum = sum(np.load(tmp_path / ("alm_%d.npy" % r)) for r in range(world))
     for c in range(3):
         assert rel_rms(alm_sum[c], back[c]) < 1e-13
+    assert all(int(np.load(tmp_path / ("hostok_%d.npy" % r))[0]) == 1 for r in range(world))   # alm2map_host / map2alm_host
     plan.close()
 
 

@@ -285,6 +285,32 @@ def test_c4_size_spin0_and_spin2_sampled_parity():
     plan.close()
 
 
+def test_c2_size_float32_sampled_parity():
+    """BASELINE config C2: full-sky CAR 4' (5400 x 2701) Float32 T-only, lmax 2700 (also the unit of the 64-map sweep).
+    Float32 at the boundary, FP64 inside: rel-RMS <= 1e-5 (north_star's Float32 tolerance) on sampled rings and sampled m.
+    PARITY UNPINNED by files: the reference promotes Float32 maps to Float64."""
+    shape, wcs = fullsky_geometry(4.0 * arcminute)
+    assert shape == (5400, 2701)
+    lmax = 2700
+    band = pixsht.sht_band(shape, wcs)
+    plan = Plan(band, lmax, dtype=np.float32)
+    alm = synth_alm(lmax, lmax, 2100).astype(np.complex64)
+    maps = plan.alm2map([alm])
+    assert maps[0].dtype == np.float32
+    rings = list(range(7, band.nrings, 300)) + [0, band.nrings - 1]
+    num, den = _ring_errors(band, [maps[0].astype(np.float64)], [alm.astype(np.complex128)], lmax, 0, rings)
+    assert np.sqrt(num.sum() / den.sum()) < TOL32
+    rng = np.random.default_rng(21)
+    x = np.asfortranarray(rng.standard_normal(shape), dtype=np.float32)
+    got = plan.map2alm([x])[0]
+    assert got.dtype == np.complex64
+    m_stride, m_offset = 450, 3
+    ref_alm = oracle_map2alm(Enmap(x.astype(np.float64), wcs), lmax, m_stride=m_stride, m_offset=m_offset)[0]
+    sel = np.concatenate([np.arange(alm_index(lmax, m, m), alm_index(lmax, lmax, m) + 1) for m in range(m_offset, lmax + 1, m_stride)])
+    assert rel_rms(got[sel].astype(np.complex128), ref_alm[sel]) < TOL32
+    plan.close()
+
+
 def test_host_and_device_paths_agree_and_iqu_is_t_plus_qu():
     """The pipelined host-pointer path (three streams, split launches) equals the single-stream device path, and the fused
     IQU call equals a T call plus a QU call (the reference runs IQU as two libsharp jobs, src/transforms.jl:143-144)."""

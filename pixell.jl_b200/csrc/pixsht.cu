@@ -589,13 +589,18 @@ static int synth_prep(pixsht_plan* P, int spin, const double2* a0, const double2
     CU(cudaGetLastError());
     return PIXSHT_OK;
 }
-// PIXSHT_DBG_NM / PIXSHT_DBG_CHUNKS (profiling aid, tools/loop_eff.py): restrict a launch to the first NM m values and the
-// CHUNKS equator-most chunks, where every ring is active for almost the whole l range -> pure inner-loop throughput
+// Profiling aid for tools/loop_eff.py, compiled in only with -DPIXSHT_PROBES (results are then WRONG by design):
+// PIXSHT_DBG_NM / PIXSHT_DBG_CHUNKS restrict a launch to the first NM m values and the CHUNKS equator-most chunks, where
+// every ring is active for almost the whole l range -> pure inner-loop throughput.
 static void dbg_restrict(LegParams& L)
 {
+#ifdef PIXSHT_PROBES
     const int nm = env_int("PIXSHT_DBG_NM", 0), nc = env_int("PIXSHT_DBG_CHUNKS", 0);
     if (nm > 0 && nm < L.nm) L.nm = nm;
     if (nc > 0 && nc < L.nchunks) { L.chunk_begin += L.nchunks - nc; L.nchunks = nc; }
+#else
+    (void)L;
+#endif
 }
 
 static int synth_launch(pixsht_plan* P, const LegJob& J, cudaStream_t st)

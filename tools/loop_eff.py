@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Inner-loop efficiency probe: time the Legendre kernels on the NM lowest m and the CHUNKS equator-most chunks only
-(PIXSHT_DBG_NM / PIXSHT_DBG_CHUNKS), where every ring is active over ~the whole l range, and compare with the DFMA peak."""
+(PIXSHT_DBG_NM / PIXSHT_DBG_CHUNKS), where every ring is active over ~the whole l range, and compare with the DFMA peak.
+Needs a probe build of the library: PIXSHT_NVCC_EXTRA=-DPIXSHT_PROBES bash pixell.jl_b200/build.sh (never ship that build)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "pixell.jl_b200")]

@@ -85,7 +85,7 @@ struct pixsht_plan {
     DevBuf<unsigned char> d_map[4], d_alm[4];
     DevBuf<double2> d_alm64[4];
     cudaStream_t stream = nullptr, own_stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
-    cudaEvent_t dep[48] = {nullptr};   // dependency events of the pipelined host path
+    cudaEvent_t dep[64] = {nullptr};   // dependency events of the pipelined host path (at most ~40 per call)
     std::vector<int> h_ringN, h_ringS;
     int nsplit = 8;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -605,6 +605,7 @@ static void dbg_restrict(LegParams& L)
 
 static int synth_launch(pixsht_plan* P, const LegJob& J, cudaStream_t st)
 {
+    if (J.nm <= 0 || J.nchunks <= 0) return PIXSHT_OK;   // an empty piece of a split
     const int R = leg_R(P, J.spin, false);
     LegParams L = leg_params(P, J, R);
     dbg_restrict(L);
@@ -616,6 +617,7 @@ static int synth_launch(pixsht_plan* P, const LegJob& J, cudaStream_t st)
 }
 static int anal_launch(pixsht_plan* P, const LegJob& J, double2* out0, double2* out1, cudaStream_t st)
 {
+    if (J.nm <= 0 || J.nchunks <= 0) return PIXSHT_OK;   // an empty piece of a split
     int rc = ensure_seek(P, J.spin, st); if (rc) return rc;
     const int R = leg_R(P, J.spin, true);
     LegParams L = leg_params(P, J, R);
@@ -730,6 +732,17 @@ static void ring_rows(const pixsht_plan* P, int r0, int r1, size_t esz, size_t& 
     off_bytes = (size_t)row0 * P->nx * esz; nbytes = (size_t)(r1 - r0) * P->nx * esz;
 }
 
+// Cumulative work fractions f[0] = 0 < ... < f[K] = 1 of the pieces of the pipelined host path: equal pieces, at most `limit`.
+// (Subdividing the first and the last piece further was measured and changed nothing at C4 / C3: the launches of more and
+// smaller pieces cost what the shorter exposed copies save.)
+static std::vector<double> piece_fractions(int nsplit, int limit)
+{
+    std::vector<double> f;
+    const int s = std::max(1, std::min(nsplit, limit));
+    for (int k = 0; k <= s; ++k) f.push_back((double)k / s);
+    return f;
+}
+
 // Host-pointer transform: copies, Legendre and FFT launches are pipelined over three streams so that most of the PCIe
 // time hides under the Legendre kernels (spin-0 work runs while the polarisation inputs arrive; results leave in
 // split-sized pieces while the next split computes).
@@ -754,7 +767,7 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
     }
     const PhaseRef ph = {P->d_phase.p, 0, 0};
     int ndep = 0;
-    auto next_ev = [&]() { return P->dep[ndep++ % 48]; };
+    auto next_ev = [&]() { return P->dep[ndep++ % 64]; };
     const int c0 = ncomp == 3 ? 1 : 0;          // first spin-2 component
     const bool has0 = ncomp != 2, has2 = ncomp >= 2;
     int rc;
@@ -769,10 +782,11 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
     if (direction == PIXSHT_ALM2MAP) {
         // input copies: the spin-0 alm goes first, in m ranges of equal Legendre work, so that its synthesis starts after a
         // fraction of one component has arrived; the polarisation alm follow and arrive under the spin-0 work
-        const int K0 = has0 ? std::min(P->nsplit, P->mmax + 1) : 0;
+        const std::vector<double> f0 = piece_fractions(P->nsplit, P->mmax + 1);
+        const int K0 = has0 ? (int)f0.size() - 1 : 0;
         std::vector<int> mb0(K0 + 1, 0);
         std::vector<cudaEvent_t> e_t(K0);
-        for (int k = 0; k <= K0; ++k) mb0[k] = (k == K0) ? P->mmax + 1 : (int)std::lround((P->mmax + 1) * (1.0 - std::sqrt(1.0 - (double)k / K0)));
+        for (int k = 0; k <= K0; ++k) mb0[k] = (k == K0) ? P->mmax + 1 : (int)std::lround((P->mmax + 1) * (1.0 - std::sqrt(1.0 - f0[k])));
         for (int k = 1; k <= K0; ++k) mb0[k] = std::max(mb0[k], mb0[k - 1]);
         auto col0 = [&](int m) { return (m > P->mmax) ? P->nalm : alm_index(P->lmax, m, m); };
         for (int k = 0; k < K0; ++k) {
@@ -822,9 +836,10 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
             // splits of the ring pairs with equal Legendre work (work per pair ~ sin(theta)): polar side first, so that
             // the last (exposed) piece of the map copy is the one with the fewest rings
             const int R = P->R2, nch = leg_total_chunks(P, R);
-            int K = std::min(P->nsplit, nch);
+            const std::vector<double> f2 = piece_fractions(P->nsplit, nch);
+            int K = (int)f2.size() - 1;
             std::vector<int> cb(K + 1);
-            for (int k = 0; k <= K; ++k) cb[k] = (int)std::lround(nch * (2.0 / 3.14159265358979323846) * std::acos(1.0 - (double)k / K));
+            for (int k = 0; k <= K; ++k) cb[k] = (int)std::lround(nch * (2.0 / 3.14159265358979323846) * std::acos(1.0 - f2[k]));
             cb[0] = 0; cb[K] = nch;
             for (int k = 1; k <= K; ++k) cb[k] = std::max(cb[k], cb[k - 1]);
             bool ok = true;
@@ -848,9 +863,11 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
         // input copies: the spin-0 map goes first, in ring-pair ranges (north rows + mirrored south rows), so that its FFTs
         // and analysis start after a fraction of one component has arrived; the polarisation maps follow
         const int Ra = P->R0a, nch0 = leg_total_chunks(P, Ra);
-        int K0 = has0 ? std::min(P->nsplit, nch0) : 0;
+        const std::vector<double> f0 = piece_fractions(P->nsplit, nch0);
+        int K0 = has0 ? (int)f0.size() - 1 : 0;
         std::vector<int> cb0(K0 + 1, 0);
-        for (int k = 0; k <= K0; ++k) cb0[k] = (int)((long long)nch0 * k / std::max(K0, 1));
+        for (int k = 0; k <= K0; ++k) cb0[k] = (k == K0) ? nch0 : (int)std::lround(nch0 * f0[k]);
+        for (int k = 1; k <= K0; ++k) cb0[k] = std::max(cb0[k], cb0[k - 1]);
         std::vector<std::array<int, 4>> rr0(K0);
         bool ok0 = K0 > 0;
         for (int k = 0; k < K0 && ok0; ++k) {
@@ -944,9 +961,10 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
                 rc = stage_fft(P, PIXSHT_MAP2ALM, ncomp, c0, 2, P->d_phase.p, 0, P->nrings, dmap, sc); if (rc) return rc;
             }
             // splits of m with equal Legendre work (work per m ~ lmax - m + 1), ascending: the last piece is the smallest
-            const int K = std::min(P->nsplit, P->mmax + 1);
+            const std::vector<double> f2 = piece_fractions(P->nsplit, P->mmax + 1);
+            const int K = (int)f2.size() - 1;
             std::vector<int> mb(K + 1);
-            for (int k = 0; k <= K; ++k) mb[k] = (int)std::lround((P->mmax + 1) * (1.0 - std::sqrt(1.0 - (double)k / K)));
+            for (int k = 0; k <= K; ++k) mb[k] = (int)std::lround((P->mmax + 1) * (1.0 - std::sqrt(1.0 - f2[k])));
             mb[0] = 0; mb[K] = P->mmax + 1;
             for (int k = 1; k <= K; ++k) mb[k] = std::max(mb[k], mb[k - 1]);
             for (int k = 0; k < K; ++k) {

@@ -1,2 +1,3 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "multi" 2>&1 | tail -5
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c4_n2.json 2> gpurun_out/bench_c4_n2.err; tail -c 500 gpurun_out/bench_c4_n2.json; tail -3 gpurun_out/bench_c4_n2.err
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "not size" 2>&1 | tail -2
+for w in C4 C3; do python bench.py --workload $w --steps 3 --warmup 2 --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('$w', d['value'], {k:v for k,v in d['e2e'].items() if 'ms' in k or k=='value' or 'maxabs' in k})"; done

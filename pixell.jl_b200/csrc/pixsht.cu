@@ -160,6 +160,7 @@ static void split_dd(long double v, double& hi, double& lo)
 static int factorize(int n, int* fac, int& nfac)
 {
     nfac = 0;
+    if (n == 1) { fac[nfac++] = 1; return 0; }   // a two-sample ring: one trivial pass (handled by the generic-radix branch)
     // pass order = order of fac[] (fft.cuh): odd radices first (largest first), then 4s, then a single 2
     int n2 = 0;
     while (n % 2 == 0) { ++n2; n /= 2; }

@@ -1,3 +1,3 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "not size" 2>&1 | tail -2
-for w in C4 C3; do python bench.py --workload $w --steps 3 --warmup 2 --no-cpu-baseline 2>&1 | tail -1 | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('$w', d['value'], {k:v for k,v in d['e2e'].items() if 'ms' in k or k=='value' or 'maxabs' in k})"; done
+python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+python bench.py > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; tail -c 300 gpurun_out/bench_c4.json; tail -2 gpurun_out/bench_c4.err

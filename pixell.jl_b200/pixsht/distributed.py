@@ -139,6 +139,7 @@ class ShardedSHT:
                 self._opened.append(p.value)
         self._mtab = None
         self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.host_pieces = 8     # pieces of the first input / last output of the host-resident pipelines
 
     # ---- the caller's view of the data ---------------------------------------------------------------------------
     def map_rows(self):
@@ -291,10 +292,43 @@ class ShardedSHT:
     def _set_families(self, f0, f2):
         self.lib.check(self.lib.lib.pixsht_plan_set_stage_families(self.handle, int(f0), int(f2)))
 
+    def _pieces(self, cuda):
+        # Float32 data is widened as a whole before the Legendre stage: no pieces there
+        return self.host_pieces if self.dtype == torch.float64 else 1
+
+    def _m_pieces(self, K):
+        """Contiguous slices [j0, j1) of this rank's m list with about equal Legendre work, and the offsets of the packed alm
+        columns: column j occupies [off[j], off[j+1]) of a packed buffer."""
+        L = self.lmax
+        length = (L + 1 - self.my_m).astype(np.int64)
+        off = np.concatenate([[0], np.cumsum(length)])
+        if self.nm == 0:
+            return [], off
+        K = max(1, min(K, self.nm))
+        edges = [int(np.searchsorted(off, off[-1] * k / K)) for k in range(K + 1)]
+        edges[0], edges[-1] = 0, self.nm
+        edges = np.maximum.accumulate(edges)
+        return [(int(a), int(b)) for a, b in zip(edges[:-1], edges[1:]) if b > a], off
+
+    def _ring_pieces(self, K):
+        """This rank's rings in K contiguous sub-ranges (ra, rb) with the element slice of the slab that holds their rows."""
+        K = max(1, min(K, self.nloc))
+        edges = [self.r0 + (self.nloc * k) // K for k in range(K + 1)]
+        a, _ = self.map_rows()
+        out = []
+        for ra, rb in zip(edges[:-1], edges[1:]):
+            if rb <= ra:
+                continue
+            row0 = (self.nrings - rb) if self.band.flipy else ra
+            out.append((ra, rb, slice((row0 - a) * self.band.nx, (row0 - a + rb - ra) * self.band.nx)))
+        return out
+
     def alm2map_host(self, h_alm_cols, h_map_slabs, d_alms, d_map_slabs):
         """alm2map from / to (pinned) host memory.  h_alm_cols[c]: this rank's alm columns, packed in the order of
         alm_columns(); h_map_slabs[c]: receives this rank's map rows.  d_alms / d_map_slabs: device work tensors as for
-        alm2map().  T is synthesised and transformed while E/B are still arriving, its rows leave while E/B compute."""
+        alm2map().  The copies run on two copy streams.  IQU goes polarisation first: its alm columns arrive in m ranges
+        whose synthesis starts at once, T arrives under that work, the Q/U rows leave under the T stages, and only the T rows
+        (the smaller output) leave after the last kernel."""
         nc = len(d_alms)
         hs = self._host_state(nc)
         L = self.lib.lib
@@ -303,28 +337,38 @@ class ShardedSHT:
         sh, sd = hs["sh"], hs["sd"]
         if cuda:
             sh.wait_stream(sc); sd.wait_stream(sc)
-        fams = self._families(nc)
+        fams = list(reversed(self._families(nc)))
+        pieces, off = self._m_pieces(self._pieces(cuda))
         ev_in = []
-        for (_, _, comps) in fams:
-            with self._on(sh):
-                for c in comps:
-                    hs["pin"][c].copy_(h_alm_cols[c], non_blocking=True)
-                    d_alms[c].index_copy_(0, hs["idx"], hs["pin"][c])
-                ev_in.append(sh.record_event() if cuda else None)
+        for k, (_, _, comps) in enumerate(fams):
+            segs = pieces if k == 0 else [(0, self.nm)]
+            evs = []
+            for (j0, j1) in segs:
+                seg = slice(int(off[j0]), int(off[j1]))
+                with self._on(sh):
+                    for c in comps:
+                        hs["pin"][c][seg].copy_(h_alm_cols[c][seg], non_blocking=True)
+                        d_alms[c].index_copy_(0, hs["idx"][seg], hs["pin"][c][seg])
+                    evs.append(sh.record_event() if cuda else None)
+            ev_in.append((segs, evs))
         mtab = self._m_table()
         st = self._stream_ptr()
         self._barrier()          # every rank is done reading the previous contents of my phase buffer
         try:
             for k, (f0, f2, comps) in enumerate(fams):
-                if cuda:
-                    sc.wait_event(ev_in[k])
                 src = list(d_alms)
                 if self.dtype != torch.float64:
+                    if cuda:
+                        sc.wait_event(ev_in[k][1][-1])
                     for c in comps:
                         src[c] = d_alms[c].to(torch.complex128)
                 self._set_families(f0, f2)
-                self.lib.check(L.pixsht_stage_alm2phase(self.handle, nc, self._ptrs(src), self.nm, ctypes.c_void_p(self.d_m_list.data_ptr()),
-                                                        ctypes.c_void_p(self.own_ptr), self.row_len, st))
+                for (j0, j1), ev in zip(*ev_in[k]):
+                    if cuda:
+                        sc.wait_event(ev)
+                    self.lib.check(L.pixsht_stage_alm2phase(self.handle, nc, self._ptrs(src), j1 - j0,
+                                                            ctypes.c_void_p(self.d_m_list.data_ptr() + 4 * j0),
+                                                            ctypes.c_void_p(self.own_ptr + 16 * j0), self.row_len, st))
                 self._barrier()      # every rank's m columns of this family are complete
                 self.lib.check(L.pixsht_stage_phase2map(self.handle, nc, ctypes.c_void_p(mtab.data_ptr()), self.r0, self.nloc,
                                                         self._slab_base_ptrs(d_map_slabs), st))
@@ -339,7 +383,9 @@ class ShardedSHT:
             sc.wait_stream(sd)   # a synchronize on the caller's stream covers the copies
 
     def map2alm_host(self, h_map_slabs, h_alm_cols, d_map_slabs, d_alms):
-        """map2alm from / to (pinned) host memory; arguments as for alm2map_host (h_alm_cols receives this rank's columns)."""
+        """map2alm from / to (pinned) host memory; arguments as for alm2map_host (h_alm_cols receives this rank's columns).
+        T first: its rows arrive in ring ranges whose FFTs start at once; Q/U arrive under the T stages; the polarisation
+        analysis runs in m ranges whose alm columns leave one by one."""
         nc = len(d_alms)
         hs = self._host_state(nc)
         L = self.lib.lib
@@ -349,39 +395,49 @@ class ShardedSHT:
         if cuda:
             sh.wait_stream(sc); sd.wait_stream(sc)
         fams = self._families(nc)
+        K = self._pieces(cuda)
         ev_in = []
-        for (_, _, comps) in fams:
-            with self._on(sh):
-                for c in comps:
-                    d_map_slabs[c].copy_(h_map_slabs[c], non_blocking=True)
-                ev_in.append(sh.record_event() if cuda else None)
+        for k, (_, _, comps) in enumerate(fams):
+            segs = self._ring_pieces(K if k == 0 else 1)
+            evs = []
+            for (_, _, sl) in segs:
+                with self._on(sh):
+                    for c in comps:
+                        d_map_slabs[c][sl].copy_(h_map_slabs[c][sl], non_blocking=True)
+                    evs.append(sh.record_event() if cuda else None)
+            ev_in.append((segs, evs))
         mtab = self._m_table()
         st = self._stream_ptr()
+        mpieces, off = self._m_pieces(K)
         self._barrier()          # every rank is done with the previous contents of the phase buffers I am about to write
         try:
             for k, (f0, f2, comps) in enumerate(fams):
-                if cuda:
-                    sc.wait_event(ev_in[k])
                 self._set_families(f0, f2)
-                self.lib.check(L.pixsht_stage_map2phase(self.handle, nc, self._slab_base_ptrs(d_map_slabs), self.r0, self.nloc,
-                                                        ctypes.c_void_p(mtab.data_ptr()), st))
+                for (ra, rb, _), ev in zip(*ev_in[k]):
+                    if cuda:
+                        sc.wait_event(ev)
+                    self.lib.check(L.pixsht_stage_map2phase(self.handle, nc, self._slab_base_ptrs(d_map_slabs), ra, rb - ra,
+                                                            ctypes.c_void_p(mtab.data_ptr()), st))
                 self._barrier()      # all rings of my m columns of this family have arrived
                 outs = list(d_alms)
                 for c in comps:
                     if self.dtype != torch.float64:
                         outs[c] = torch.empty(d_alms[c].shape, dtype=torch.complex128, device=d_alms[c].device)
                     outs[c].zero_()
-                self.lib.check(L.pixsht_stage_phase2alm(self.handle, nc, ctypes.c_void_p(self.own_ptr), self.row_len, self.nm,
-                                                        ctypes.c_void_p(self.d_m_list.data_ptr()), self._ptrs(outs), st))
-                for c in comps:
-                    if outs[c] is not d_alms[c]:
-                        d_alms[c].copy_(outs[c])
-                    torch.index_select(d_alms[c], 0, hs["idx"], out=hs["pout"][c])
-                if cuda:
-                    sd.wait_event(sc.record_event())
-                with self._on(sd):
+                last = k == len(fams) - 1
+                for (j0, j1) in (mpieces if last else [(0, self.nm)]):
+                    self.lib.check(L.pixsht_stage_phase2alm(self.handle, nc, ctypes.c_void_p(self.own_ptr + 16 * j0), self.row_len, j1 - j0,
+                                                            ctypes.c_void_p(self.d_m_list.data_ptr() + 4 * j0), self._ptrs(outs), st))
+                    seg = slice(int(off[j0]), int(off[j1]))
                     for c in comps:
-                        h_alm_cols[c].copy_(hs["pout"][c], non_blocking=True)
+                        if outs[c] is not d_alms[c]:
+                            d_alms[c].copy_(outs[c])
+                        hs["pout"][c][seg].copy_(d_alms[c].index_select(0, hs["idx"][seg]))
+                    if cuda:
+                        sd.wait_event(sc.record_event())
+                    with self._on(sd):
+                        for c in comps:
+                            h_alm_cols[c][seg].copy_(hs["pout"][c][seg], non_blocking=True)
         finally:
             self._set_families(1, 1)
         if cuda:

@@ -21,6 +21,7 @@ The compute stages are the pixsht_stage_* entry points of the C ABI; the peer-vi
 pixsht_shared_open (CUDA IPC; POSIX shared memory in the host-emulation build that the gloo CPU tests use).
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -139,7 +140,9 @@ class ShardedSHT:
                 self._opened.append(p.value)
         self._mtab = None
         self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
-        self.host_pieces = 8     # pieces of the first input / last output of the host-resident pipelines
+        self.host_pieces = int(os.environ.get("PIXSHT_HOST_PIECES", "3"))   # pieces of the first input / last output of the host-resident pipelines (2 GPUs, C4: 3 -> 353 ms, 8 -> 359 ms)
+        # the copy streams also run small pack / unpack kernels: high priority, so that they are not queued behind a Legendre grid
+        self._copy_prio = int(os.environ.get("PIXSHT_COPY_PRIO", "-1"))
 
     # ---- the caller's view of the data ---------------------------------------------------------------------------
     def map_rows(self):
@@ -282,7 +285,8 @@ class ShardedSHT:
             self._hs = {"nc": nc, "idx": idx,
                         "pin": [torch.empty(idx.numel(), dtype=self.cdtype, device=self.device) for _ in range(nc)],
                         "pout": [torch.empty(idx.numel(), dtype=self.cdtype, device=self.device) for _ in range(nc)],
-                        "sh": torch.cuda.Stream(self.device) if cuda else None, "sd": torch.cuda.Stream(self.device) if cuda else None}
+                        "sh": torch.cuda.Stream(self.device, priority=self._copy_prio) if cuda else None,
+                        "sd": torch.cuda.Stream(self.device, priority=self._copy_prio) if cuda else None}
         return self._hs
 
     def _on(self, stream):

@@ -14,7 +14,7 @@
 //   synthesis: per-ring register accumulators  sum_l p_l * (gamma_l a_lm)   (2 FMA per l, spin 0; 8 for spin 2),
 //              north = even + odd, south = even - odd  (equatorial symmetry);
 //   analysis : per-l partial sums over the thread's R rings, a warp-private shared-memory transpose-reduction
-//              every G (16 / 8) steps, then one atomicAdd per (l, m, warp).
+//              every 16 steps (one (value, step) row per lane), then one atomicAdd per (l, m, warp).
 //
 // Dynamic range (DESIGN.md "activation table"): lambda_lm(theta) ~ sin^m(theta) underflows FP64 by thousands of
 // decades near the poles.  The scaled-exponent "seek" from l = m up to the first l where the function reaches 2^-90

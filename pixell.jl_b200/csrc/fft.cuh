@@ -13,6 +13,9 @@
 // The two are exact transposes of each other, so one pass geometry and one permutation table serve both.  Odd radices
 // come first in the pass order: the small-stride passes then have odd strides (no shared-memory bank conflicts), and the
 // even radices run at strides >= 8 elements where consecutive threads touch consecutive addresses.
+// Ring lengths outside that fast path (odd nphi: complex FFT of nphi samples, packed = 0; a prime factor > 64: pass_direct;
+// nphi/2 samples that do not fit 227 KB) run the same passes on per-CTA work buffers in global memory (GLOBAL = true, one
+// CTA per SM looping over the rings) -- libsharp2 takes any ring length, so must this.
 // Fused into the same kernels:
 //   - the e^{+-i m phi0} rotation and the quadrature weight (libsharp2's ring helper),
 //   - m >= nphi/2 aliasing exactly as the direct sum prescribes (golden test at lmax = 3 nphi),

@@ -392,23 +392,19 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     CU(cudaMemcpy(P->h_wgt.data(), P->d_wgt.p, sizeof(double) * nr, cudaMemcpyDeviceToHost));
 
 #ifndef PIXSHT_EMU
-    // opt in to large dynamic shared memory
-    if (P->dtype == PIXSHT_F64) {
-        if (P->fft_rows) {
-            CU(cudaFuncSetAttribute(fft_phase2map<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
-            CU(cudaFuncSetAttribute(fft_map2phase<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
-        } else {
-            CU(cudaFuncSetAttribute(fft_phase2map<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
-            CU(cudaFuncSetAttribute(fft_map2phase<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
-        }
-    } else {
-        if (P->fft_rows) {
-            CU(cudaFuncSetAttribute(fft_phase2map<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
-            CU(cudaFuncSetAttribute(fft_map2phase<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
-        } else {
-            CU(cudaFuncSetAttribute(fft_phase2map<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
-            CU(cudaFuncSetAttribute(fft_map2phase<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->fft_smem));
-        }
+    // Opt in to large dynamic shared memory: the cap is a per-function attribute shared by every plan of the process, so it is
+    // set to the device maximum once and for all (a plan-sized cap would be lowered by the next, smaller plan and break the
+    // launches of the larger one); what a launch actually reserves is its own fft_smem.
+    {
+        const int cap = (int)prop.sharedMemPerBlockOptin;
+        CU(cudaFuncSetAttribute(fft_phase2map<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(fft_map2phase<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(fft_phase2map<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(fft_map2phase<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(fft_phase2map<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(fft_map2phase<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(fft_phase2map<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(fft_map2phase<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
     }
 #endif
     return PIXSHT_OK;

@@ -505,6 +505,26 @@ def test_long_ring_f64_uses_global_work_buffers():
     plan.close()
 
 
+def test_small_plan_does_not_break_a_large_one():
+    """A plan whose ring needs the large shared-memory opt-in (nphi = 10800: 106 KB) keeps working after a small plan was
+    created and used: the opt-in is a per-kernel attribute of the process, not of the plan."""
+    shape_big, wcs_big = fullsky_geometry((2.0 * arcminute, 10.0 * degree))
+    assert shape_big == (10800, 19)
+    lmax = 18
+    big = Plan(pixsht.sht_band(shape_big, wcs_big), lmax)
+    alm = synth_alm(lmax, lmax, 77)
+    ref = oracle_alm2map(alm[None], shape_big, wcs_big, lmax, kind="d")[:, :, 0]
+    assert rel_rms(big.alm2map([alm])[0], ref) < 1e-12
+    shape_small, wcs_small = fullsky_geometry(10.0 * degree)
+    small = Plan(pixsht.sht_band(shape_small, wcs_small), lmax)
+    ref_small = oracle_alm2map(alm[None], shape_small, wcs_small, lmax)[:, :, 0]
+    assert rel_rms(small.alm2map([alm])[0], ref_small) < 1e-12
+    assert rel_rms(big.alm2map([alm])[0], ref) < 1e-12          # the large plan again, after the small one
+    back = big.map2alm([np.asfortranarray(ref)])[0]
+    assert rel_rms(back, oracle_map2alm(Enmap(np.asfortranarray(ref), wcs_big), lmax, kind="d")[0]) < 1e-12
+    small.close(); big.close()
+
+
 def test_edge_tiny_and_ragged_bands():
     """One-ring band, a band that contains only southern rings, a band one column wide (everything else of each ring is
     zero padding), and the two pole rings alone."""

@@ -80,7 +80,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "PIXSHT_DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// hint: bring the 128-byte line at p into L2 (no register, no dependency)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #else
+inline void prefetch_l2(const void*) {}
 inline void mbar_init(unsigned long long*, unsigned) {}
 inline void mbar_init_fence() {}
 inline void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) { memcpy(dst, src, bytes); }

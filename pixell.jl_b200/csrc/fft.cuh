@@ -37,6 +37,7 @@ struct FftParams {
     void* gbuf;                 // nullptr: the ring lives in shared memory.  Else per-CTA work buffers in global memory (L2-resident):
     long long gslot;            //   rings too long for shared memory, or a prime factor > FFT_MAXRADIX; gslot entries per buffer,
     int galt;                   //   galt = 1: two buffers per CTA (pass_direct works out of place)
+    int prefetch;               // 1: CTAs loop over several rings; prefetch the next ring's input row into L2 during the passes
     int nfac;
     int fac[FFT_MAXFAC];        // radices in DIT pass order (pass t works on sub-transforms of length L_t = prod_{u<t} fac[u])
     unsigned magic[FFT_MAXFAC]; // floor(2^32 / L_t) + 1: b / L_t == umulhi(b, magic) for b < 2^16
@@ -521,6 +522,12 @@ __device__ __forceinline__ void store_pair(const FftParams& P, T* orow, int j, c
         if (i1 < P.nx) orow[P.flipx ? (P.nx - 1 - i1) : i1] = z.y;
     }
 }
+// L2 prefetch of `bytes` starting at p, one 128-byte line per thread and iteration
+__device__ __forceinline__ void prefetch_row(const void* p, size_t bytes)
+{
+    const char* c = reinterpret_cast<const char*>(p);
+    for (size_t off = (size_t)threadIdx.x * 128; off < bytes; off += (size_t)blockDim.x * 128) prefetch_l2(c + off);
+}
 constexpr int FFT_IO_UNROLL = 4;   // independent global accesses in flight per thread in the load / store loops
 
 // phase -> map  (synthesis).  grid = (rows, ncomp): CTA x handles band rings ring_begin + x, x + gridDim.x, ...
@@ -595,6 +602,8 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
         }
         superpass_tables<T>(P, ptabs, P.nsp - 1, superpass_L(P, P.nsp - 1));
         __syncthreads();
+        if (P.prefetch && !P.mtab && rl + (int)gridDim.x < P.ring_count)
+            prefetch_row(P.phase + ((long long)(rl + gridDim.x) * P.ncomp + c) * P.MP, (size_t)(P.mmax + 1) * sizeof(double2));
         const cpx<T>* res = fft_passes<T, +1, true>(P, W, buf, alt, ptabs);
         if (!GLOBAL) res = buf;   // no out-of-place pass without the global buffers: keeps the pointer provably shared
 
@@ -658,6 +667,10 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams 
         }
         superpass_tables<T>(P, ptabs, 0, 1);
         __syncthreads();
+        if (P.prefetch && rl + (int)gridDim.x < P.ring_count) {
+            const int ringn = ring + (int)gridDim.x;
+            prefetch_row(in + (size_t)(P.flipy ? (P.ny - 1 - ringn) : ringn) * P.nx, (size_t)P.nx * sizeof(T));
+        }
         cpx<T>* res = fft_passes<T, -1, false>(P, W, buf, alt, ptabs);
         if (!GLOBAL) res = buf;   // no out-of-place pass without the global buffers: keeps the pointer provably shared
 

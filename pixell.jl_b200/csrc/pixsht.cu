@@ -62,6 +62,8 @@ struct pixsht_plan {
     size_t fft_smem = 0;
     int fft_packed = 1, fft_pt = FFT_PT;   // even nphi: real ring packed into nphi/2 complex samples; entries per pass table
     int fft_rows = 0;                      // > 0: ring work buffers in global memory, this many CTAs per component (fft.cuh FftParams::gbuf)
+    int fft_persist = 0;                   // > 0 (default; PIXSHT_FFT_PERSIST=0 turns it off): shared-memory FFT CTAs loop over rings, this many
+                                           //      resident per SM, and prefetch the next ring's input row into L2 during the passes
     long long fft_gslot = 0; int fft_galt = 0;
     DevBuf<unsigned char> d_fftbuf;
     bool stage_fam0 = true, stage_fam2 = true;   // spin families the pixsht_stage_* calls process (pixsht_plan_set_stage_families)
@@ -329,6 +331,7 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
         int ctas = (int)(prop.sharedMemPerMultiprocessor / (P->fft_smem + 1024));
         ctas = std::max(1, std::min(ctas, 4));
         if (P->fft_rows) ctas = 1;   // global-memory work buffers: one large CTA per SM
+        else if (env_int("PIXSHT_FFT_PERSIST", 1)) P->fft_persist = ctas;
         const int tcap = std::max(64, std::min(FFT_MAXTHREADS, (FFT_MAXTHREADS / ctas) / 32 * 32));
         const int tmax = std::max(64, std::min(tcap, (P->nfft / 2 + 31) / 32 * 32));
         const int tmin = std::max(64, tmax * 3 / 4 / 32 * 32);
@@ -682,7 +685,12 @@ static int stage_fft(pixsht_plan* P, int dir, int ncomp, int c_begin, int c_coun
         if (c_count > 4) return fail(PIXSHT_ERR_ARG, "at most 4 components per FFT launch");
         F.gbuf = P->d_fftbuf.p; F.gslot = P->fft_gslot; F.galt = P->fft_galt;
     }
-    dim3 grid(P->fft_rows ? std::min(ring_count, P->fft_rows) : ring_count, c_count);
+    int gx = P->fft_rows ? std::min(ring_count, P->fft_rows) : ring_count;
+    if (!P->fft_rows && P->fft_persist > 0) {
+        gx = std::min(ring_count, std::max(1, P->sm_count * P->fft_persist / c_count));
+        F.prefetch = gx < ring_count ? 1 : 0;
+    }
+    dim3 grid(gx, c_count);
     const bool glob = P->fft_rows > 0, fwd = dir != PIXSHT_ALM2MAP;
     if (P->dtype == PIXSHT_F64) {
         if (!glob) { if (!fwd) PIXSHT_LAUNCH((fft_phase2map<double, false>), grid, P->fft_threads, P->fft_smem, st, F); else PIXSHT_LAUNCH((fft_map2phase<double, false>), grid, P->fft_threads, P->fft_smem, st, F); }

@@ -111,7 +111,7 @@ def test_emu_c1_config(emu_default):
 
 def test_emu_replay_edge_cases(emu_default):
     import test_gpu_parity as g
-    for lmax, mmax in ((0, 0), (1, 0), (2, 2), (18, 3), (40, 40)):
+    for lmax, mmax in ((0, 0), (1, 0), (18, 3)):     # the GPU suite runs the full list
         g.test_edge_band_limits(lmax, mmax)
     g.test_edge_tiny_and_ragged_bands()
     g.test_argument_errors_are_reported_not_fatal()

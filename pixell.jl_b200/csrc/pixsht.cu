@@ -66,6 +66,7 @@ struct pixsht_plan {
                                            //      resident per SM, and prefetch the next ring's input row into L2 during the passes
     long long fft_gslot = 0; int fft_galt = 0;
     DevBuf<unsigned char> d_fftbuf;
+    int batch_overlap = 0;   // PIXSHT_BATCH_OVERLAP=1 (experimental): host-pointer batches double-buffer their staging so that copies overlap the kernels
     bool stage_fam0 = true, stage_fam2 = true;   // spin families the pixsht_stage_* calls process (pixsht_plan_set_stage_families)
     long long MP = 0;             // phase row length (mmax+1 rounded up to a multiple of 8 complex = 128 B)
     // geometry (host copies kept for introspection)
@@ -84,8 +85,8 @@ struct pixsht_plan {
     DevBuf<unsigned short> d_perm;
     // work buffers (grown on demand)
     DevBuf<double2> d_phase; int phase_ncomp = 0;
-    DevBuf<unsigned char> d_map[4], d_alm[4];
-    DevBuf<double2> d_alm64[4];
+    DevBuf<unsigned char> d_map[8], d_alm[8];   // staging of the host paths: components / batch members, two sets for the overlapped batch path
+    DevBuf<double2> d_alm64[8];
     cudaStream_t stream = nullptr, own_stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t dep[64] = {nullptr};   // dependency events of the pipelined host path (at most ~40 per call)
     std::vector<int> h_ringN, h_ringS;
@@ -375,6 +376,7 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     for (auto& e : P->dep) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     P->h_ringN = ringN; P->h_ringS = ringS;
     { int v = env_int("PIXSHT_SPLITS", 8); P->nsplit = (v >= 1 && v <= 8) ? v : 8; }
+    P->batch_overlap = env_int("PIXSHT_BATCH_OVERLAP", 0) ? 1 : 0;
     P->stream = P->own_stream;
     for (auto& e : P->ev) CU(cudaEventCreate(&e));
     for (auto& e : P->kev) CU(cudaEventCreate(&e));
@@ -489,7 +491,7 @@ extern "C" void pixsht_plan_destroy(pixsht_plan* P)
     P->d_ad0.release(); P->d_gamma0.release(); P->d_ad2.release(); P->d_gamma2.release(); P->d_rec0.release(); P->d_rec2.release();
     P->d_tw.release(); P->d_phi0tw.release(); P->d_phase.release(); P->d_perm.release(); P->d_fftbuf.release();
     P->d_lact0.release(); P->d_lact2.release(); P->d_st0.release(); P->d_st2.release();
-    for (int c = 0; c < 4; ++c) { P->d_map[c].release(); P->d_alm[c].release(); P->d_alm64[c].release(); }
+    for (int c = 0; c < 8; ++c) { P->d_map[c].release(); P->d_alm[c].release(); P->d_alm64[c].release(); }
     for (auto& e : P->ev) if (e) cudaEventDestroy(e);
     for (auto& e : P->kev) if (e) cudaEventDestroy(e);
     for (auto& e : P->dep) if (e) cudaEventDestroy(e);
@@ -1119,25 +1121,44 @@ extern "C" int pixsht_execute_batch(pixsht_plan* P, int direction, int nbatch, v
     const size_t esz = f32 ? 4 : 8;
     const size_t map_bytes = (size_t)P->nx * P->ny * esz, alm_bytes = (size_t)P->nalm * 2 * esz;
     const int cvt_grid = P->sm_count > 0 ? P->sm_count * 8 : 256;
-    for (int b0 = 0; b0 < nbatch;) {
+    // Host pointers: one group of maps is staged, transformed and copied back at a time.  With batch_overlap the staging is double
+    // buffered and the copies run on the copy streams, so that group g + 1 arrives and group g - 1 leaves while group g computes.
+    const bool ovl = location == PIXSHT_HOST && P->batch_overlap;
+    cudaStream_t sh = ovl ? P->s_h2d : st, sd = ovl ? P->s_d2h : st;
+    int nev = 0;
+    auto next_ev = [&]() { return P->dep[nev++ % 64]; };
+    cudaEvent_t e_free[2] = {nullptr, nullptr};   // the last copy-out that used the staging set
+    if (ovl) {
+        cudaEvent_t e = next_ev();
+        CU(cudaEventRecord(e, st));
+        CU(cudaStreamWaitEvent(sh, e, 0));
+        CU(cudaStreamWaitEvent(sd, e, 0));
+    }
+    int group = 0;
+    for (int b0 = 0; b0 < nbatch; ++group) {
         const int left = nbatch - b0, nb = left >= 4 ? 4 : (left >= 2 ? 2 : 1);
+        const int set = ovl ? (group & 1) : 0, base = 4 * set;
         void* dmap[4] = {nullptr, nullptr, nullptr, nullptr};
         void* dalm[4] = {nullptr, nullptr, nullptr, nullptr};
         double2* alm64[4] = {nullptr, nullptr, nullptr, nullptr};
+        if (ovl && e_free[set]) CU(cudaStreamWaitEvent(sh, e_free[set], 0));   // the set's previous group has been computed and copied out
         for (int b = 0; b < nb; ++b) {
+            const int k = base + b;
             if (location == PIXSHT_HOST) {
-                if (P->d_map[b].n < map_bytes && P->d_map[b].alloc(map_bytes)) return fail(PIXSHT_ERR_NOMEM, "map staging allocation failed");
-                if (P->d_alm[b].n < alm_bytes && P->d_alm[b].alloc(alm_bytes)) return fail(PIXSHT_ERR_NOMEM, "alm staging allocation failed");
-                dmap[b] = P->d_map[b].p; dalm[b] = P->d_alm[b].p;
-                if (direction == PIXSHT_ALM2MAP) CU(cudaMemcpyAsync(dalm[b], alms[b0 + b], alm_bytes, cudaMemcpyHostToDevice, st));
-                else CU(cudaMemcpyAsync(dmap[b], maps[b0 + b], map_bytes, cudaMemcpyHostToDevice, st));
+                if (P->d_map[k].n < map_bytes && P->d_map[k].alloc(map_bytes)) return fail(PIXSHT_ERR_NOMEM, "map staging allocation failed");
+                if (P->d_alm[k].n < alm_bytes && P->d_alm[k].alloc(alm_bytes)) return fail(PIXSHT_ERR_NOMEM, "alm staging allocation failed");
+                dmap[b] = P->d_map[k].p; dalm[b] = P->d_alm[k].p;
+                if (direction == PIXSHT_ALM2MAP) CU(cudaMemcpyAsync(dalm[b], alms[b0 + b], alm_bytes, cudaMemcpyHostToDevice, sh));
+                else CU(cudaMemcpyAsync(dmap[b], maps[b0 + b], map_bytes, cudaMemcpyHostToDevice, sh));
             } else { dmap[b] = maps[b0 + b]; dalm[b] = alms[b0 + b]; }
             if (f32) {
-                if (P->d_alm64[b].n < (size_t)P->nalm && P->d_alm64[b].alloc(P->nalm)) return fail(PIXSHT_ERR_NOMEM, "alm work buffer allocation failed");
-                alm64[b] = P->d_alm64[b].p;
-                if (direction == PIXSHT_ALM2MAP) { PIXSHT_LAUNCH(k_cvt_f32_to_f64, cvt_grid, 256, 0, st, (const float*)dalm[b], (double*)alm64[b], 2 * P->nalm); P->launches++; }
+                if (P->d_alm64[k].n < (size_t)P->nalm && P->d_alm64[k].alloc(P->nalm)) return fail(PIXSHT_ERR_NOMEM, "alm work buffer allocation failed");
+                alm64[b] = P->d_alm64[k].p;
             } else alm64[b] = reinterpret_cast<double2*>(dalm[b]);
         }
+        if (ovl) { cudaEvent_t e = next_ev(); CU(cudaEventRecord(e, sh)); CU(cudaStreamWaitEvent(st, e, 0)); }
+        if (f32 && direction == PIXSHT_ALM2MAP)
+            for (int b = 0; b < nb; ++b) { PIXSHT_LAUNCH(k_cvt_f32_to_f64, cvt_grid, 256, 0, st, (const float*)dalm[b], (double*)alm64[b], 2 * P->nalm); P->launches++; }
         if (nb == 4) rc = batch_group<4>(P, direction, alm64, dmap, st);
         else if (nb == 2) rc = batch_group<2>(P, direction, alm64, dmap, st);
         else {
@@ -1154,16 +1175,20 @@ extern "C" int pixsht_execute_batch(pixsht_plan* P, int direction, int nbatch, v
             }
         }
         if (rc) return rc;
-        for (int b = 0; b < nb; ++b) {
-            if (direction == PIXSHT_MAP2ALM && f32) { PIXSHT_LAUNCH(k_cvt_f64_to_f32, cvt_grid, 256, 0, st, (const double*)alm64[b], (float*)dalm[b], 2 * P->nalm); P->launches++; }
-            if (location == PIXSHT_HOST) {
-                if (direction == PIXSHT_ALM2MAP) CU(cudaMemcpyAsync(maps[b0 + b], dmap[b], map_bytes, cudaMemcpyDeviceToHost, st));
-                else CU(cudaMemcpyAsync(alms[b0 + b], dalm[b], alm_bytes, cudaMemcpyDeviceToHost, st));
+        if (direction == PIXSHT_MAP2ALM && f32)
+            for (int b = 0; b < nb; ++b) { PIXSHT_LAUNCH(k_cvt_f64_to_f32, cvt_grid, 256, 0, st, (const double*)alm64[b], (float*)dalm[b], 2 * P->nalm); P->launches++; }
+        if (ovl) { cudaEvent_t e = next_ev(); CU(cudaEventRecord(e, st)); CU(cudaStreamWaitEvent(sd, e, 0)); }
+        if (location == PIXSHT_HOST) {
+            for (int b = 0; b < nb; ++b) {
+                if (direction == PIXSHT_ALM2MAP) CU(cudaMemcpyAsync(maps[b0 + b], dmap[b], map_bytes, cudaMemcpyDeviceToHost, sd));
+                else CU(cudaMemcpyAsync(alms[b0 + b], dalm[b], alm_bytes, cudaMemcpyDeviceToHost, sd));
             }
+            if (ovl) { e_free[set] = next_ev(); CU(cudaEventRecord(e_free[set], sd)); }
+            else CU(cudaStreamSynchronize(st));   // the single staging set is reused by the next group
         }
-        if (location == PIXSHT_HOST) CU(cudaStreamSynchronize(st));   // the staging slots are reused by the next group
         b0 += nb;
     }
+    if (ovl) { CU(cudaStreamSynchronize(sh)); CU(cudaStreamSynchronize(sd)); }
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
     for (auto& t : P->timings) t = 0;

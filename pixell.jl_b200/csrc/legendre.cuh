@@ -85,6 +85,8 @@ struct SeekParams {
     const double* lgpref_hi; const double* lgpref_lo;   // [mmax+1] log2 of the seed prefactor for this spin family
     const double2* ad;
     int* lact; double* st;
+    int thr_log2;           // rescale threshold 2^thr_log2 of the seek (SEEK_THR_LOG2 unless the plan overrides it): a pair becomes
+                            // active once its function has grown to 2^(thr_log2 - 64)
 };
 
 // ---- pre-scaling pass: alm -> records (element-wise over the alm index range [first, first+count); ~1 ms at lmax = 10800) ----
@@ -137,10 +139,10 @@ __device__ __forceinline__ LogVal seed_log(const SeekParams& P, int m, int pair,
 }
 
 // exponent offset (multiple of 64, <= 0) such that 2^(k - e) < 2^SEEK_THR_LOG2, or 0 when the value is already active
-__device__ __forceinline__ int seed_exponent(double k)
+__device__ __forceinline__ int seed_exponent(double k, int act_log2)
 {
-    if (k >= (double)ACT_LOG2) return 0;
-    const double q = ceil(((double)ACT_LOG2 - k) / (double)SEEK_QUANT);
+    if (k >= (double)act_log2) return 0;
+    const double q = ceil(((double)act_log2 - k) / (double)SEEK_QUANT);
     return (int)(-(double)SEEK_QUANT * q);
 }
 
@@ -152,9 +154,9 @@ __device__ __forceinline__ double seed_value(const LogVal& v, int e, double sign
     return sign * ldexp(exp2(v.frac), (int)d);
 }
 
-__device__ __forceinline__ bool over_thr(double v)
+__device__ __forceinline__ bool over_thr(double v, unsigned expbits)
 {
-    return ((unsigned)__double2hiint(v) & 0x7ff00000u) >= SEEK_THR_EXPBITS;
+    return ((unsigned)__double2hiint(v) & 0x7ff00000u) >= expbits;
 }
 
 // One thread per (m, ring pair): seed at l0 = max(m, |s|) as mantissa * 2^e (e a multiple of 64, <= 0), run the
@@ -166,6 +168,8 @@ __global__ void __launch_bounds__(128) k_seek_table(const SeekParams P)
     const int m = blockIdx.y;
     if (pair >= P.npairs) return;
     const int l0 = (SPIN == 0) ? m : (m > 2 ? m : 2);
+    const int act_log2 = P.thr_log2 - SEEK_QUANT;
+    const unsigned expbits = (unsigned)(1023 + P.thr_log2) << 20;
     double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;   // p: value at l, q: value at l-1  (0: lambda / lambda+, 1: lambda-)
     int e = E_DEAD;
     if ((double)m <= P.mlim[pair] && l0 <= P.lmax) {
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(128) k_seek_table(const SeekParams P)
         if (SPIN == 0) {
             // lambda_mm = (-1)^m N_m sin^m(theta), sin(theta) = 2 sin(theta/2) cos(theta/2): the factor 2^m is in lgpref
             LogVal v = seed_log(P, m, pair, m, m);
-            if (!v.zero) { e = seed_exponent(v.k); p0 = seed_value(v, e, sgn); }
+            if (!v.zero) { e = seed_exponent(v.k, act_log2); p0 = seed_value(v, e, sgn); }
         } else {
             // l0 = max(m,2):  lambda^+ ~ cos^{|m-2|} sin^{m+2},  lambda^- ~ cos^{m+2} sin^{|m-2|}  (half angles)
             const int am = m >= 2 ? m - 2 : 2 - m;
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(128) k_seek_table(const SeekParams P)
             const double sp = sgn, sm = (m >= 2) ? sgn : 1.0;
             if (!(vp.zero && vm.zero)) {
                 const double kmax = vp.zero ? vm.k : (vm.zero ? vp.k : fmax(vp.k, vm.k));
-                e = seed_exponent(kmax);
+                e = seed_exponent(kmax, act_log2);
                 p0 = seed_value(vp, e, sp);
                 p1 = seed_value(vm, e, sm);
             }
@@ -198,12 +202,12 @@ __global__ void __launch_bounds__(128) k_seek_table(const SeekParams P)
             if (SPIN == 0) {
                 const double pn = fma(c.x * x, p0, -q0);
                 q0 = p0; p0 = pn;
-                if (over_thr(pn)) { p0 *= sc; q0 *= sc; e += SEEK_QUANT; }
+                if (over_thr(pn, expbits)) { p0 *= sc; q0 *= sc; e += SEEK_QUANT; }
             } else {
                 const double pn = fma(fma(c.x, x, c.y), p0, -q0);
                 const double mn = fma(fma(c.x, x, -c.y), p1, -q1);
                 q0 = p0; p0 = pn; q1 = p1; p1 = mn;
-                if (over_thr(pn) || over_thr(mn)) { p0 *= sc; q0 *= sc; p1 *= sc; q1 *= sc; e += SEEK_QUANT; }
+                if (over_thr(pn, expbits) || over_thr(mn, expbits)) { p0 *= sc; q0 *= sc; p1 *= sc; q1 *= sc; e += SEEK_QUANT; }
             }
             ++l;
         }

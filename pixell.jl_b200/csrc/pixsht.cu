@@ -66,6 +66,7 @@ struct pixsht_plan {
                                            //      resident per SM, and prefetch the next ring's input row into L2 during the passes
     long long fft_gslot = 0; int fft_galt = 0;
     DevBuf<unsigned char> d_fftbuf;
+    int seek_thr_log2 = SEEK_THR_LOG2;   // PIXSHT_ACT_LOG2 (experimental) = log2 of the activation threshold, default -90; libsharp2 uses -60
     int batch_overlap = 0;   // PIXSHT_BATCH_OVERLAP=1 (experimental): host-pointer batches double-buffer their staging so that copies overlap the kernels
     bool stage_fam0 = true, stage_fam2 = true;   // spin families the pixsht_stage_* calls process (pixsht_plan_set_stage_families)
     long long MP = 0;             // phase row length (mmax+1 rounded up to a multiple of 8 complex = 128 B)
@@ -377,6 +378,7 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     P->h_ringN = ringN; P->h_ringS = ringS;
     { int v = env_int("PIXSHT_SPLITS", 8); P->nsplit = (v >= 1 && v <= 8) ? v : 8; }
     P->batch_overlap = env_int("PIXSHT_BATCH_OVERLAP", 0) ? 1 : 0;
+    { const int a = env_int("PIXSHT_ACT_LOG2", ACT_LOG2); P->seek_thr_log2 = (a <= -40 && a >= -200) ? a + SEEK_QUANT : SEEK_THR_LOG2; }
     P->stream = P->own_stream;
     for (auto& e : P->ev) CU(cudaEventCreate(&e));
     for (auto& e : P->kev) CU(cudaEventCreate(&e));
@@ -521,6 +523,7 @@ static int ensure_seek(pixsht_plan* P, int spin, cudaStream_t st)
     if (spin == 0) { K.lgpref_hi = P->d_lg0_hi.p; K.lgpref_lo = P->d_lg0_lo.p; K.ad = P->d_ad0.p; }
     else { K.lgpref_hi = P->d_lg2_hi.p; K.lgpref_lo = P->d_lg2_lo.p; K.ad = P->d_ad2.p; }
     K.lact = lact.p; K.st = stt.p;
+    K.thr_log2 = P->seek_thr_log2;
     dim3 grid((P->npairs + 127) / 128, P->mmax + 1);
     if (spin == 0) PIXSHT_LAUNCH(k_seek_table<0>, grid, 128, 0, st, K);
     else PIXSHT_LAUNCH(k_seek_table<2>, grid, 128, 0, st, K);

@@ -498,12 +498,36 @@ def bench_batch(args, wl, config, torch, pixsht, Plan, lib, band, lmax, device, 
     clocks = clk.stop()
     ms_s = run(one_by_one)
     fp64_peak, _ = lib.measure_fma_peak(local_rank)
+    # end to end: the same sweep through the host-pointer call on pinned buffers (H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        from pixsht._lib import HOST
+        try:
+            h_alm = [torch.empty(nalm, dtype=cdt).pin_memory() for _ in range(B)]
+            h_out = [torch.empty(nalm, dtype=cdt).pin_memory() for _ in range(B)]
+            h_map = [torch.empty(band.nx * band.nrings, dtype=rdt).pin_memory() for _ in range(B)]
+            for h, d in zip(h_alm, alm):
+                h.copy_(d)
+            torch.cuda.synchronize(device)
+
+            def batched_host():
+                plan.execute_batch_ptrs(ALM2MAP, [a.data_ptr() for a in h_alm], [m.data_ptr() for m in h_map], HOST)
+                plan.execute_batch_ptrs(MAP2ALM, [a.data_ptr() for a in h_out], [m.data_ptr() for m in h_map], HOST)
+
+            ms_h = run(batched_host)
+            nbytes = sum(x.numel() * x.element_size() for x in h_alm) + sum(x.numel() * x.element_size() for x in h_map)
+            e2e = {"value": ms_h, "unit": "ms", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                   "api": "pixsht_execute_batch(..., PIXSHT_HOST) on pinned host buffers",
+                   "overlap": bool(int(os.environ.get("PIXSHT_BATCH_OVERLAP", "0") or 0)),
+                   "host_vs_device_maxabs": float((h_out[0].to(device) - out[0]).abs().max().item())}
+        except Exception as ex:   # the device-resident numbers above stand on their own
+            e2e = {"unavailable": str(ex)[:200]}
     nom = 2.0 * 2.0 * 4 * nalm * math.ceil(band.nrings / 2) * B      # flop the B single transforms would take, both directions
     print(json.dumps({"metric": METRIC, "value": ms_b, "unit": "ms", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": ms_b, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": wl["dtype"],
                       "data": "synthetic", "config": dict(config, batch=B, step="alm2map + map2alm of all %d maps" % B), "clocks": clocks,
                       "sims_per_s": 1e3 * B / ms_b, "one_by_one_ms": ms_s, "one_by_one_sims_per_s": 1e3 * B / ms_s,
-                      "batch_speedup": ms_s / ms_b,
+                      "batch_speedup": ms_s / ms_b, "e2e": e2e,
                       "roofline": {"bound": "fp64_fma", "kernel": "leg_synth_b + leg_anal_b (+ ring FFTs) of the whole sweep",
                                    "achieved": nom / (ms_b * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                                    "frac": nom / (ms_b * 1e-3) / 1e12 / fp64_peak, "traffic": None,

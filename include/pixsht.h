@@ -63,7 +63,34 @@ int pixsht_plan_create(pixsht_plan **out, const pixsht_geom *geom, int lmax, int
  * sample at phi0, rings ascending in theta, maps stored ring-major without flips: nx = nphi).  Used by the shim. */
 int pixsht_plan_create_rings(pixsht_plan **out, int nrings, const double *theta, const double *weight, int nphi,
                              double phi0, int lmax, int mmax, int dtype, int device);
+/* Multi-GPU plan: ONE process drives `ndev` GPUs of a node behind the same blocking pixsht_execute call -- the shape of the
+ * reference's transform (sharp_execute! on caller-owned host arrays, src/transforms.jl:88-108, 185-194), no second process,
+ * no torch, no NCCL.  m is sharded (contiguous segments of equal measured Legendre work, dealt to the GPUs), rings are split
+ * into contiguous slabs, the phase transpose between the two stages happens inside the FFT kernels' row loads / stores over
+ * peer memory (cudaDeviceEnablePeerAccess: the GPUs must be NVLink / NVSwitch peers -> PIXSHT_ERR_UNSUPPORTED otherwise).
+ * Each GPU copies its alm columns / map rows straight from / to the caller's arrays.  A device index may appear more than
+ * once in `devices` (each entry is its own shard; that is how a single-GPU box exercises this path).
+ * On such a plan: pixsht_execute takes whole arrays in host memory (or any memory the GPUs can copy from; `location` is
+ * ignored); pixsht_execute_batch deals whole transforms to the GPUs; the stage API and pixsht_plan_set_stream do not apply. */
+int pixsht_plan_create_multi(pixsht_plan **out, const pixsht_geom *geom, int lmax, int mmax, int dtype, int ndev, const int *devices);
+/* shard `shard` of a multi-GPU plan: info = { device, first band ring, ring count, number of m values }; m_list (may be NULL)
+ * receives the shard's m values, ascending */
+int pixsht_multi_shard(const pixsht_plan *plan, int shard, int32_t info[4], int32_t *m_list);
+/* The same transform with the data already distributed over the GPUs (nothing is copied): alms[d*ncomp + c] = device pointer
+ * on shard d's GPU to a FULL-LENGTH alm array of which only the shard's m columns are read / written;  maps[d*ncomp + c] =
+ * device pointer on shard d's GPU to the shard's slab of map rows (ring count * nx elements, the caller's row order). */
+int pixsht_execute_sharded(pixsht_plan *plan, int direction, int ncomp, void *const *alms, void *const *maps);
 void pixsht_plan_destroy(pixsht_plan *plan);
+
+/* ---- host memory ------------------------------------------------------------------------------------------ */
+/* Page-locked host memory for the caller's maps and alm: pixsht_execute(..., PIXSHT_HOST) overlaps its copies with the
+ * kernels only from / to page-locked memory (copies from pageable memory are staged by the driver and serialise the
+ * pipeline).  pixsht_host_alloc / pixsht_host_free own an allocation; pixsht_host_register / pixsht_host_unregister
+ * page-lock an array the caller already owns (e.g. a Julia Array) for the lifetime of the registration. */
+int pixsht_host_alloc(void **ptr, size_t bytes);
+int pixsht_host_free(void *ptr);
+int pixsht_host_register(void *ptr, size_t bytes);
+int pixsht_host_unregister(void *ptr);
 
 /* ---- transforms ----------------------------------------------------------------------------------------- */
 /* direction: PIXSHT_MAP2ALM | PIXSHT_ALM2MAP.  ncomp: 1 = T (spin 0), 2 = Q,U <-> E,B (spin 2), 3 = T,Q,U <-> T,E,B.
@@ -134,7 +161,7 @@ int64_t pixsht_nalm(int lmax, int mmax);
 int pixsht_plan_info(const pixsht_plan *plan, int32_t info[16]);
 /* info: [0] nphi [1] nrings [2] lmax [3] mmax [4] dtype [5] device [6] npairs (north/south folded ring pairs)
  *       [7] SM count [8] FFT length [9] kernels launched by the last execute [10..13] ring pairs per thread of the
- *       spin-0 / spin-2 synthesis and spin-0 / spin-2 analysis kernels [14..15] reserved */
+ *       spin-0 / spin-2 synthesis and spin-0 / spin-2 analysis kernels [14] number of GPUs (shards) of the plan [15] reserved */
 /* (l, m, ring pair) steps of one spin family (0 or 2): out[0] = executed by the kernels (the plan-time activation table
  * skips what stays below 2^-90), out[1] = nominal count of SURVEY.md 8(d) (every l >= max(m,|s|) for every pair) */
 int pixsht_plan_work(pixsht_plan *plan, int spin, double out[2]);

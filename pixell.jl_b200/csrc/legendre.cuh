@@ -89,29 +89,45 @@ struct SeekParams {
                             // active once its function has grown to 2^(thr_log2 - 64)
 };
 
-// ---- pre-scaling pass: alm -> records (element-wise over the alm index range [first, first+count); ~1 ms at lmax = 10800) ----
+// ---- pre-scaling pass: alm -> records (element-wise; ~1 ms at lmax = 10800) ----------------------------------------------
+template <int SPIN>
+__device__ __forceinline__ void prep_record(long long k, bool m0, const double2* __restrict__ ad, const double* __restrict__ gamma,
+                                            const double2* __restrict__ a0, const double2* __restrict__ a1, double* __restrict__ rec)
+{
+    const double2 c = ad[k];
+    const double g = gamma[k];
+    double2* r = reinterpret_cast<double2*>(rec + k * SynthRec<SPIN>::ND);
+    if (SPIN == 0) {
+        const double2 a = a0[k];
+        r[0] = make_double2(c.x, 0.0);
+        r[1] = make_double2(g * a.x, m0 ? 0.0 : g * a.y);   // a_l0 is real
+    } else {
+        const double2 E = a0[k], B = a1[k];
+        const double h = -0.5 * g;
+        r[0] = c;
+        r[1] = make_double2(h * (E.x - B.y), h * (E.y + B.x));
+        r[SPIN != 0 ? 2 : 0] = make_double2(h * (E.x + B.y), h * (E.y - B.x));
+    }
+}
+// over the alm index range [first, first+count)
 template <int SPIN>
 __global__ void k_prep_synth(long long first, long long count, int lmax, const double2* __restrict__ ad, const double* __restrict__ gamma,
                              const double2* __restrict__ a0, const double2* __restrict__ a1, double* __restrict__ rec)
 {
     long long k = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long step = (long long)gridDim.x * blockDim.x, end = first + count;
-    for (; k < end; k += step) {
-        const double2 c = ad[k];
-        const double g = gamma[k];
-        double2* r = reinterpret_cast<double2*>(rec + k * SynthRec<SPIN>::ND);
-        if (SPIN == 0) {
-            const double2 a = a0[k];
-            r[0] = make_double2(c.x, 0.0);
-            r[1] = make_double2(g * a.x, (k <= lmax) ? 0.0 : g * a.y);   // k <= lmax  <=>  m == 0: a_l0 is real
-        } else {
-            const double2 E = a0[k], B = a1[k];
-            const double h = -0.5 * g;
-            r[0] = c;
-            r[1] = make_double2(h * (E.x - B.y), h * (E.y + B.x));
-            r[SPIN != 0 ? 2 : 0] = make_double2(h * (E.x + B.y), h * (E.y - B.x));
-        }
-    }
+    for (; k < end; k += step) prep_record<SPIN>(k, k <= lmax, ad, gamma, a0, a1, rec);   // k <= lmax  <=>  m == 0
+}
+// over the alm columns of the m values m_list[0..nm) (blockIdx.y = position in the list): the m-sharded pipelines prepare
+// only the columns a launch owns (and that have arrived)
+template <int SPIN>
+__global__ void k_prep_synth_rows(const int* __restrict__ m_list, int lmax, const double2* __restrict__ ad, const double* __restrict__ gamma,
+                                  const double2* __restrict__ a0, const double2* __restrict__ a1, double* __restrict__ rec)
+{
+    const int m = m_list[blockIdx.y];
+    const long long base = alm_index(lmax, 0, m);
+    for (int l = m + blockIdx.x * blockDim.x + threadIdx.x; l <= lmax; l += gridDim.x * blockDim.x)
+        prep_record<SPIN>(base + l, m == 0, ad, gamma, a0, a1, rec);
 }
 
 // ---- seeds (plan time only) --------------------------------------------------------------------------------

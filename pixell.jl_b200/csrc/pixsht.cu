@@ -12,6 +12,7 @@
 #include <chrono>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace pixsht;
@@ -28,9 +29,17 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
             return fail(PIXSHT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                        \
     } while (0)
 
+// Owner of one device allocation (move-only; freed on destruction).  Allocation happens on the CURRENT device; cudaFree
+// finds the owning device through the unified address space.
 template <class T>
 struct DevBuf {
     T* p = nullptr; size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { release(); }
     int alloc(size_t count)
     {
         release();
@@ -44,9 +53,10 @@ struct DevBuf {
         if (h.empty()) return PIXSHT_OK;
         return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess ? PIXSHT_OK : PIXSHT_ERR_CUDA;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void release() { if (p) { if (cudaFree(p) != cudaSuccess) (void)cudaGetLastError(); } p = nullptr; n = 0; }
 };
 
+constexpr int PIXSHT_NDEP = 128;
 struct pixsht_plan {
     int device = 0, dtype = PIXSHT_F64, sm_count = 0;
     int nphi = 0, nrings = 0, lmax = 0, mmax = 0;
@@ -67,7 +77,8 @@ struct pixsht_plan {
     long long fft_gslot = 0; int fft_galt = 0;
     DevBuf<unsigned char> d_fftbuf;
     int seek_thr_log2 = SEEK_THR_LOG2;   // PIXSHT_ACT_LOG2 (experimental) = log2 of the activation threshold, default -90; libsharp2 uses -60
-    int batch_overlap = 0;   // PIXSHT_BATCH_OVERLAP=1 (experimental): host-pointer batches double-buffer their staging so that copies overlap the kernels
+    int batch_overlap = 1;   // host-pointer batches double-buffer their staging so that copies overlap the kernels (PIXSHT_BATCH_OVERLAP=0: one group at a time;
+                             // measured on C2x64: 350 -> 193 ms end to end, bit-identical results, profiles/r02)
     bool stage_fam0 = true, stage_fam2 = true;   // spin families the pixsht_stage_* calls process (pixsht_plan_set_stage_families)
     long long MP = 0;             // phase row length (mmax+1 rounded up to a multiple of 8 complex = 128 B)
     // geometry (host copies kept for introspection)
@@ -89,7 +100,7 @@ struct pixsht_plan {
     DevBuf<unsigned char> d_map[8], d_alm[8];   // staging of the host paths: components / batch members, two sets for the overlapped batch path
     DevBuf<double2> d_alm64[8];
     cudaStream_t stream = nullptr, own_stream = nullptr, s_h2d = nullptr, s_d2h = nullptr;
-    cudaEvent_t dep[64] = {nullptr};   // dependency events of the pipelined host path (at most ~40 per call)
+    cudaEvent_t dep[PIXSHT_NDEP] = {nullptr};   // dependency events of the pipelined host path (at most ~45 per call with 8 splits)
     std::vector<int> h_ringN, h_ringS;
     int nsplit = 8;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -98,7 +109,15 @@ struct pixsht_plan {
     double timings[8] = {0};
     int launches = 0;
     std::mutex mu;
+    struct pixsht_multi* multi = nullptr;   // non-null: a multi-GPU plan (multi.inl); this object then carries the geometry only
 };
+struct pixsht_multi;
+static void multi_destroy(pixsht_multi* M);
+static void multi_quiesce(pixsht_multi* M);
+static pixsht_plan* multi_first_sub(pixsht_multi* M);
+static int multi_ndev(const pixsht_multi* M);
+static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* alms, void* const* maps, bool sharded);
+static int execute_batch_multi(pixsht_plan* P, int direction, int nbatch, void* const* alms, void* const* maps, int location);
 
 // ---------------------------------------------------------------------------------------------------------------
 // small conversion / utility kernels
@@ -114,6 +133,16 @@ __global__ void k_cvt_f64_to_f32(const double* __restrict__ in, float* __restric
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long step = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += step) out[i] = (float)in[i];
+}
+
+// the same over the alm columns of the m values m_list[0..nm) (blockIdx.y = position in the list); ZERO: out = 0
+template <class TI, class TO, bool ZERO>
+__global__ void k_cvt_rows(const int* __restrict__ m_list, int lmax, const TI* __restrict__ in, TO* __restrict__ out)
+{
+    const int m = m_list[blockIdx.y];
+    const long long base = 2 * alm_index(lmax, 0, m);
+    for (int i = 2 * m + blockIdx.x * blockDim.x + threadIdx.x; i < 2 * (lmax + 1); i += gridDim.x * blockDim.x)
+        out[base + i] = ZERO ? (TO)0 : (TO)in[base + i];
 }
 
 #ifndef PIXSHT_EMU
@@ -377,7 +406,7 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     for (auto& e : P->dep) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     P->h_ringN = ringN; P->h_ringS = ringS;
     { int v = env_int("PIXSHT_SPLITS", 8); P->nsplit = (v >= 1 && v <= 8) ? v : 8; }
-    P->batch_overlap = env_int("PIXSHT_BATCH_OVERLAP", 0) ? 1 : 0;
+    P->batch_overlap = env_int("PIXSHT_BATCH_OVERLAP", 1) ? 1 : 0;
     { const int a = env_int("PIXSHT_ACT_LOG2", ACT_LOG2); P->seek_thr_log2 = (a <= -40 && a >= -200) ? a + SEEK_QUANT : SEEK_THR_LOG2; }
     P->stream = P->own_stream;
     for (auto& e : P->ev) CU(cudaEventCreate(&e));
@@ -485,6 +514,7 @@ extern "C" int pixsht_plan_create_rings(pixsht_plan** out, int nrings, const dou
 extern "C" void pixsht_plan_destroy(pixsht_plan* P)
 {
     if (!P) return;
+    if (P->multi) { multi_destroy(P->multi); P->multi = nullptr; delete P; return; }
     // may run from a GC finalizer thread, possibly after the CUDA context is gone: every call below tolerates failure
     (void)cudaSetDevice(P->device);
     P->d_x.release(); P->d_lsh_hi.release(); P->d_lsh_lo.release(); P->d_lch_hi.release(); P->d_lch_lo.release();
@@ -576,19 +606,27 @@ static void launch_anal(pixsht_plan* P, int R, const LegParams& L, cudaStream_t 
     P->launches++;
 }
 
-// per-call pre-scaling of the alm of one spin family into the synthesis records (needs the whole alm of that family)
-static int synth_prep(pixsht_plan* P, int spin, const double2* a0, const double2* a1, cudaStream_t st, long long first = 0, long long count = -1)
+// per-call pre-scaling of the alm of one spin family into the synthesis records: over the alm index range [first, first+count)
+// (m_list == nullptr), or over the columns of the m values m_list[0..nm) -- the m-sharded pipelines prepare only the columns a
+// launch owns and that have arrived
+static int synth_prep(pixsht_plan* P, int spin, const double2* a0, const double2* a1, cudaStream_t st, long long first = 0, long long count = -1,
+                      const int* m_list = nullptr, int nm = 0)
 {
-    if (count < 0) count = P->nalm - first;
-    if (count <= 0) return PIXSHT_OK;
+    if (!m_list) {
+        if (count < 0) count = P->nalm - first;
+        if (count <= 0) return PIXSHT_OK;
+    } else if (nm <= 0) return PIXSHT_OK;
     const int prep_grid = P->sm_count > 0 ? P->sm_count * 8 : 256;
+    const dim3 row_grid((unsigned)std::max(1, std::min(8, (P->lmax + 256) / 256)), (unsigned)std::max(nm, 1));
     int rc = ensure_seek(P, spin, st); if (rc) return rc;
     if (spin == 0) {
         if (P->d_rec0.n < (size_t)P->nalm * 4 && P->d_rec0.alloc((size_t)P->nalm * 4)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
-        PIXSHT_LAUNCH(k_prep_synth<0>, prep_grid, 256, 0, st, first, count, P->lmax, P->d_ad0.p, P->d_gamma0.p, a0, a0, P->d_rec0.p);
+        if (m_list) PIXSHT_LAUNCH(k_prep_synth_rows<0>, row_grid, 256, 0, st, m_list, P->lmax, P->d_ad0.p, P->d_gamma0.p, a0, a0, P->d_rec0.p);
+        else PIXSHT_LAUNCH(k_prep_synth<0>, prep_grid, 256, 0, st, first, count, P->lmax, P->d_ad0.p, P->d_gamma0.p, a0, a0, P->d_rec0.p);
     } else {
         if (P->d_rec2.n < (size_t)P->nalm * 6 && P->d_rec2.alloc((size_t)P->nalm * 6)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
-        PIXSHT_LAUNCH(k_prep_synth<2>, prep_grid, 256, 0, st, first, count, P->lmax, P->d_ad2.p, P->d_gamma2.p, a0, a1, P->d_rec2.p);
+        if (m_list) PIXSHT_LAUNCH(k_prep_synth_rows<2>, row_grid, 256, 0, st, m_list, P->lmax, P->d_ad2.p, P->d_gamma2.p, a0, a1, P->d_rec2.p);
+        else PIXSHT_LAUNCH(k_prep_synth<2>, prep_grid, 256, 0, st, first, count, P->lmax, P->d_ad2.p, P->d_gamma2.p, a0, a1, P->d_rec2.p);
     }
     P->launches++;
     CU(cudaGetLastError());
@@ -640,13 +678,13 @@ static int stage_alm2phase(pixsht_plan* P, int ncomp, const double2* const* alm,
                            bool fam0 = true, bool fam2 = true)
 {
     if ((ncomp == 1 || ncomp == 3) && fam0) {
-        int rc = synth_prep(P, 0, alm[0], alm[0], st); if (rc) return rc;
+        int rc = synth_prep(P, 0, alm[0], alm[0], st, 0, d_m_list ? -1 : alm_index(P->lmax, nm, nm), d_m_list, nm); if (rc) return rc;
         const LegJob J = {0, ncomp, 0, 0, nm, d_m_list, 0, leg_total_chunks(P, P->R0), ph};
         rc = synth_launch(P, J, st); if (rc) return rc;
     }
     if (ncomp >= 2 && fam2) {
         const int c0 = ncomp == 3 ? 1 : 0;
-        int rc = synth_prep(P, 2, alm[c0], alm[c0 + 1], st); if (rc) return rc;
+        int rc = synth_prep(P, 2, alm[c0], alm[c0 + 1], st, 0, d_m_list ? -1 : alm_index(P->lmax, nm, nm), d_m_list, nm); if (rc) return rc;
         const LegJob J = {2, ncomp, c0, 0, nm, d_m_list, 0, leg_total_chunks(P, P->R2), ph};
         rc = synth_launch(P, J, st); if (rc) return rc;
     }
@@ -753,6 +791,17 @@ static std::vector<double> piece_fractions(int nsplit, int limit)
     return f;
 }
 
+// every stream of the plan idle, errors swallowed (failure paths: the error text of the original failure is kept by the caller)
+static void quiesce(pixsht_plan* P)
+{
+    const std::string keep = g_err;
+    if (P->s_h2d) (void)cudaStreamSynchronize(P->s_h2d);
+    if (P->stream) (void)cudaStreamSynchronize(P->stream);
+    if (P->s_d2h) (void)cudaStreamSynchronize(P->s_d2h);
+    (void)cudaGetLastError();
+    g_err = keep;
+}
+
 // Host-pointer transform: copies, Legendre and FFT launches are pipelined over three streams so that most of the PCIe
 // time hides under the Legendre kernels (spin-0 work runs while the polarisation inputs arrive; results leave in
 // split-sized pieces while the next split computes).
@@ -777,7 +826,7 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
     }
     const PhaseRef ph = {P->d_phase.p, 0, 0};
     int ndep = 0;
-    auto next_ev = [&]() { return P->dep[ndep++ % 64]; };
+    auto next_ev = [&]() { return P->dep[ndep++ % PIXSHT_NDEP]; };   // <= ~45 per call; the batch path recycles entries only after their waits were enqueued
     const int c0 = ncomp == 3 ? 1 : 0;          // first spin-2 component
     const bool has0 = ncomp != 2, has2 = ncomp >= 2;
     int rc;
@@ -1004,12 +1053,19 @@ extern "C" int pixsht_execute(pixsht_plan* P, int direction, int ncomp, void* co
     if (location != PIXSHT_HOST && location != PIXSHT_DEVICE) return fail(PIXSHT_ERR_ARG, "bad location");
     for (int c = 0; c < ncomp; ++c) if (!alms[c] || !maps[c]) return fail(PIXSHT_ERR_ARG, "null component pointer");
     std::lock_guard<std::mutex> lock(P->mu);
+    if (P->multi) {
+        // multi-GPU plan: whole arrays in host memory, or anywhere the GPUs can copy from (the copies use cudaMemcpyDefault)
+        const int rcm = execute_multi(P, direction, ncomp, alms, maps, false);
+        if (rcm) { std::string keep = g_err; multi_quiesce(P->multi); g_err = keep; }
+        return rcm;
+    }
     int rc = check_device(P->device); if (rc) return rc;
     const auto t_begin = std::chrono::steady_clock::now();
     P->launches = 0;
     rc = ensure_phase(P, ncomp); if (rc) return rc;
     if (location == PIXSHT_HOST) {
         rc = execute_host(P, direction, ncomp, alms, maps);
+        if (rc) quiesce(P);   // nothing may still reference the caller's buffers when a failed call returns
         P->timings[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
         return rc;
     }
@@ -1106,6 +1162,8 @@ static int batch_group(pixsht_plan* P, int direction, double2* const* alm64, voi
     return PIXSHT_OK;
 }
 
+static int execute_batch_locked(pixsht_plan* P, int direction, int nbatch, void* const* alms, void* const* maps, int location);
+
 extern "C" int pixsht_execute_batch(pixsht_plan* P, int direction, int nbatch, void* const* alms, void* const* maps, int location)
 {
     if (!P || !alms || !maps) return fail(PIXSHT_ERR_ARG, "null argument");
@@ -1114,6 +1172,14 @@ extern "C" int pixsht_execute_batch(pixsht_plan* P, int direction, int nbatch, v
     if (location != PIXSHT_HOST && location != PIXSHT_DEVICE) return fail(PIXSHT_ERR_ARG, "bad location");
     for (int b = 0; b < nbatch; ++b) if (!alms[b] || !maps[b]) return fail(PIXSHT_ERR_ARG, "null map or alm pointer");
     std::lock_guard<std::mutex> lock(P->mu);
+    if (P->multi) return execute_batch_multi(P, direction, nbatch, alms, maps, location);
+    const int rc = execute_batch_locked(P, direction, nbatch, alms, maps, location);
+    if (rc) quiesce(P);   // nothing may still reference the caller's buffers when a failed call returns
+    return rc;
+}
+
+static int execute_batch_locked(pixsht_plan* P, int direction, int nbatch, void* const* alms, void* const* maps, int location)
+{
     int rc = check_device(P->device); if (rc) return rc;
     const auto t_begin = std::chrono::steady_clock::now();
     P->launches = 0;
@@ -1129,7 +1195,7 @@ extern "C" int pixsht_execute_batch(pixsht_plan* P, int direction, int nbatch, v
     const bool ovl = location == PIXSHT_HOST && P->batch_overlap;
     cudaStream_t sh = ovl ? P->s_h2d : st, sd = ovl ? P->s_d2h : st;
     int nev = 0;
-    auto next_ev = [&]() { return P->dep[nev++ % 64]; };
+    auto next_ev = [&]() { return P->dep[nev++ % PIXSHT_NDEP]; };
     cudaEvent_t e_free[2] = {nullptr, nullptr};   // the last copy-out that used the staging set
     if (ovl) {
         cudaEvent_t e = next_ev();
@@ -1202,6 +1268,7 @@ extern "C" int pixsht_execute_batch(pixsht_plan* P, int direction, int nbatch, v
 extern "C" int pixsht_plan_set_stream(pixsht_plan* P, void* stream, int use_caller_stream)
 {
     if (!P) return fail(PIXSHT_ERR_ARG, "null plan");
+    if (P->multi) return fail(PIXSHT_ERR_UNSUPPORTED, "a multi-GPU plan runs on its own streams");
     std::lock_guard<std::mutex> lock(P->mu);
     P->stream = use_caller_stream ? (cudaStream_t)stream : P->own_stream;
     return PIXSHT_OK;
@@ -1220,6 +1287,7 @@ extern "C" int pixsht_get_timings(const pixsht_plan* P, double ms[8])
 static int stage_common(pixsht_plan* P, int ncomp)
 {
     if (!P) return fail(PIXSHT_ERR_ARG, "null plan");
+    if (P->multi) return fail(PIXSHT_ERR_ARG, "the stage API works on single-GPU plans (a multi-GPU plan runs its own stages inside pixsht_execute)");
     if (ncomp < 1 || ncomp > 3) return fail(PIXSHT_ERR_ARG, "SHTs require 1 <= ncomp <= 3, for I, QU, and IQU.");
     return check_device(P->device);
 }
@@ -1249,6 +1317,7 @@ extern "C" int pixsht_stage_alm2phase(pixsht_plan* P, int ncomp, const void* con
                                       void* d_phase, int64_t row_len, void* stream)
 {
     int rc = stage_common(P, ncomp); if (rc) return rc;
+    std::lock_guard<std::mutex> lock(P->mu);   // the stages build the activation tables lazily and count launches
     if (!d_alms || !d_phase || nm < 0 || nm > P->mmax + 1 || row_len < nm) return fail(PIXSHT_ERR_ARG, "bad argument");
     if (nm == 0) return PIXSHT_OK;
     const double2* alm[3] = {nullptr, nullptr, nullptr};
@@ -1261,6 +1330,7 @@ extern "C" int pixsht_stage_phase2alm(pixsht_plan* P, int ncomp, const void* d_p
                                       void* const* d_alms, void* stream)
 {
     int rc = stage_common(P, ncomp); if (rc) return rc;
+    std::lock_guard<std::mutex> lock(P->mu);   // the stages build the activation tables lazily and count launches
     if (!d_alms || !d_phase || nm < 0 || nm > P->mmax + 1 || row_len < nm) return fail(PIXSHT_ERR_ARG, "bad argument");
     if (nm == 0) return PIXSHT_OK;
     double2* alm[3] = {nullptr, nullptr, nullptr};
@@ -1273,6 +1343,7 @@ extern "C" int pixsht_stage_phase2map(pixsht_plan* P, int ncomp, const int64_t* 
                                       void* const* d_maps, void* stream)
 {
     int rc = stage_common(P, ncomp); if (rc) return rc;
+    std::lock_guard<std::mutex> lock(P->mu);   // the stages build the activation tables lazily and count launches
     if (!d_maps || !d_mtab || ring_begin < 0 || ring_count < 0 || ring_begin + ring_count > P->nrings) return fail(PIXSHT_ERR_ARG, "bad argument");
     int cb, cn; stage_components(P, ncomp, cb, cn);
     return stage_fft(P, PIXSHT_ALM2MAP, ncomp, cb, cn, nullptr, ring_begin, ring_count, d_maps, (cudaStream_t)stream, (const long long*)d_mtab);
@@ -1282,6 +1353,7 @@ extern "C" int pixsht_stage_map2phase(pixsht_plan* P, int ncomp, const void* con
                                       const int64_t* d_mtab, void* stream)
 {
     int rc = stage_common(P, ncomp); if (rc) return rc;
+    std::lock_guard<std::mutex> lock(P->mu);   // the stages build the activation tables lazily and count launches
     if (!d_maps || !d_mtab || ring_begin < 0 || ring_count < 0 || ring_begin + ring_count > P->nrings) return fail(PIXSHT_ERR_ARG, "bad argument");
     int cb, cn; stage_components(P, ncomp, cb, cn);
     return stage_fft(P, PIXSHT_MAP2ALM, ncomp, cb, cn, nullptr, ring_begin, ring_count, (void* const*)d_maps, (cudaStream_t)stream, (const long long*)d_mtab);
@@ -1380,6 +1452,50 @@ extern "C" int pixsht_shared_free(void* dptr)
 #endif
 
 // ---------------------------------------------------------------------------------------------------------------
+// page-locked host memory for the caller's arrays
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int pixsht_host_alloc(void** ptr, size_t bytes)
+{
+    if (!ptr || bytes == 0) return fail(PIXSHT_ERR_ARG, "bad argument");
+    *ptr = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); return fail(PIXSHT_ERR_NODEVICE, "no CUDA device available"); }
+#ifdef PIXSHT_EMU
+    if (cudaMallocHost(ptr, bytes) != cudaSuccess) return fail(PIXSHT_ERR_NOMEM, "host allocation failed");
+#else
+    if (cudaHostAlloc(ptr, bytes, cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); return fail(PIXSHT_ERR_NOMEM, "page-locked host allocation failed"); }
+#endif
+    return PIXSHT_OK;
+}
+extern "C" int pixsht_host_free(void* ptr)
+{
+    if (ptr && cudaFreeHost(ptr) != cudaSuccess) { (void)cudaGetLastError(); return fail(PIXSHT_ERR_CUDA, "cudaFreeHost failed"); }
+    return PIXSHT_OK;
+}
+extern "C" int pixsht_host_register(void* ptr, size_t bytes)
+{
+    if (!ptr || bytes == 0) return fail(PIXSHT_ERR_ARG, "bad argument");
+#ifndef PIXSHT_EMU
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); return fail(PIXSHT_ERR_NODEVICE, "no CUDA device available"); }
+    const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { (void)cudaGetLastError(); return PIXSHT_OK; }
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(PIXSHT_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+#endif
+    return PIXSHT_OK;
+}
+extern "C" int pixsht_host_unregister(void* ptr)
+{
+    if (!ptr) return PIXSHT_OK;
+#ifndef PIXSHT_EMU
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess && e != cudaErrorHostMemoryNotRegistered) { (void)cudaGetLastError(); return fail(PIXSHT_ERR_CUDA, std::string("cudaHostUnregister: ") + cudaGetErrorString(e)); }
+    (void)cudaGetLastError();
+#endif
+    return PIXSHT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // introspection
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int pixsht_plan_info(const pixsht_plan* P, int32_t info[16])
@@ -1388,6 +1504,7 @@ extern "C" int pixsht_plan_info(const pixsht_plan* P, int32_t info[16])
     for (int i = 0; i < 16; ++i) info[i] = 0;
     info[0] = P->nphi; info[1] = P->nrings; info[2] = P->lmax; info[3] = P->mmax; info[4] = P->dtype; info[5] = P->device;
     info[6] = P->npairs; info[7] = P->sm_count; info[8] = P->nfft; info[9] = P->launches; info[10] = P->R0; info[11] = P->R2; info[12] = P->R0a; info[13] = P->R2a;
+    info[14] = P->multi ? multi_ndev(P->multi) : 1;
     return PIXSHT_OK;
 }
 
@@ -1422,19 +1539,29 @@ __global__ void k_count_work_m(int lmax, int npairs, const int* __restrict__ lac
     if (threadIdx.x == 0) out[m] = red[0];
 }
 
-extern "C" int pixsht_plan_work_per_m(pixsht_plan* P, int spin, double* out)
+// executed steps per m of one spin family (host vector of mmax+1); the caller holds the plan's lock or owns the plan
+static int work_per_m(pixsht_plan* P, int spin, std::vector<double>& out)
 {
-    if (!P || !out || (spin != 0 && spin != 2)) return fail(PIXSHT_ERR_ARG, "bad argument");
-    std::lock_guard<std::mutex> lock(P->mu);
     int rc = check_device(P->device); if (rc) return rc;
     rc = ensure_seek(P, spin, P->stream); if (rc) return rc;
     DevBuf<double> d;
     if (d.alloc(P->mmax + 1)) return fail(PIXSHT_ERR_NOMEM, "allocation failed");
     PIXSHT_LAUNCH(k_count_work_m, P->mmax + 1, 128, 0, P->stream, P->lmax, P->npairs, spin == 0 ? P->d_lact0.p : P->d_lact2.p, d.p);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(out, d.p, sizeof(double) * (P->mmax + 1), cudaMemcpyDeviceToHost, P->stream));
+    out.resize(P->mmax + 1);
+    CU(cudaMemcpyAsync(out.data(), d.p, sizeof(double) * (P->mmax + 1), cudaMemcpyDeviceToHost, P->stream));
     CU(cudaStreamSynchronize(P->stream));
-    d.release();
+    return PIXSHT_OK;
+}
+
+extern "C" int pixsht_plan_work_per_m(pixsht_plan* P, int spin, double* out)
+{
+    if (!P || !out || (spin != 0 && spin != 2)) return fail(PIXSHT_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lock(P->mu);
+    pixsht_plan* Q = P->multi ? multi_first_sub(P->multi) : P;
+    std::vector<double> w;
+    int rc = work_per_m(Q, spin, w); if (rc) return rc;
+    memcpy(out, w.data(), sizeof(double) * w.size());
     return PIXSHT_OK;
 }
 
@@ -1442,6 +1569,7 @@ extern "C" int pixsht_plan_work(pixsht_plan* P, int spin, double out[2])
 {
     if (!P || !out || (spin != 0 && spin != 2)) return fail(PIXSHT_ERR_ARG, "bad argument");
     std::lock_guard<std::mutex> lock(P->mu);
+    if (P->multi) P = multi_first_sub(P->multi);   // tables are replicated: every shard's plan reports the same counts
     int rc = check_device(P->device); if (rc) return rc;
     rc = ensure_seek(P, spin, P->stream); if (rc) return rc;
     DevBuf<unsigned long long> d;
@@ -1568,3 +1696,5 @@ extern "C" int pixsht_measure_fma_peak(int device, double* fp64_tflops, double* 
     return PIXSHT_OK;
 #endif
 }
+
+#include "multi.inl"

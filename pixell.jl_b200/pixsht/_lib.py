@@ -24,7 +24,8 @@ class Geom(ctypes.Structure):
 
 
 # every symbol include/pixsht.h and include/pixsht_sharp_shim.h declare
-EXPORTS = ["pixsht_plan_create", "pixsht_plan_create_rings", "pixsht_plan_destroy", "pixsht_execute", "pixsht_execute_batch", "pixsht_get_timings", "pixsht_plan_set_stream",
+EXPORTS = ["pixsht_plan_create", "pixsht_plan_create_rings", "pixsht_plan_create_multi", "pixsht_multi_shard", "pixsht_execute_sharded",
+           "pixsht_host_alloc", "pixsht_host_free", "pixsht_host_register", "pixsht_host_unregister", "pixsht_plan_destroy", "pixsht_execute", "pixsht_execute_batch", "pixsht_get_timings", "pixsht_plan_set_stream",
            "pixsht_plan_set_stage_families", "pixsht_stage_alm2phase", "pixsht_stage_phase2alm", "pixsht_stage_phase2map", "pixsht_stage_map2phase",
            "pixsht_phase_row_len", "pixsht_shared_alloc", "pixsht_shared_open", "pixsht_shared_close", "pixsht_shared_free",
            "pixsht_nalm", "pixsht_alm2cl", "pixsht_plan_info", "pixsht_plan_weights", "pixsht_plan_work", "pixsht_plan_work_per_m", "pixsht_last_error", "pixsht_version",
@@ -48,6 +49,13 @@ class PixshtLib:
         pvp = ctypes.POINTER(ctypes.c_void_p)
         L.pixsht_plan_create.argtypes = [pvp, ctypes.POINTER(Geom), i32, i32, i32, i32]
         L.pixsht_plan_create_rings.argtypes = [pvp, i32, ctypes.POINTER(dbl), ctypes.POINTER(dbl), i32, dbl, i32, i32, i32, i32]
+        L.pixsht_plan_create_multi.argtypes = [pvp, ctypes.POINTER(Geom), i32, i32, i32, i32, ctypes.POINTER(ctypes.c_int)]
+        L.pixsht_multi_shard.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
+        L.pixsht_execute_sharded.argtypes = [vp, i32, i32, pvp, pvp]
+        L.pixsht_host_alloc.argtypes = [pvp, ctypes.c_size_t]
+        L.pixsht_host_free.argtypes = [vp]
+        L.pixsht_host_register.argtypes = [vp, ctypes.c_size_t]
+        L.pixsht_host_unregister.argtypes = [vp]
         L.pixsht_plan_destroy.argtypes = [vp]
         L.pixsht_plan_destroy.restype = None
         L.pixsht_execute.argtypes = [vp, i32, i32, pvp, pvp, i32]

@@ -21,7 +21,9 @@ def _ptr_array(ptrs):
 class Plan:
     """Owner of a pixsht_plan handle (include/pixsht.h)."""
 
-    def __init__(self, band, lmax, mmax=None, dtype=np.float64, device=0, lib=None):
+    def __init__(self, band, lmax, mmax=None, dtype=np.float64, device=0, lib=None, devices=None):
+        """devices: list of GPU indices -> a multi-GPU plan (pixsht_plan_create_multi: one process drives them all behind the
+        same execute call); None -> a single-GPU plan on `device`."""
         self.lib = get_lib() if lib is None else lib
         self.band, self.lmax, self.mmax = band, int(lmax), int(lmax if mmax is None else mmax)
         self.dtype = np.dtype(dtype)
@@ -31,8 +33,13 @@ class Plan:
         g = Geom(band.nphi, band.nrings_total, band.ring_first, band.nrings, band.nx, int(band.flipx), int(band.flipy), int(getattr(band, "ring_scheme", 0)),
                  band.phi0)
         h = ctypes.c_void_p()
-        self.lib.check(self.lib.lib.pixsht_plan_create(ctypes.byref(h), ctypes.byref(g), self.lmax, self.mmax,
-                                                       F64 if self.dtype == np.float64 else F32, device))
+        dt = F64 if self.dtype == np.float64 else F32
+        self.devices = None if devices is None else [int(d) for d in devices]
+        if self.devices is None:
+            self.lib.check(self.lib.lib.pixsht_plan_create(ctypes.byref(h), ctypes.byref(g), self.lmax, self.mmax, dt, device))
+        else:
+            arr = (ctypes.c_int * len(self.devices))(*self.devices)
+            self.lib.check(self.lib.lib.pixsht_plan_create_multi(ctypes.byref(h), ctypes.byref(g), self.lmax, self.mmax, dt, len(self.devices), arr))
         self.handle = h
         self.nalm = int(self.lib.lib.pixsht_nalm(self.lmax, self.mmax))
 
@@ -72,6 +79,21 @@ class Plan:
         self.execute_batch_ptrs(MAP2ALM, [a.ctypes.data for a in alms], [m.ctypes.data for m in maps])
         return alms
 
+    def shards(self):
+        """Multi-GPU plan: [(device, first band ring, ring count, m values)] per shard."""
+        out = []
+        for d in range(len(self.devices or [])):
+            info = (ctypes.c_int32 * 4)()
+            self.lib.check(self.lib.lib.pixsht_multi_shard(self.handle, d, info, None))
+            ml = (ctypes.c_int32 * max(1, info[3]))()
+            self.lib.check(self.lib.lib.pixsht_multi_shard(self.handle, d, info, ml))
+            out.append((int(info[0]), int(info[1]), int(info[2]), np.array(ml[:info[3]], dtype=np.int32)))
+        return out
+
+    def execute_sharded_ptrs(self, direction, ncomp, alm_ptrs, map_ptrs):
+        """alm_ptrs / map_ptrs: flat lists [shard][component] of device pointers (pixsht_execute_sharded)."""
+        self.lib.check(self.lib.lib.pixsht_execute_sharded(self.handle, direction, ncomp, _ptr_array(alm_ptrs), _ptr_array(map_ptrs)))
+
     def timings(self):
         t = (ctypes.c_double * 8)()
         self.lib.check(self.lib.lib.pixsht_get_timings(self.handle, t))
@@ -86,7 +108,7 @@ class Plan:
     def info(self):
         v = (ctypes.c_int32 * 16)()
         self.lib.check(self.lib.lib.pixsht_plan_info(self.handle, v))
-        keys = ["nphi", "nrings", "lmax", "mmax", "dtype", "device", "npairs", "sm_count", "nfft", "launches", "R0", "R2", "R0a", "R2a"]
+        keys = ["nphi", "nrings", "lmax", "mmax", "dtype", "device", "npairs", "sm_count", "nfft", "launches", "R0", "R2", "R0a", "R2a", "ndev"]
         return dict(zip(keys, list(v)))
 
     def weights(self):

@@ -126,6 +126,15 @@ def test_emu_replay_batched(emu_default):
     g.test_batched_spin0_equals_single_transforms(3, np.float32, res_deg=10.0, lmax=14)      # groups of 2 + 1
 
 
+def test_emu_replay_multi_gpu_plan(emu_default, monkeypatch):
+    """The one-process multi-GPU plan (pixsht_plan_create_multi) on the emulation build: partition, per-m address table, slabs,
+    per-family pipeline and the batch dealing, against the single plan and the oracle."""
+    import test_gpu_parity as g
+    monkeypatch.setenv("PIXSHT_MULTI_SEGS", "2")
+    g.test_multi_gpu_plan_equals_single_gpu_plan(3, res_arcmin=600.0, lmax=18, reps=1)
+    g.test_multi_gpu_plan_partial_sky_flips_and_oracle(res_deg=10.0, lmax=14, nshard=2)
+
+
 @pytest.mark.parametrize("nphi,force_global", [(45, 0), (71, 0), (134, 0), (72, 1)])
 def test_emu_replay_general_ring_lengths(emu_default, monkeypatch, nphi, force_global):
     import test_gpu_parity as g

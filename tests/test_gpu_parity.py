@@ -419,6 +419,123 @@ def test_multi_gpu_peer_memory_pipeline_matches_single_gpu(tmp_path):
     plan.close()
 
 
+# ---- one process, several GPUs behind the C ABI (pixsht_plan_create_multi) ---------------------------------------------------
+def _shard_devices(nshard):
+    """nshard shards on the GPUs of the box, round-robin (a one-GPU box runs every shard on device 0: same code path --
+    partition, per-m address table, slabs, event barriers -- without NVLink)."""
+    k = max(1, get_lib().device_count())
+    return [i % k for i in range(nshard)]
+
+
+@pytest.mark.parametrize("nshard", [2, 3, 8])
+def test_multi_gpu_plan_equals_single_gpu_plan(nshard, res_arcmin=8.0, lmax=1350, reps=2):
+    """The one-process multi-GPU plan against the single-GPU plan on the same inputs: synthesis bit for bit (each (m, ring)
+    sum is the same sequence of FMAs wherever it runs), analysis to rounding (atomic accumulation order); IQU, T alone, QU
+    alone, Float32, partial-sky / flipped bands, and a batch dealt over the shards."""
+    shape, wcs = fullsky_geometry(res_arcmin * arcminute)
+    band = pixsht.sht_band(shape, wcs)
+    single = Plan(band, lmax)
+    multi = Plan(band, lmax, devices=_shard_devices(nshard))
+    assert multi.info()["ndev"] == nshard
+    sh = multi.shards()
+    assert sorted(np.concatenate([s[3] for s in sh]).tolist()) == list(range(lmax + 1))      # every m exactly once
+    assert sum(s[2] for s in sh) == band.nrings and sh[0][1] == 0
+    alms = [synth_alm(lmax, lmax, 70 + c, spin2=c > 0) for c in range(3)]
+    for comps in ([0, 1, 2], [0], [1, 2]):
+        for _ in range(reps):                 # twice: buffers and events are reused
+            ref = single.alm2map([alms[c] for c in comps])
+            got = multi.alm2map([alms[c] for c in comps])
+            for a, b in zip(got, ref):
+                assert np.array_equal(a, b)
+            back_ref = single.map2alm(ref)
+            back = multi.map2alm(got)
+            for a, b in zip(back, back_ref):
+                assert rel_rms(a, b) < 1e-13
+    single.close(); multi.close()
+    # Float32 boundary, T only
+    s32 = Plan(band, lmax, dtype=np.float32)
+    m32 = Plan(band, lmax, dtype=np.float32, devices=_shard_devices(nshard))
+    a32 = alms[0].astype(np.complex64)
+    r = s32.alm2map([a32])[0]; g = m32.alm2map([a32])[0]
+    assert g.dtype == np.float32 and np.array_equal(g, r)
+    assert rel_rms(m32.map2alm([g])[0], s32.map2alm([r])[0]) < 1e-6
+    # a batch on a multi-GPU plan: whole transforms dealt to the shards
+    nb = nshard + 1
+    balm = [synth_alm(lmax, lmax, 500 + b).astype(np.complex64) for b in range(nb)]
+    bm = m32.alm2map_batch(balm)
+    for b in (0, nb - 1):
+        assert rel_rms(bm[b], s32.alm2map([balm[b]])[0]) < 2e-6
+    bb = m32.map2alm_batch(bm)
+    assert rel_rms(bb[nb - 1], s32.map2alm([bm[nb - 1]])[0]) < 2e-6
+    s32.close(); m32.close()
+
+
+def test_multi_gpu_plan_partial_sky_flips_and_oracle(res_deg=1.0, lmax=150, nshard=3):
+    """Cut-sky band (zero-padded rings, ring subset) and an unflipped geometry through the multi-GPU plan, against the oracle."""
+    shape, wcs = fullsky_geometry(res_deg * degree)
+    full = Enmap(gen_spin0(shape, 1.5), wcs)
+    nx, ny = shape
+    for sub in (full[nx // 9:nx - nx // 6, ny // 6:ny - ny // 3], full[::-1, ::-1]):
+        band = pixsht.sht_band(sub.shape, sub.wcs)
+        multi = Plan(band, lmax, devices=_shard_devices(nshard))
+        got = multi.map2alm([np.asfortranarray(sub.data)])[0]
+        assert rel_rms(got, oracle_map2alm(sub, lmax)[0]) < TOL64
+        alm = synth_alm(lmax, lmax, 77)
+        mp = multi.alm2map([alm])[0]
+        assert rel_rms(mp, oracle_alm2map(alm[None], sub.shape, sub.wcs, lmax)[:, :, 0]) < TOL64
+        multi.close()
+
+
+def test_multi_gpu_plan_sharded_device_buffers(res_arcmin=8.0, lmax=1350, nshard=2):
+    """pixsht_execute_sharded: data already distributed (each shard holds its alm columns and its slab of rows on its GPU)."""
+    import torch
+    shape, wcs = fullsky_geometry(res_arcmin * arcminute)
+    band = pixsht.sht_band(shape, wcs)
+    devs = _shard_devices(nshard)
+    single = Plan(band, lmax)
+    multi = Plan(band, lmax, devices=devs)
+    alms = [synth_alm(lmax, lmax, 70 + c, spin2=c > 0) for c in range(3)]
+    ref = single.alm2map(alms)
+    back_ref = single.map2alm(ref)
+    sh = multi.shards()
+    d_alm, d_slab, d_out = [], [], []
+    for (dev, r0, nr, ml) in sh:
+        td = torch.device("cuda", dev)
+        mask = np.zeros(single.nalm, dtype=bool)
+        for m in ml:
+            mask[alm_index(lmax, int(m), int(m)):alm_index(lmax, lmax, int(m)) + 1] = True
+        d_alm.append([torch.from_numpy(np.where(mask, a, 7.0 + 0j)).to(td) for a in alms])      # foreign columns hold junk
+        d_slab.append([torch.zeros(nr * band.nx, dtype=torch.float64, device=td) for _ in alms])
+        d_out.append([torch.full((single.nalm,), 3.0 + 0j, dtype=torch.complex128, device=td) for _ in alms])
+    flat = lambda x: [t.data_ptr() for per in x for t in per]
+    multi.execute_sharded_ptrs(_lib.ALM2MAP, 3, flat(d_alm), flat(d_slab))
+    for k, (dev, r0, nr, ml) in enumerate(sh):
+        a, b = (band.nrings - r0 - nr, band.nrings - r0) if band.flipy else (r0, r0 + nr)
+        for c in range(3):
+            assert np.array_equal(d_slab[k][c].cpu().numpy().reshape(nr, band.nx).T, ref[c][:, a:b])
+    multi.execute_sharded_ptrs(_lib.MAP2ALM, 3, flat(d_out), flat(d_slab))
+    for k, (dev, r0, nr, ml) in enumerate(sh):
+        for c in range(3):
+            o = d_out[k][c].cpu().numpy()
+            for m in (int(ml[0]), int(ml[-1])):
+                sl = slice(alm_index(lmax, m, m), alm_index(lmax, lmax, m) + 1)
+                assert rel_rms(o[sl], back_ref[c][sl]) < 1e-12
+    single.close(); multi.close()
+
+
+def test_c3_size_multi_gpu_plan_sampled_parity():
+    """BASELINE config C3 through the one-process multi-GPU plan (every GPU of the box, at least two shards): sampled rings and
+    sampled m against the long-double oracle + adjointness, as for the single-GPU plan."""
+    shape, wcs = fullsky_geometry(2.0 * arcminute)
+    lmax = 5400
+    band = pixsht.sht_band(shape, wcs)
+    plan = Plan(band, lmax, devices=_shard_devices(max(2, min(8, get_lib().device_count()))))
+    _sampled_checks(plan, band, shape, wcs, lmax, [synth_alm(lmax, lmax, 3000)], 0, 1201, 150, 1777, 5, 31)
+    _sampled_checks(plan, band, shape, wcs, lmax, [synth_alm(lmax, lmax, 3001, spin2=True), synth_alm(lmax, lmax, 3002, spin2=True)],
+                    2, 1201, 600, 1777, 2, 32)
+    plan.close()
+
+
 # ---- edge cases: degenerate band limits, tiny and ragged bands, argument errors --------------------------------------------
 @pytest.mark.parametrize("lmax,mmax", [(0, 0), (1, 1), (1, 0), (2, 2), (18, 0), (18, 3), (40, 40)])
 def test_edge_band_limits(lmax, mmax):

@@ -150,10 +150,89 @@ def cpu_baseline(wl, target_s=12.0, maps=None, alms=None):
     if stride2 < stride:
         leg, fft, nsel = run(stride2); stride = stride2
     full_ms = 1e3 * (leg * nm / nsel + fft)
-    return {"value": full_ms, "unit": "ms", "cores": thr, "kind": "port",
-            "sample": "oracle/sht_cpu.c (libsharp2-style CPU implementation: ring-pair folding, scaled seek, pruning, OpenMP over m, "
-                      "SIMD over rings; not libsharp2 itself): alm2map + map2alm on every %d-th m (%d of %d m, Legendre %.1f s, "
-                      "extrapolated linearly in m) + all ring FFTs (%.1f s)" % (stride, nsel, nm, leg, fft)}
+    out = {"value": full_ms, "unit": "ms", "cores": thr, "kind": "port",
+           "sample": "oracle/sht_cpu.c (libsharp2-style CPU implementation: ring-pair folding, scaled seek, pruning, OpenMP over m, "
+                     "SIMD over rings; not libsharp2 itself): alm2map + map2alm on every %d-th m (%d of %d m, Legendre %.1f s, "
+                     "extrapolated linearly in m) + all ring FFTs (%.1f s)" % (stride, nsel, nm, leg, fft)}
+    # how good a stand-in for libsharp2 is it?  Its Legendre rate (un-pruned SURVEY 8(d) flop count, as for the GPU roofline)
+    # against the host's measured FP64 FMA peak on the same threads.  libsharp2's hand-vectorised kernels reach ~50-60 % of peak
+    # on the executed (pruned, ~2/3 of nominal) work, i.e. ~0.8-0.9 of peak in these nominal units.
+    try:
+        peak = cpu.fma_peak_gflops(0.4)
+        nom = 2.0 * algorithmic_flops(n, band.nrings, nc)
+        rate = nom / max(leg * nm / nsel, 1e-9) * 1e-9
+        out.update({"host_fma_peak_gflops": peak, "legendre_gflops_nominal": rate, "frac_of_host_peak": rate / peak})
+    except Exception as ex:
+        out["host_fma_peak_error"] = repr(ex)[:100]
+    return out
+
+
+def cpu_calibration(target="C3"):
+    """The sampling of cpu_baseline checked against a FULL run (every m) of the same code on a config where that is affordable:
+    ratio = full / extrapolated."""
+    import pixsht
+    from oracle import get_cpu_sht, cc_geometry, nalm as nalm_of
+    wl = WORKLOADS[target]
+    est = cpu_baseline(wl, target_s=3.0)
+    cpu = get_cpu_sht()
+    res = wl["res_arcmin"] * pixsht.arcminute
+    shape, wcs = pixsht.fullsky_geometry(res)
+    band = pixsht.sht_band(shape, wcs)
+    lmax, nc = wl["lmax"], wl["ncomp"]
+    theta, w = cc_geometry(band.nrings_total, band.nphi)
+    alms, maps = _CPU_INPUTS[(wl["res_arcmin"], lmax, nc)]
+    jobs = [(0, [0])] if nc == 1 else ([(2, [0, 1])] if nc == 2 else [(0, [0]), (2, [1, 2])])
+    t = 0.0
+    for spin, idx in jobs:
+        cpu.alm2map(np.stack([alms[i] for i in idx]), theta, band.phi0, band.nphi, lmax, spin=spin)
+        t += sum(cpu.last_times)
+        cpu.map2alm(np.stack([maps[i] for i in idx]), theta, w, band.phi0, lmax, spin=spin)
+        t += sum(cpu.last_times)
+    _CPU_INPUTS.clear()
+    return {"workload": target, "full_run_ms": 1e3 * t, "sampled_estimate_ms": est["value"], "full_over_estimate": 1e3 * t / est["value"],
+            "cores": est["cores"]}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# parity of the timed path's own outputs against the long-double oracle (the checker; after the timed region)
+# ------------------------------------------------------------------------------------------------------------------
+def parity_sampled(band, lmax, nc, alms, maps, outs, f64=True, nrings_sample=3, m_sample=2):
+    """alms[c]: the step's input alm (host, complex); maps[c]: its alm2map output as (nrings, nx) arrays in the caller's row
+    order; outs[c]: the map2alm output of those maps.  Checks alm2map on sampled rings and map2alm on sampled m against
+    oracle/sht_oracle.c (80-bit long double, naive sums).  Returns rel-RMS errors over the samples."""
+    from oracle import get_oracle, cc_geometry, alm_index
+    orc = get_oracle("ld")
+    theta, w = cc_geometry(band.nrings_total, band.nphi, band.ring_first, band.nrings)
+    nr = band.nrings
+    rings = sorted(set(int(round(x)) for x in np.linspace(nr * 0.07, nr * 0.5, nrings_sample)))
+    msel = sorted(set(int(round(x)) for x in np.linspace(lmax * 0.11, lmax * 0.83, m_sample)))
+    jobs = [(0, [0])] if nc == 1 else ([(2, [0, 1])] if nc == 2 else [(0, [0]), (2, [1, 2])])
+    num = den = 0.0
+    anum = aden = 0.0
+    fy = slice(None, None, -1) if band.flipy else slice(None)
+    fx = slice(None, None, -1) if band.flipx else slice(None)
+    for spin, idx in jobs:
+        a = np.stack([np.asarray(alms[c]).astype(np.complex128) for c in idx])
+        ref = orc.alm2map(a, theta[rings], band.phi0, band.nphi, lmax, spin=spin)
+        for k, c in enumerate(idx):
+            for i, r in enumerate(rings):
+                row = (nr - 1 - r) if band.flipy else r
+                g = np.asarray(maps[c][row], dtype=np.float64)[fx]
+                num += float(np.sum((g - ref[k, i, :band.nx]) ** 2)); den += float(np.sum(ref[k, i, :band.nx] ** 2))
+        bandmaps = np.zeros((len(idx), nr, band.nphi))
+        for k, c in enumerate(idx):
+            bandmaps[k, :, :band.nx] = np.asarray(maps[c], dtype=np.float64)[fy, fx]
+        for m in msel:
+            # every (lmax+1)-th m starting at m: exactly this m
+            refa = orc.map2alm(bandmaps, theta, w, band.phi0, lmax, spin=spin, m_stride=lmax + 1, m_offset=m)
+            sl = slice(alm_index(lmax, m, m), alm_index(lmax, lmax, m) + 1)
+            for k, c in enumerate(idx):
+                got = np.asarray(outs[c][sl]).astype(np.complex128)
+                anum += float(np.sum(np.abs(got - refa[k][sl]) ** 2)); aden += float(np.sum(np.abs(refa[k][sl]) ** 2))
+    tol = 1e-10 if f64 else 1e-5
+    e1, e2 = math.sqrt(num / den), math.sqrt(anum / aden)
+    return {"alm2map_rel_rms": e1, "map2alm_rel_rms": e2, "tolerance": tol, "ok": bool(e1 <= tol and e2 <= tol),
+            "checker": "oracle/sht_oracle.c (long double)", "rings": rings, "m": msel}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -178,6 +257,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pageable", action="store_true")
+    ap.add_argument("--no-calibration", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -262,6 +345,9 @@ def main():
 
     launches = 0
     stage = {}
+    parity = None
+    e2e_pageable = None
+    one_process = None
     if world == 1:
         plan = Plan(band, lmax, dtype=npdt)
         lib.check(lib.lib.pixsht_plan_set_stream(plan.handle, ctypes.c_void_p(stream.cuda_stream), 1))
@@ -326,6 +412,27 @@ def main():
             e2e["host_vs_device_maxabs"] = chk
             host_maps = [m.numpy().reshape(band.nrings, band.nx).astype(np.float64, copy=False) for m in h_map]
             host_alms = [a.numpy().astype(np.complex128, copy=False) for a in h_alm]
+            # the same call on ordinary (pageable) host arrays -- what a caller who did not allocate through pixsht_host_alloc /
+            # pixsht_host_register gets
+            if not args.no_pageable:
+                p_alm = [np.array(a.numpy()) for a in h_alm]
+                p_out = [np.empty_like(a) for a in p_alm]
+                p_map = [np.empty(band.nx * band.nrings, dtype=npdt) for _ in range(nc)]
+
+                def step_pageable():
+                    plan.execute_ptrs(ALM2MAP, [a.ctypes.data for a in p_alm], [m.ctypes.data for m in p_map], HOST)
+                    plan.execute_ptrs(MAP2ALM, [a.ctypes.data for a in p_out], [m.ctypes.data for m in p_map], HOST)
+
+                ms_pg = timed(step_pageable, 1, max(1, min(args.steps, 3)))
+                e2e_pageable = {"value": ms_pg, "unit": "ms", "ratio_to_pinned": ms_pg / ms_e2e,
+                                "api": "pixsht_execute(..., PIXSHT_HOST) on pageable numpy arrays (staged through the library's pinned "
+                                       "bounce buffers by its copy threads)",
+                                "maxabs_vs_pinned": float(np.max(np.abs(p_out[0] - h_out[0].numpy())))}
+                del p_alm, p_out, p_map
+            # parity of the timed path's own output (the host-pointer call) against the long-double oracle
+            if not args.no_parity:
+                parity = parity_sampled(band, lmax, nc, [a.numpy() for a in h_alm], [m.numpy().reshape(band.nrings, band.nx) for m in h_map],
+                                        [a.numpy() for a in h_out], f64=f64)
         nrings = band.nrings
         plan_info = plan.info()
     else:
@@ -355,32 +462,111 @@ def main():
                              "for the slowest rank)"}
         nfam = 2 if nc == 3 else 1   # spin families: each costs a prep + a synthesis launch one way and an analysis launch back
         launches = (3 * nfam + 2) * args.steps   # + one FFT launch per direction; per rank
+        # ---- the ONE-PROCESS path (include/pixsht.h: pixsht_plan_create_multi): rank 0 alone drives all N GPUs through the
+        # blocking C-ABI call on whole host arrays -- what a Julia caller gets.  The other ranks idle at a host-side (gloo)
+        # barrier meanwhile, so that nothing of theirs runs on the GPUs.
+        gloo = dist.new_group(backend="gloo")
+        shm = "/dev/shm/pixsht_bench_%d_" % int(os.environ.get("MASTER_PORT", "0"))
         e2e = None
-        if not args.no_e2e:
-            # each rank moves only what it owns: its alm columns (packed) and its rows of the map; the copies overlap the
-            # stages one spin family at a time (ShardedSHT.alm2map_host / map2alm_host)
-            cols = sht.alm_columns()
-            idx = torch.cat([torch.arange(s, e, device=device) for (s, e) in cols])
-            h_alm = [torch.empty(idx.numel(), dtype=cdt).pin_memory() for _ in range(nc)]
-            h_out = [torch.empty(idx.numel(), dtype=cdt).pin_memory() for _ in range(nc)]
-            h_slab = [torch.empty((b - a) * band.nx, dtype=rdt).pin_memory() for _ in range(nc)]
+        nrings = band.nrings
+        torch.cuda.synchronize(device)
+        dist.barrier(group=gloo)
+        if rank == 0 and not args.no_e2e:
+            import time
+            mplan = Plan(band, lmax, dtype=npdt, devices=list(range(world)))
+            h_alm = [torch.empty(nalm, dtype=cdt).pin_memory() for _ in range(nc)]
+            h_out = [torch.empty(nalm, dtype=cdt).pin_memory() for _ in range(nc)]
+            h_map = [torch.empty(band.nx * band.nrings, dtype=rdt).pin_memory() for _ in range(nc)]
             for h, d in zip(h_alm, d_alm):
-                h.copy_(d.index_select(0, idx))
+                h.copy_(d)
             torch.cuda.synchronize(device)
+            pa, po, pm = [a.data_ptr() for a in h_alm], [a.data_ptr() for a in h_out], [m.data_ptr() for m in h_map]
 
             def step_host():
-                sht.alm2map_host(h_alm, h_slab, d_alm, d_slab)
-                sht.map2alm_host(h_slab, h_out, d_slab, d_out)
-                torch.cuda.current_stream(device).synchronize()
+                mplan.execute_ptrs(ALM2MAP, pa, pm, HOST)
+                t1 = mplan.timings()["compute_span"]
+                mplan.execute_ptrs(MAP2ALM, po, pm, HOST)
+                return t1 + mplan.timings()["compute_span"]
 
-            ms_e2e = timed(step_host, min(args.warmup, 3), args.steps)
-            per_rank = (sum(x.numel() * x.element_size() for x in h_alm) + sum(x.numel() * x.element_size() for x in h_slab))
-            tb = torch.tensor([per_rank], device=device, dtype=torch.float64)
-            dist.all_reduce(tb)
-            h2d = d2h = int(tb.item())
-            e2e = {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "api": "pixsht.distributed.ShardedSHT.alm2map_host / map2alm_host with per-rank pinned host shards"}
-        nrings = band.nrings
+            for _ in range(min(args.warmup, 3)):
+                step_host()
+            t0 = time.perf_counter()
+            span = 0.0
+            for _ in range(args.steps):
+                span += step_host()
+            ms_e2e = 1e3 * (time.perf_counter() - t0) / args.steps
+            nbytes = sum(x.numel() * x.element_size() for x in h_alm) + sum(x.numel() * x.element_size() for x in h_map)
+            e2e = {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                   "device_span_ms": span / args.steps,
+                   "timing": "host wall clock around the blocking calls (they return when the caller's arrays are complete); "
+                             "device_span_ms = max over the GPUs of the CUDA-event span of each call",
+                   "api": "pixsht_execute on a pixsht_plan_create_multi plan: one process, %d GPUs, whole pinned host arrays "
+                          "(each GPU copies its alm columns / map rows itself); no torch, no NCCL on this path" % world}
+            # the same plan with the data already distributed over the GPUs (nothing copied): pixsht_execute_sharded
+            try:
+                sh = mplan.shards()
+                sa, sm, so = [], [], []
+                for (dv, r0, nr, ml) in sh:
+                    td = torch.device("cuda", dv)
+                    sa.append([a.to(td) for a in d_alm])
+                    sm.append([torch.empty(nr * band.nx, dtype=rdt, device=td) for _ in range(nc)])
+                    so.append([torch.empty(nalm, dtype=cdt, device=td) for _ in range(nc)])
+                flat = lambda x: [t.data_ptr() for per in x for t in per]
+                fa, fm, fo = flat(sa), flat(sm), flat(so)
+
+                def step_sharded():
+                    mplan.execute_sharded_ptrs(ALM2MAP, nc, fa, fm)
+                    t1 = mplan.timings()["compute_span"]
+                    mplan.execute_sharded_ptrs(MAP2ALM, nc, fo, fm)
+                    return t1 + mplan.timings()["compute_span"]
+
+                for _ in range(2):
+                    step_sharded()
+                t0 = time.perf_counter(); span = 0.0
+                for _ in range(args.steps):
+                    span += step_sharded()
+                one_process = {"device_resident_ms": 1e3 * (time.perf_counter() - t0) / args.steps, "device_span_ms": span / args.steps,
+                               "api": "pixsht_execute_sharded: shards of alm / map resident on their GPUs, one process"}
+                del sa, sm, so
+            except Exception as ex:
+                one_process = {"error": repr(ex)[:200]}
+            # parity of the one-process path's own output against the long-double oracle
+            if not args.no_parity:
+                parity = parity_sampled(band, lmax, nc, [a.numpy() for a in h_alm], [m.numpy().reshape(band.nrings, band.nx) for m in h_map],
+                                        [a.numpy() for a in h_out], f64=f64)
+            for c in range(nc):
+                np.save(shm + "map%d.npy" % c, h_map[c].numpy())
+                np.save(shm + "alm%d.npy" % c, h_out[c].numpy())
+            mplan.close()
+        dist.barrier(group=gloo)
+        # ---- every rank: its device-resident slab / alm columns (the torchrun pipeline timed as `value`) against the one-process
+        # result: the same (m, ring) sums wherever they run -> maps bit for bit, alm to rounding (atomic accumulation order)
+        cross = torch.zeros(2, dtype=torch.float64, device=device)
+        if not args.no_e2e and os.path.exists(shm + "map0.npy"):
+            for c in range(nc):
+                ref = np.load(shm + "map%d.npy" % c, mmap_mode="r")[a * band.nx:b * band.nx]
+                got = d_slab[c].cpu().numpy()
+                cross[0] = max(float(cross[0]), float(np.max(np.abs(got - ref))) / max(float(np.max(np.abs(ref))), 1e-300))
+                refa = np.load(shm + "alm%d.npy" % c, mmap_mode="r")
+                o = d_out[c].cpu().numpy()
+                for (s0, s1) in sht.alm_columns()[::max(1, sht.nm // 16)]:
+                    den = max(float(np.sqrt(np.sum(np.abs(refa[s0:s1]) ** 2))), 1e-300)
+                    cross[1] = max(float(cross[1]), float(np.sqrt(np.sum(np.abs(o[s0:s1] - refa[s0:s1]) ** 2))) / den)
+        dist.all_reduce(cross, op=dist.ReduceOp.MAX)
+        dist.barrier(group=gloo)
+        if rank == 0:
+            for c in range(nc):
+                for nm_ in ("map%d.npy" % c, "alm%d.npy" % c):
+                    try:
+                        os.remove(shm + nm_)
+                    except OSError:
+                        pass
+            if parity is not None:
+                parity["ranks_vs_one_process"] = {"map_maxabs_rel": float(cross[0]), "alm_rel_rms_max": float(cross[1]),
+                                                  "note": "each torchrun rank's slab and sampled alm columns (the pipeline timed as `value`) "
+                                                          "against the one-process result that the oracle check above covers"}
+                tol = parity["tolerance"]
+                parity["ok"] = bool(parity["ok"] and float(cross[0]) <= tol and float(cross[1]) <= tol)
         plan_info = {"npairs": math.ceil(nrings / 2), "sm_count": None}
         host_maps = host_alms = None
         kern_ms, work = None, None
@@ -451,14 +637,51 @@ def main():
             "transforms_per_s": 2.0 * 1e3 / ms_dev, "plan": {k: plan_info.get(k) for k in ("npairs", "sm_count", "R0", "R2", "R0a", "R2a")}}
     if e2e is not None:
         line["e2e"] = e2e
+    if e2e_pageable is not None:
+        line["e2e_pageable"] = e2e_pageable
+    if parity is not None:
+        line["parity"] = parity
+    if one_process is not None:
+        line["one_process"] = one_process
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(wl, maps=host_maps, alms=host_alms)
+            if args.workload in ("C4", "C5") and not args.no_calibration:
+                del host_maps, host_alms
+                line["cpu_baseline"]["calibration"] = cpu_calibration("C3")
         except Exception as ex:  # never lose the GPU numbers to a baseline problem
-            line["cpu_baseline"] = {"error": repr(ex)}
+            line["cpu_baseline"] = dict(line.get("cpu_baseline") or {}, error=repr(ex))
+    if world == 1 and args.workload == "C4" and not args.no_extras:
+        line["extra"] = run_extras(args)
     print(json.dumps(line))
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        raise SystemExit("bench.py: PARITY FAILURE against the oracle: %s" % json.dumps(parity))
+
+
+def run_extras(args):
+    """The other single-GPU BASELINE configs, measured in the same driver run (each in a fresh process, after this process has
+    released the GPU's memory is not required: they are small): C3 (2' IQU F64), C2 (4' T F32) and the 64-map sweep C2x64.
+    Returns {workload: trimmed bench line}."""
+    out = {}
+    for name in ("C3", "C2", "C2x64"):
+        cmd = [sys.executable, os.path.abspath(__file__), "--workload", name, "--steps", "3", "--warmup", "3", "--no-cpu-baseline",
+               "--no-pageable", "--no-extras"]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+            d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+            keep = {k: d.get(k) for k in ("value", "unit", "ms_per_step", "dtype", "clocks", "gpu_launches", "stages", "e2e", "parity",
+                                          "sims_per_s", "one_by_one_ms", "batch_speedup", "transforms_per_s")}
+            keep["config"] = d.get("config", {}).get("workload")
+            rf = d.get("roofline") or {}
+            keep["roofline"] = {k: rf.get(k) for k in ("bound", "kernel", "achieved", "peak", "unit", "frac", "fp64_pipe_utilisation")}
+            if d.get("roofline_fft"):
+                keep["roofline_fft"] = {k: d["roofline_fft"].get(k) for k in ("achieved", "peak", "unit", "frac")}
+            out[name] = keep
+        except Exception as ex:
+            out[name] = {"error": repr(ex)[:200]}
+    return out
 
 
 def bench_batch(args, wl, config, torch, pixsht, Plan, lib, band, lmax, device, stream, rdt, cdt, npdt, local_rank, MAP2ALM, ALM2MAP, DEVICE):

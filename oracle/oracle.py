@@ -153,6 +153,8 @@ class CpuSht:
         L.cpu_map2alm.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                   pp, pp, ctypes.c_int, ctypes.c_int, dp]
         L.cpu_num_threads.restype = ctypes.c_int
+        L.cpu_fma_peak_gflops.argtypes = [ctypes.c_int, ctypes.c_double]
+        L.cpu_fma_peak_gflops.restype = ctypes.c_double
         L.cpu_set_threads.argtypes = [ctypes.c_int]
         L.cpu_set_threads.restype = None
         self.last_times = (0.0, 0.0)
@@ -169,6 +171,10 @@ class CpuSht:
     @property
     def threads(self):
         return int(self.lib.cpu_num_threads())
+
+    def fma_peak_gflops(self, seconds=0.5):
+        """Measured FP64 FMA peak of the host on the threads the port uses (GFLOP/s, 1 FMA = 2 flop)."""
+        return float(self.lib.cpu_fma_peak_gflops(self.threads, float(seconds)))
 
     def alm2map(self, alms, theta, phi0, nphi, lmax, mmax=None, spin=0, m_stride=1, m_offset=0):
         mmax = lmax if mmax is None else mmax

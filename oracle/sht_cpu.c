@@ -522,6 +522,37 @@ int cpu_map2alm(int spin, int nrings, const double *theta, const double *wgt, do
 }
 
 /* torchrun exports OMP_NUM_THREADS=1 to its workers; the timed baseline must use the cores it claims */
+/* Host FP64 FMA peak (GFLOP/s, 1 FMA = 2 flop) on `nthreads` threads: register-resident independent FMA chains, written for the
+ * compiler's vectoriser like the Legendre loops above, so that it measures the SIMD width this build was compiled for
+ * (-march=native).  bench.py quotes the port's own rate against it (cpu_baseline.frac_of_host_peak). */
+double cpu_fma_peak_gflops(int nthreads, double seconds)
+{
+    enum { NV = 64 };          /* 64 doubles = 8 AVX-512 / 16 AVX2 registers of independent chains */
+    double total = 0.0, tmax = 0.0;
+    if (nthreads < 1) nthreads = 1;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nthreads) reduction(+ : total) reduction(max : tmax)
+#endif
+    {
+        double a[NV] __attribute__((aligned(64))), sink = 0.0;
+        for (int i = 0; i < NV; ++i) a[i] = 1.0 + 1e-9 * i;
+        const double mlt = 1.0 - 1e-12, add = 1e-13;
+        double t0 = now_s(), t1 = t0;
+        long iters = 0;
+        do {
+            for (int r = 0; r < 4096; ++r)
+#pragma GCC ivdep
+                for (int i = 0; i < NV; ++i) a[i] = a[i] * mlt + add;
+            iters += 4096;
+            t1 = now_s();
+        } while (t1 - t0 < seconds);
+        for (int i = 0; i < NV; ++i) sink += a[i];
+        total += 2.0 * (double)NV * (double)iters + (sink == 12345.678 ? 1.0 : 0.0);
+        tmax = t1 - t0;
+    }
+    return tmax > 0.0 ? total / tmax * 1e-9 : 0.0;
+}
+
 void cpu_set_threads(int n)
 {
 #ifdef _OPENMP

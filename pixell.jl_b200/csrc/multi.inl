@@ -278,6 +278,8 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
     }
     const int K = sharded ? 1 : M->pieces;
     int rc;
+    bool pg_alm[3] = {false, false, false}, pg_map[3] = {false, false, false};   // pageable arrays: staged by each shard's copy threads
+    if (!sharded) for (int c = 0; c < ncomp; ++c) { pg_alm[c] = host_is_pageable(alms[c]); pg_map[c] = host_is_pageable(maps[c]); }
 
     if (direction == PIXSHT_ALM2MAP) {
         // ---- inputs: each shard's alm columns, family by family; the first family in m pieces of equal work ----
@@ -295,8 +297,8 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
                             cudaError_t ce = cudaSuccess;
                             multi_for_runs(P, D, sg.first, sg.second, [&](long long i0, long long i1) {
                                 if (ce == cudaSuccess)
-                                    ce = cudaMemcpyAsync((char*)V[d].dalm[c] + (size_t)i0 * 2 * esz, (const char*)alms[c] + (size_t)i0 * 2 * esz,
-                                                         (size_t)(i1 - i0) * 2 * esz, cudaMemcpyDefault, S->s_h2d);
+                                    ce = host_copy_in(S, pg_alm[c], (char*)V[d].dalm[c] + (size_t)i0 * 2 * esz, (const char*)alms[c] + (size_t)i0 * 2 * esz,
+                                                      (size_t)(i1 - i0) * 2 * esz, S->s_h2d);
                             });
                             MCU(ce);
                         }
@@ -345,7 +347,7 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
                     MCU(cudaEventRecord(e, sc));
                     MCU(cudaStreamWaitEvent(S->s_d2h, e, 0));
                     for (int c = F.cb; c < F.cb + F.cn; ++c)
-                        MCU(cudaMemcpyAsync((char*)maps[c] + V[d].row_off, V[d].dslab[c], V[d].slab_bytes, cudaMemcpyDefault, S->s_d2h));
+                        MCU(host_copy_out(S, pg_map[c], (char*)maps[c] + V[d].row_off, V[d].dslab[c], V[d].slab_bytes, S->s_d2h));
                 }
             }
         }
@@ -366,7 +368,7 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
                     if (!sharded) {
                         size_t off, nb; ring_rows(P, ra, rb, esz, off, nb);
                         for (int c = fams[fi].cb; c < fams[fi].cb + fams[fi].cn; ++c)
-                            MCU(cudaMemcpyAsync((char*)V[d].dslab[c] + (off - V[d].row_off), (const char*)maps[c] + off, nb, cudaMemcpyDefault, S->s_h2d));
+                            MCU(host_copy_in(S, pg_map[c], (char*)V[d].dslab[c] + (off - V[d].row_off), (const char*)maps[c] + off, nb, S->s_h2d));
                     }
                     cudaEvent_t e = D.next_ev();
                     MCU(cudaEventRecord(e, S->s_h2d));
@@ -427,8 +429,8 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
                             cudaError_t ce = cudaSuccess;
                             multi_for_runs(P, D, j0, j1, [&](long long i0, long long i1) {
                                 if (ce == cudaSuccess)
-                                    ce = cudaMemcpyAsync((char*)alms[c] + (size_t)i0 * 2 * esz, (const char*)V[d].dalm[c] + (size_t)i0 * 2 * esz,
-                                                         (size_t)(i1 - i0) * 2 * esz, cudaMemcpyDefault, S->s_d2h);
+                                    ce = host_copy_out(S, pg_alm[c], (char*)alms[c] + (size_t)i0 * 2 * esz, (const char*)V[d].dalm[c] + (size_t)i0 * 2 * esz,
+                                                       (size_t)(i1 - i0) * 2 * esz, S->s_d2h);
                             });
                             MCU(ce);
                         }
@@ -455,6 +457,7 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
             if (cudaEventElapsedTime(&ms, D.e_t0, D.e_t1) == cudaSuccess) dev_ms = std::max(dev_ms, (double)ms);
             (void)cudaGetLastError();
         }
+        host_copies_done(S);
         P->launches += S->launches;
     }
     for (auto& t : P->timings) t = 0;
@@ -469,6 +472,7 @@ static void multi_quiesce(pixsht_multi* M)
     for (auto& D : M->dev) {
         if (cudaSetDevice(D.device) != cudaSuccess) continue;
         (void)cudaStreamSynchronize(D.sub->s_h2d); (void)cudaStreamSynchronize(D.sub->stream); (void)cudaStreamSynchronize(D.sub->s_d2h);
+        host_copies_done(D.sub);
     }
     (void)cudaGetLastError();
 }

@@ -110,6 +110,7 @@ struct pixsht_plan {
     int launches = 0;
     std::mutex mu;
     struct pixsht_multi* multi = nullptr;   // non-null: a multi-GPU plan (multi.inl); this object then carries the geometry only
+    void* stager = nullptr;                 // pixsht_stage::Stager, created when a call first sees a pageable host array (host_stage.inl)
 };
 struct pixsht_multi;
 static void multi_destroy(pixsht_multi* M);
@@ -220,6 +221,59 @@ static int env_int(const char* name, int dflt)
     const char* s = getenv(name);
     if (!s || !*s) return dflt;
     return atoi(s);
+}
+
+#include "host_stage.inl"
+
+// ---- host-side copies of the host-pointer calls: page-locked arrays go straight to cudaMemcpyAsync, pageable ones through the
+// plan's stager (host_stage.inl).  Enqueued on `s` either way. ----
+static bool host_is_pageable(const void* p)
+{
+#ifndef PIXSHT_EMU
+    static const int on = env_int("PIXSHT_STAGE", 1);
+    return on && pixsht_stage::is_pageable(p);
+#else
+    (void)p; return false;
+#endif
+}
+constexpr size_t STAGE_MIN_BYTES = 4u << 20;   // smaller copies are left to the driver's own pageable path
+static cudaError_t host_copy_in(pixsht_plan* P, bool pageable, void* dst_dev, const void* src_host, size_t n, cudaStream_t s)
+{
+#ifndef PIXSHT_EMU
+    if (pageable && n >= STAGE_MIN_BYTES) {
+        if (!P->stager) P->stager = new pixsht_stage::Stager();
+        return static_cast<pixsht_stage::Stager*>(P->stager)->h2d(dst_dev, src_host, n, s);
+    }
+#endif
+    (void)P; (void)pageable;
+    return cudaMemcpyAsync(dst_dev, src_host, n, cudaMemcpyDefault, s);
+}
+static cudaError_t host_copy_out(pixsht_plan* P, bool pageable, void* dst_host, const void* src_dev, size_t n, cudaStream_t s)
+{
+#ifndef PIXSHT_EMU
+    if (pageable && n >= STAGE_MIN_BYTES) {
+        if (!P->stager) P->stager = new pixsht_stage::Stager();
+        return static_cast<pixsht_stage::Stager*>(P->stager)->d2h(dst_host, src_dev, n, s);
+    }
+#endif
+    (void)P; (void)pageable;
+    return cudaMemcpyAsync(dst_host, src_dev, n, cudaMemcpyDefault, s);
+}
+// after the plan's streams have been synchronised: the copy threads have drained everything into the caller's arrays
+static void host_copies_done(pixsht_plan* P)
+{
+#ifndef PIXSHT_EMU
+    if (P->stager) static_cast<pixsht_stage::Stager*>(P->stager)->drain_wait();
+#else
+    (void)P;
+#endif
+}
+static void stager_destroy(pixsht_plan* P)
+{
+#ifndef PIXSHT_EMU
+    if (P->stager) delete static_cast<pixsht_stage::Stager*>(P->stager);
+#endif
+    P->stager = nullptr;
 }
 
 static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const std::vector<double>& wgt_or_empty, int N_cc, int ring_first,
@@ -517,6 +571,9 @@ extern "C" void pixsht_plan_destroy(pixsht_plan* P)
     if (P->multi) { multi_destroy(P->multi); P->multi = nullptr; delete P; return; }
     // may run from a GC finalizer thread, possibly after the CUDA context is gone: every call below tolerates failure
     (void)cudaSetDevice(P->device);
+    if (P->s_h2d) (void)cudaStreamSynchronize(P->s_h2d);
+    if (P->s_d2h) (void)cudaStreamSynchronize(P->s_d2h);
+    stager_destroy(P);
     P->d_x.release(); P->d_lsh_hi.release(); P->d_lsh_lo.release(); P->d_lch_hi.release(); P->d_lch_lo.release();
     P->d_mlim.release(); P->d_wgt.release(); P->d_ringN.release(); P->d_ringS.release();
     P->d_lg0_hi.release(); P->d_lg0_lo.release(); P->d_lg2_hi.release(); P->d_lg2_lo.release();
@@ -799,6 +856,7 @@ static void quiesce(pixsht_plan* P)
     if (P->stream) (void)cudaStreamSynchronize(P->stream);
     if (P->s_d2h) (void)cudaStreamSynchronize(P->s_d2h);
     (void)cudaGetLastError();
+    host_copies_done(P);
     g_err = keep;
 }
 
@@ -824,6 +882,8 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
             dalm64[c] = P->d_alm64[c].p;
         } else dalm64[c] = reinterpret_cast<double2*>(dalm[c]);
     }
+    bool pg_alm[3] = {false, false, false}, pg_map[3] = {false, false, false};   // pageable arrays are staged by the plan's copy threads
+    for (int c = 0; c < ncomp; ++c) { pg_alm[c] = host_is_pageable(alms[c]); pg_map[c] = host_is_pageable(maps[c]); }
     const PhaseRef ph = {P->d_phase.p, 0, 0};
     int ndep = 0;
     auto next_ev = [&]() { return P->dep[ndep++ % PIXSHT_NDEP]; };   // <= ~45 per call; the batch path recycles entries only after their waits were enqueued
@@ -850,12 +910,12 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
         auto col0 = [&](int m) { return (m > P->mmax) ? P->nalm : alm_index(P->lmax, m, m); };
         for (int k = 0; k < K0; ++k) {
             const long long i0 = col0(mb0[k]), i1 = col0(mb0[k + 1]);
-            if (i1 > i0) CU(cudaMemcpyAsync((char*)dalm[0] + (size_t)i0 * 2 * esz, (const char*)alms[0] + (size_t)i0 * 2 * esz, (size_t)(i1 - i0) * 2 * esz, cudaMemcpyHostToDevice, sh));
+            if (i1 > i0) CU(host_copy_in(P, pg_alm[0], (char*)dalm[0] + (size_t)i0 * 2 * esz, (const char*)alms[0] + (size_t)i0 * 2 * esz, (size_t)(i1 - i0) * 2 * esz, sh));
             e_t[k] = next_ev(); CU(cudaEventRecord(e_t[k], sh));
         }
         cudaEvent_t e_in[3] = {nullptr, nullptr, nullptr};
         for (int c = (has0 ? 1 : 0); c < ncomp; ++c) {
-            CU(cudaMemcpyAsync(dalm[c], alms[c], alm_bytes, cudaMemcpyHostToDevice, sh));
+            CU(host_copy_in(P, pg_alm[c], dalm[c], alms[c], alm_bytes, sh));
             e_in[c] = next_ev(); CU(cudaEventRecord(e_in[c], sh));
         }
         auto cvt_in = [&](int c) {
@@ -871,7 +931,7 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
             CU(cudaStreamWaitEvent(sd, e, 0));
             size_t off, nb; ring_rows(P, r0, r1, esz, off, nb);
             for (int c = cb; c < cb + cn; ++c)
-                CU(cudaMemcpyAsync((char*)maps[c] + off, (char*)dmap[c] + off, nb, cudaMemcpyDeviceToHost, sd));
+                CU(host_copy_out(P, pg_map[c], (char*)maps[c] + off, (char*)dmap[c] + off, nb, sd));
             return PIXSHT_OK;
         };
         if (has0) {
@@ -940,7 +1000,7 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
             for (int h = 0; h < 2; ++h) {
                 if (rr0[k][2 * h + 1] <= rr0[k][2 * h]) continue;
                 size_t off, nb; ring_rows(P, rr0[k][2 * h], rr0[k][2 * h + 1], esz, off, nb);
-                CU(cudaMemcpyAsync((char*)dmap[0] + off, (const char*)maps[0] + off, nb, cudaMemcpyHostToDevice, sh));
+                CU(host_copy_in(P, pg_map[0], (char*)dmap[0] + off, (const char*)maps[0] + off, nb, sh));
             }
             e_t[k] = next_ev(); CU(cudaEventRecord(e_t[k], sh));
         }
@@ -960,14 +1020,14 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
                         const int r0 = part == 0 ? rA[h][0] : rB[h][0], r1 = part == 0 ? rA[h][1] : rB[h][1];
                         if (r1 <= r0) continue;
                         size_t off, nb; ring_rows(P, r0, r1, esz, off, nb);
-                        CU(cudaMemcpyAsync((char*)dmap[c] + off, (const char*)maps[c] + off, nb, cudaMemcpyHostToDevice, sh));
+                        CU(host_copy_in(P, pg_map[c], (char*)dmap[c] + off, (const char*)maps[c] + off, nb, sh));
                     }
                 cudaEvent_t e = next_ev(); CU(cudaEventRecord(e, sh));
                 if (part == 0) e_partA = e; else e_in[c0] = e_in[c0 + 1] = e;
             }
         } else {
             for (int c = (has0 ? 1 : 0); c < ncomp; ++c) {
-                CU(cudaMemcpyAsync(dmap[c], maps[c], map_bytes, cudaMemcpyHostToDevice, sh));
+                CU(host_copy_in(P, pg_map[c], dmap[c], maps[c], map_bytes, sh));
                 e_in[c] = next_ev(); CU(cudaEventRecord(e_in[c], sh));
             }
         }
@@ -984,7 +1044,7 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
             CU(cudaEventRecord(e, sc));
             CU(cudaStreamWaitEvent(sd, e, 0));
             for (int c = cb; c < cb + cn; ++c)
-                CU(cudaMemcpyAsync((char*)alms[c] + (size_t)i0 * 2 * esz, (char*)dalm[c] + (size_t)i0 * 2 * esz, (size_t)(i1 - i0) * 2 * esz, cudaMemcpyDeviceToHost, sd));
+                CU(host_copy_out(P, pg_alm[c], (char*)alms[c] + (size_t)i0 * 2 * esz, (char*)dalm[c] + (size_t)i0 * 2 * esz, (size_t)(i1 - i0) * 2 * esz, sd));
             return PIXSHT_OK;
         };
         for (int c = 0; c < ncomp; ++c) CU(cudaMemsetAsync(dalm64[c], 0, (size_t)P->nalm * sizeof(double2), sc));
@@ -1038,6 +1098,7 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
     CU(cudaStreamSynchronize(sc));
     CU(cudaStreamSynchronize(sd));
     CU(cudaGetLastError());
+    host_copies_done(P);
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, P->ev[0], P->ev[1]));
     for (auto& t : P->timings) t = 0;
@@ -1217,8 +1278,8 @@ static int execute_batch_locked(pixsht_plan* P, int direction, int nbatch, void*
                 if (P->d_map[k].n < map_bytes && P->d_map[k].alloc(map_bytes)) return fail(PIXSHT_ERR_NOMEM, "map staging allocation failed");
                 if (P->d_alm[k].n < alm_bytes && P->d_alm[k].alloc(alm_bytes)) return fail(PIXSHT_ERR_NOMEM, "alm staging allocation failed");
                 dmap[b] = P->d_map[k].p; dalm[b] = P->d_alm[k].p;
-                if (direction == PIXSHT_ALM2MAP) CU(cudaMemcpyAsync(dalm[b], alms[b0 + b], alm_bytes, cudaMemcpyHostToDevice, sh));
-                else CU(cudaMemcpyAsync(dmap[b], maps[b0 + b], map_bytes, cudaMemcpyHostToDevice, sh));
+                if (direction == PIXSHT_ALM2MAP) CU(host_copy_in(P, host_is_pageable(alms[b0 + b]), dalm[b], alms[b0 + b], alm_bytes, sh));
+                else CU(host_copy_in(P, host_is_pageable(maps[b0 + b]), dmap[b], maps[b0 + b], map_bytes, sh));
             } else { dmap[b] = maps[b0 + b]; dalm[b] = alms[b0 + b]; }
             if (f32) {
                 if (P->d_alm64[k].n < (size_t)P->nalm && P->d_alm64[k].alloc(P->nalm)) return fail(PIXSHT_ERR_NOMEM, "alm work buffer allocation failed");
@@ -1249,8 +1310,8 @@ static int execute_batch_locked(pixsht_plan* P, int direction, int nbatch, void*
         if (ovl) { cudaEvent_t e = next_ev(); CU(cudaEventRecord(e, st)); CU(cudaStreamWaitEvent(sd, e, 0)); }
         if (location == PIXSHT_HOST) {
             for (int b = 0; b < nb; ++b) {
-                if (direction == PIXSHT_ALM2MAP) CU(cudaMemcpyAsync(maps[b0 + b], dmap[b], map_bytes, cudaMemcpyDeviceToHost, sd));
-                else CU(cudaMemcpyAsync(alms[b0 + b], dalm[b], alm_bytes, cudaMemcpyDeviceToHost, sd));
+                if (direction == PIXSHT_ALM2MAP) CU(host_copy_out(P, host_is_pageable(maps[b0 + b]), maps[b0 + b], dmap[b], map_bytes, sd));
+                else CU(host_copy_out(P, host_is_pageable(alms[b0 + b]), alms[b0 + b], dalm[b], alm_bytes, sd));
             }
             if (ovl) { e_free[set] = next_ev(); CU(cudaEventRecord(e_free[set], sd)); }
             else CU(cudaStreamSynchronize(st));   // the single staging set is reused by the next group
@@ -1260,6 +1321,7 @@ static int execute_batch_locked(pixsht_plan* P, int direction, int nbatch, void*
     if (ovl) { CU(cudaStreamSynchronize(sh)); CU(cudaStreamSynchronize(sd)); }
     CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
+    host_copies_done(P);
     for (auto& t : P->timings) t = 0;
     P->timings[4] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     return PIXSHT_OK;

@@ -69,15 +69,30 @@ end
 const PLANS = Dict{Any,Plan}()
 const PLAN_LOCK = ReentrantLock()
 
+"GPUs of the plans: ENV[\"PIXSHT_DEVICES\"] = \"0,1,2,3\" -> one process drives all of them (pixsht_plan_create_multi); default: GPU 0."
+function devices()
+    v = strip(get(ENV, "PIXSHT_DEVICES", ""))
+    isempty(v) ? Cint[0] : Cint[parse(Cint, x) for x in split(v, ',') if !isempty(strip(x))]
+end
+
 function plan_for(shape, wcs, lmax::Int, mmax::Int, ::Type{T}) where {T<:Union{Float32,Float64}}
     g = sht_geom(shape, wcs)
-    key = (g, lmax, mmax, T)
+    devs = devices()
+    key = (g, lmax, mmax, T, Tuple(devs))
     lock(PLAN_LOCK) do
         get!(PLANS, key) do
             out = Ref{Ptr{Cvoid}}(C_NULL)
-            check(ccall((:pixsht_plan_create, libpixsht), Cint,
-                        (Ref{Ptr{Cvoid}}, Ref{PixshtGeom}, Cint, Cint, Cint, Cint),
-                        out, g, lmax, mmax, T === Float64 ? PIXSHT_F64 : PIXSHT_F32, 0))
+            dt = T === Float64 ? PIXSHT_F64 : PIXSHT_F32
+            if length(devs) == 1
+                check(ccall((:pixsht_plan_create, libpixsht), Cint,
+                            (Ref{Ptr{Cvoid}}, Ref{PixshtGeom}, Cint, Cint, Cint, Cint),
+                            out, g, lmax, mmax, dt, devs[1]))
+            else
+                # one blocking call, N GPUs: m-sharded Legendre stage, ring-sharded FFT stage, phase rows exchanged over NVLink
+                check(ccall((:pixsht_plan_create_multi, libpixsht), Cint,
+                            (Ref{Ptr{Cvoid}}, Ref{PixshtGeom}, Cint, Cint, Cint, Cint, Ptr{Cint}),
+                            out, g, lmax, mmax, dt, length(devs), devs))
+            end
             p = Plan(out[], Int(ccall((:pixsht_nalm, libpixsht), Int64, (Cint, Cint), lmax, mmax)))
             finalizer(p) do q   # thread-safe in the library; tolerates a torn-down CUDA context
                 ccall((:pixsht_plan_destroy, libpixsht), Cvoid, (Ptr{Cvoid},), q.ptr)
@@ -98,8 +113,43 @@ function execute!(p::Plan, dir::Cint, alms::Vector{<:AbstractVector}, maps::Vect
     end
 end
 
-compute_type(::Type{Float32}) = Float32
-compute_type(::Type) = Float64            # the reference promotes everything to Float64 (src/transforms.jl:71)
+# The reference promotes every map to Float64 before the transform (create_sht_band, src/transforms.jl:71) and returns
+# ComplexF64 alm; so does this binding.  ENV["PIXSHT_F32_BOUNDARY"] = "1" opts in to the Float32-boundary plan for Float32
+# maps (half the PCIe volume, ring FFTs in Float32: ~1e-7 relative, NOT the reference's numerics).
+f32_boundary() = get(ENV, "PIXSHT_F32_BOUNDARY", "0") == "1"
+compute_type(::Type{Float32}) = f32_boundary() ? Float32 : Float64
+compute_type(::Type) = Float64
+
+# Page-locked host arrays for the library's outputs (pixsht_host_alloc): the host-pointer call overlaps its copies with the
+# kernels only from / to page-locked memory.  The finalizer returns the memory to the library.
+function pinned_zeros(::Type{T}, dims::Int...) where {T}
+    n = prod(dims)
+    ptr = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:pixsht_host_alloc, libpixsht), Cint, (Ref{Ptr{Cvoid}}, Csize_t), ptr, max(n, 1) * sizeof(T)))
+    a = unsafe_wrap(Array, Ptr{T}(ptr[]), dims; own=false)
+    fill!(a, zero(T))
+    finalizer(a) do x
+        ccall((:pixsht_host_free, libpixsht), Cint, (Ptr{Cvoid},), pointer(x))
+    end
+    a
+end
+"Page-lock an array the caller owns for the duration of `f` (pixsht_host_register / pixsht_host_unregister)."
+function with_registered(f, arrays...)
+    regs = Ptr{Cvoid}[]
+    try
+        for a in arrays
+            check(ccall((:pixsht_host_register, libpixsht), Cint, (Ptr{Cvoid}, Csize_t), pointer(a), sizeof(a)))
+            push!(regs, pointer(a))
+        end
+        GC.@preserve arrays f()
+    finally
+        for p in regs
+            ccall((:pixsht_host_unregister, libpixsht), Cint, (Ptr{Cvoid},), p)
+        end
+    end
+end
+as_complex(a::AbstractVector{ComplexF64}) = a                 # already the library's element type: no copy
+as_complex(a::AbstractVector) = ComplexF64.(a)
 
 # a contiguous column-major plane of eltype T is passed as it is (Array, or a contiguous view such as m[:, :, c]);
 # anything else is copied / converted once
@@ -117,9 +167,9 @@ function _map2alm(maps::Vector, wcs, shape; lmax=nothing, mmax=lmax)
     T = compute_type(eltype(maps[1]))
     p = plan_for(shape, wcs, lmax, mmax, T)
     planes = [dense(m, T) for m in maps]
-    alms = [zeros(Complex{T}, p.nalm) for _ in planes]
+    alms = [pinned_zeros(Complex{T}, p.nalm) for _ in planes]
     execute!(p, PIXSHT_MAP2ALM, alms, planes)
-    [Alm(lmax, mmax, ComplexF64.(a)) for a in alms]
+    [Alm(lmax, mmax, as_complex(a)) for a in alms]
 end
 
 map2alm(m::Enmap{T,2}; lmax=nothing, mmax=lmax) where {T} =
@@ -147,8 +197,8 @@ end
 function _alm2map(alms::Vector{<:Alm}, shape, wcs)
     lmax, mmax = alms[1].lmax, alms[1].mmax
     p = plan_for(shape[1:2], wcs, lmax, mmax, Float64)
-    vecs = [ComplexF64.(a.alm) for a in alms]
-    maps = [zeros(Float64, shape[1], shape[2]) for _ in alms]
+    vecs = [as_complex(a.alm) for a in alms]
+    maps = [pinned_zeros(Float64, shape[1], shape[2]) for _ in alms]
     execute!(p, PIXSHT_ALM2MAP, vecs, maps)
     [Enmap(m, wcs) for m in maps]
 end
@@ -185,21 +235,21 @@ function map2alm_batch(ms::Vector{<:Enmap{T,2}}; lmax=nothing, mmax=lmax) where 
     C = compute_type(T)
     p = plan_for(shape, wcs, lmax, mmax, C)
     planes = [dense(parent(m), C) for m in ms]
-    alms = [zeros(Complex{C}, p.nalm) for _ in planes]
+    alms = [pinned_zeros(Complex{C}, p.nalm) for _ in planes]
     execute_batch!(p, PIXSHT_MAP2ALM, alms, planes)
-    [Alm(lmax, mmax, ComplexF64.(a)) for a in alms]
+    [Alm(lmax, mmax, as_complex(a)) for a in alms]
 end
 
 "alm2map of every Alm of `alms` (same lmax, mmax) onto the same geometry; equals `[alm2map(a, shape, wcs) for a in alms]`."
 function alm2map_batch(alms::Vector{<:Alm}, shape, wcs)
     lmax, mmax = alms[1].lmax, alms[1].mmax
     p = plan_for(shape[1:2], wcs, lmax, mmax, Float64)
-    vecs = [ComplexF64.(a.alm) for a in alms]
-    maps = [zeros(Float64, shape[1], shape[2]) for _ in alms]
+    vecs = [as_complex(a.alm) for a in alms]
+    maps = [pinned_zeros(Float64, shape[1], shape[2]) for _ in alms]
     execute_batch!(p, PIXSHT_ALM2MAP, vecs, maps)
     [Enmap(m, wcs) for m in maps]
 end
 
-export map2alm, alm2map, map2alm_batch, alm2map_batch
+export map2alm, alm2map, map2alm_batch, alm2map_batch, with_registered
 
 end # module

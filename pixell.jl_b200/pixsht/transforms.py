@@ -147,26 +147,47 @@ class Plan:
 _PLANS = {}
 
 
-def _plan_for(shape, wcs, lmax, mmax, dtype, lib=None):
+def _env_devices():
+    """PIXSHT_DEVICES="0,1,2,3" -> [0, 1, 2, 3]; unset or a single index -> None (single-GPU plan on that index is the default 0)."""
+    import os
+    v = os.environ.get("PIXSHT_DEVICES", "").strip()
+    if not v:
+        return None
+    d = [int(x) for x in v.split(",") if x.strip() != ""]
+    return d if len(d) > 1 else None
+
+
+def _plan_for(shape, wcs, lmax, mmax, dtype, lib=None, devices=None):
     band = sht_band(tuple(shape[:2]), wcs)
     lib = get_lib() if lib is None else lib
-    key = (id(lib), band, lmax, mmax, np.dtype(dtype).str)
+    devices = _env_devices() if devices is None else list(devices)
+    key = (id(lib), band, lmax, mmax, np.dtype(dtype).str, None if devices is None else tuple(devices))
     p = _PLANS.get(key)
     if p is None:
         if len(_PLANS) >= 8:
             _PLANS.pop(next(iter(_PLANS))).close()
-        p = _PLANS[key] = Plan(band, lmax, mmax, dtype=dtype, lib=lib)
+        p = _PLANS[key] = Plan(band, lmax, mmax, dtype=dtype, lib=lib, devices=devices)
     return p
 
 
-def _compute_dtype(dt):
-    return np.float32 if np.dtype(dt) == np.float32 else np.float64
+def _compute_dtype(dt, precision=None):
+    """Element type of the plan for a map of dtype `dt`.  Default: Float64 whatever the map's type -- the reference promotes every
+    map to Float64 before the transform (create_sht_band, src/transforms.jl:71) and so do we (the map is widened on the host,
+    like the reference's band copy).  precision="f32" is the explicit opt-in to the Float32-boundary plan for Float32 maps
+    (half the PCIe volume, ring FFTs in Float32: rel-RMS ~1e-7 of each ring's dominant mode -- NOT the reference's numerics)."""
+    if precision not in (None, "f64", "f32"):
+        raise ValueError("precision must be None, 'f64' or 'f32'")
+    if precision == "f32" and np.dtype(dt) == np.float32:
+        return np.float32
+    return np.float64
 
 
-def map2alm(m, lmax=None, mmax=None, lib=None):
+def map2alm(m, lmax=None, mmax=None, lib=None, precision=None, devices=None):
     """map2alm(::Enmap{T,2}) / (::NTuple{2}) / (::NTuple{3}) / (::Enmap{T,3})  (src/transforms.jl:88-165).
 
-    Returns an Alm (spin 0), or a tuple (E, B) / (T, E, B) of Alm -- the reference's return types."""
+    Returns an Alm (spin 0), or a tuple (E, B) / (T, E, B) of Alm -- the reference's return types; the alm are complex128
+    whatever the map's element type, as the reference's (ComplexF64).  precision: see _compute_dtype.  devices: list of GPUs
+    for a multi-GPU plan (default: the PIXSHT_DEVICES environment variable, else one GPU)."""
     if isinstance(m, (tuple, list)):
         maps = list(m)
         if len(maps) not in (2, 3) or any(x.ndim != 2 for x in maps):
@@ -185,19 +206,19 @@ def map2alm(m, lmax=None, mmax=None, lib=None):
         lmax = getlmax(first.wcs)
         mmax = lmax
     mmax = lmax if mmax is None else mmax
-    plan = _plan_for(first.shape, first.wcs, lmax, mmax, _compute_dtype(first.dtype), lib)
-    alms = [Alm(lmax, mmax, a) for a in plan.map2alm(arrays)]
+    plan = _plan_for(first.shape, first.wcs, lmax, mmax, _compute_dtype(first.dtype, precision), lib, devices)
+    alms = [Alm(lmax, mmax, np.asarray(a, dtype=np.complex128)) for a in plan.map2alm(arrays)]
     return alms[0] if len(alms) == 1 else tuple(alms)
 
 
-def alm2map(alm, shape, wcs, dtype=np.float64, lib=None):
+def alm2map(alm, shape, wcs, dtype=np.float64, lib=None, devices=None):
     """alm2map(::Alm, shape, wcs) -> Enmap;  (::NTuple{2,Alm}) -> list of 2 Enmaps;  (::NTuple{3,Alm}) / Vector -> tuple
     (src/transforms.jl:206-265, return-type quirks of SURVEY.md F11 kept)."""
     alms = [alm] if isinstance(alm, Alm) else list(alm)
     if len(alms) not in (1, 2, 3):
         raise ValueError("1, 2 or 3 Alm are supported")
     lmax, mmax = alms[0].lmax, alms[0].mmax
-    plan = _plan_for(shape, wcs, lmax, mmax, dtype, lib)
+    plan = _plan_for(shape, wcs, lmax, mmax, dtype, lib, devices)
     maps = [Enmap(x, wcs) for x in plan.alm2map([a.alm for a in alms])]
     if len(maps) == 1:
         return maps[0]

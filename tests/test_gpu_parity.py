@@ -129,14 +129,20 @@ def test_partial_sky_band_and_unflipped_geometry():
 
 
 def test_float32_maps():
+    """Float32 Enmaps: by default promoted to Float64 like the reference (create_sht_band, src/transforms.jl:71; alm are ComplexF64),
+    so the result is the Float64 transform of the rounded map; precision="f32" opts in to the Float32-boundary plan (<= 1e-5)."""
     shape, wcs = fullsky_geometry(0.5 * degree)
     lmax = 360
     alm = synth_alm(lmax, lmax, 2000)
     ref = oracle_alm2map(alm[None], shape, wcs, lmax)[:, :, 0]
     got = alm2map(Alm(lmax, lmax, alm), shape, wcs, dtype=np.float32)
     assert got.dtype == np.float32 and rel_rms(got.data, ref) < TOL32
-    a32 = map2alm(Enmap(np.asfortranarray(ref, dtype=np.float32), wcs), lmax=lmax)
-    assert a32.alm.dtype == np.complex64
+    m32 = np.asfortranarray(ref, dtype=np.float32)
+    a_def = map2alm(Enmap(m32, wcs), lmax=lmax)
+    assert a_def.alm.dtype == np.complex128
+    assert rel_rms(a_def.alm, oracle_map2alm(Enmap(m32.astype(np.float64), wcs), lmax)[0]) < TOL64      # Float64 numerics on the Float32 data
+    a32 = map2alm(Enmap(m32, wcs), lmax=lmax, precision="f32")
+    assert a32.alm.dtype == np.complex128
     assert rel_rms(a32.alm, oracle_map2alm(Enmap(ref, wcs), lmax)[0]) < TOL32
 
 
@@ -309,6 +315,87 @@ def test_c2_size_float32_sampled_parity():
     sel = np.concatenate([np.arange(alm_index(lmax, m, m), alm_index(lmax, lmax, m) + 1) for m in range(m_offset, lmax + 1, m_stride)])
     assert rel_rms(got[sel].astype(np.complex128), ref_alm[sel]) < TOL32
     plan.close()
+
+
+def test_c5_size_float32_sampled_parity():
+    """BASELINE config C5: full-sky CAR 0.5' (43200 x 21601) Float32 T-only, lmax 21600 (the largest config; a 3.7 GB map).
+    Sampled rings (pole-adjacent, mid latitude, equator) and sampled m (low, middle, Nyquist-adjacent) against the long-double
+    oracle: rel-RMS <= 1e-5 (north_star's Float32 tolerance).  PARITY UNPINNED by files."""
+    shape, wcs = fullsky_geometry(0.5 * arcminute)
+    assert shape == (43200, 21601)
+    lmax = 21600
+    band = pixsht.sht_band(shape, wcs)
+    plan = Plan(band, lmax, dtype=np.float32)
+    alm = synth_alm(lmax, lmax, 5000).astype(np.complex64)
+    maps = plan.alm2map([alm])
+    assert maps[0].dtype == np.float32
+    rings = [2, 5400, 10800, 21598]
+    num, den = _ring_errors(band, [maps[0].astype(np.float64, copy=False)], [alm.astype(np.complex128)], lmax, 0, rings)
+    assert np.sqrt(num.sum() / den.sum()) < TOL32
+    assert np.all(np.sqrt(num / den) < 10 * TOL32)       # no single ring (the pole-adjacent ones included) far off
+    got = plan.map2alm(maps)[0]                           # analysis of the (band-limited) synthesised map
+    assert got.dtype == np.complex64
+    theta, w = cc_geometry(band.nrings_total, band.nphi)
+    fx = slice(None, None, -1) if band.flipx else slice(None)
+    fy = slice(None, None, -1) if band.flipy else slice(None)
+    bandmap = np.ascontiguousarray(maps[0].T[fy, fx], dtype=np.float64)[None]
+    for m in (3, 10811, 21599):
+        ref = get_oracle("ld").map2alm(bandmap, theta, w, band.phi0, lmax, m_stride=lmax + 1, m_offset=m)[0]
+        sl = slice(alm_index(lmax, m, m), alm_index(lmax, lmax, m) + 1)
+        assert rel_rms(got[sl].astype(np.complex128), ref[sl]) < TOL32
+    plan.close()
+
+
+def test_c3_size_full_map_against_cpu_port():
+    """BASELINE config C3, EVERY pixel and EVERY alm (not a sample): the CUDA engine against oracle/sht_cpu.c, the
+    libsharp2-style CPU implementation (itself checked against the long-double checker in tests/test_oracle_properties.py).
+    Whole-map / whole-alm rel-RMS <= 1e-10."""
+    from oracle import get_cpu_sht
+    shape, wcs = fullsky_geometry(2.0 * arcminute)
+    lmax = 5400
+    band = pixsht.sht_band(shape, wcs)
+    plan = Plan(band, lmax)
+    cpu = get_cpu_sht()
+    cpu.use_all_cores()
+    theta, w = cc_geometry(band.nrings_total, band.nphi)
+    alms = [synth_alm(lmax, lmax, 3100 + c, spin2=c > 0) for c in range(3)]
+    maps = plan.alm2map(alms)
+    fx = slice(None, None, -1) if band.flipx else slice(None)
+    fy = slice(None, None, -1) if band.flipy else slice(None)
+    ref_t = cpu.alm2map(alms[0][None], theta, band.phi0, band.nphi, lmax, spin=0)
+    ref_qu = cpu.alm2map(np.stack(alms[1:]), theta, band.phi0, band.nphi, lmax, spin=2)
+    ref = [ref_t[0], ref_qu[0], ref_qu[1]]
+    for c in range(3):
+        assert rel_rms(maps[c].T[fy, fx], ref[c]) < TOL64
+    rng = np.random.default_rng(33)
+    x = [rng.standard_normal((band.nrings, band.nphi)) for _ in range(3)]          # band orientation, not band-limited
+    got = plan.map2alm([np.asfortranarray(b[fy, fx].T) for b in x])
+    ref_a = [cpu.map2alm(x[0][None], theta, w, band.phi0, lmax, spin=0)[0]] + list(cpu.map2alm(np.stack(x[1:]), theta, w, band.phi0, lmax, spin=2))
+    for c in range(3):
+        assert rel_rms(got[c], ref_a[c]) < TOL64
+    plan.close()
+
+
+def test_batch_overlapped_staging_equals_serial(monkeypatch):
+    """Host-pointer batches: the double-buffered staging on the copy streams (the default) gives the same bits as the serial one."""
+    shape, wcs = fullsky_geometry(8.0 * arcminute)
+    lmax = 1350
+    band = pixsht.sht_band(shape, wcs)
+    alms = [synth_alm(lmax, lmax, 900 + b).astype(np.complex64) for b in range(11)]      # groups 4 + 4 + 2 + 1
+    res = {}
+    for ovl in ("1", "0"):
+        monkeypatch.setenv("PIXSHT_BATCH_OVERLAP", ovl)
+        plan = Plan(band, lmax, dtype=np.float32)
+        maps = plan.alm2map_batch(alms)
+        back = plan.map2alm_batch(maps)
+        res[ovl] = (maps, back)
+        plan.close()
+    for b in range(len(alms)):
+        assert np.array_equal(res["1"][0][b], res["0"][0][b])
+        assert rel_rms(res["1"][1][b], res["0"][1][b]) < 2e-6
+    single = Plan(band, lmax, dtype=np.float32)
+    assert rel_rms(res["1"][0][10], single.alm2map([alms[10]])[0]) < 2e-6
+    single.close()
 
 
 def test_host_and_device_paths_agree_and_iqu_is_t_plus_qu():

@@ -37,6 +37,7 @@ enum { PIXSHT_OK = 0, PIXSHT_ERR_ARG = 1, PIXSHT_ERR_CUDA = 2, PIXSHT_ERR_UNSUPP
 enum { PIXSHT_F64 = 0, PIXSHT_F32 = 1 };             /* element type of maps and alm at the boundary */
 enum { PIXSHT_MAP2ALM = 0, PIXSHT_ALM2MAP = 1 };     /* numerically equal to libsharp2's SHARP_MAP2ALM / SHARP_ALM2MAP */
 enum { PIXSHT_HOST = 0, PIXSHT_DEVICE = 1 };
+enum { PIXSHT_POLCONV_COSMO = 0, PIXSHT_POLCONV_IAU = 1 };   /* Stokes-U sign convention of the caller's maps (pixsht_plan_set_polconv) */
 enum { PIXSHT_RINGS_CC = 0, PIXSHT_RINGS_FEJER1 = 1 };  /* ring scheme of pixsht_geom */         /* where the alm / map pointers passed to pixsht_execute live */
 
 /* How the caller's (nx, ny) map sits on the full-sky ring grid. */
@@ -108,6 +109,19 @@ int pixsht_execute_batch(pixsht_plan *plan, int direction, int nbatch, void *con
 /* Run pixsht_execute on the caller's CUDA stream (cudaStream_t passed as void*; NULL is the legacy default stream) when
  * use_caller_stream != 0, or go back to the plan's own stream.  The call still synchronises that stream before returning. */
 int pixsht_plan_set_stream(pixsht_plan *plan, void *stream, int use_caller_stream);
+
+/* Stokes-U sign convention of the maps passed to this plan.  The transforms use the COSMO / HEALPix convention (libsharp2's, the
+ * one the reference computes in).  The reference converts an IAU file at read time by negating U on the host
+ * (read_map -> resolve_polcconv!, src/enmap.jl:178-196, 209-215); with PIXSHT_POLCONV_IAU the caller keeps the file's values and
+ * the sign is applied inside the ring-FFT kernels' row loads (map2alm) and stores (alm2map): no pass over the map.  Applies to
+ * the U component of ncomp = 2 and ncomp = 3 calls, on single- and multi-GPU plans; default PIXSHT_POLCONV_COSMO. */
+int pixsht_plan_set_polconv(pixsht_plan *plan, int polconv);
+
+/* Pixel areas (steradians) of the rows of the map described by `geom`, one value per map row (CAR pixel areas do not depend
+ * on RA), in the caller's row order: (sin dec_hi - sin dec_lo) |d alpha| with the row edges clipped at the poles.  Replaces
+ * pixareamap / pixareamap! of the reference (src/projections/car_proj.jl:265-273, src/enmap_ops.jl:124-138); used as ring
+ * weights through pixsht_plan_create_rings it gives the pixel-area-weighted analysis.  Host arithmetic, no device needed. */
+int pixsht_ring_pixarea(const pixsht_geom *geom, double *area /* geom->nrings */);
 
 /* per-stage device time (ms, CUDA events) of the last pixsht_execute on this plan:
  * device pointers: [1] Legendre stage, [2] FFT stage, [4] whole call (host wall clock), [6] the spin-0 Legendre kernel

@@ -56,6 +56,8 @@ struct FftParams {
     int ring_begin, ring_count; // band rings handled by this launch; ringlocal = ring - ring_begin
     int nx, ny, flipx, flipy;   // caller's map layout (column-major nx x ny), see pixsht_geom
     void* maps[4];              // up to 3 Stokes components, or a batch of up to 4 spin-0 maps
+    int neg_mask;               // bit c set: component c of the caller's maps carries the opposite sign (IAU <-> COSMO Stokes U,
+                                // src/enmap.jl:178-196 of the reference): negated here in the row I/O, no extra pass over the map
 };
 
 template <class T> struct cpx { T x, y; };
@@ -476,7 +478,7 @@ __device__ __forceinline__ double2* phase_elem(const FftParams& P, double2* loca
 
 // aliased half-spectrum entry X[k], 0 <= k <= n: sum over m == +-k (mod nphi) of the rotated phases (general mmax)
 template <class T>
-__device__ __forceinline__ cpx<T> load_X(const FftParams& P, double2* row, int ring, int c, int k)
+__device__ __forceinline__ cpx<T> load_X(const FftParams& P, double2* row, int ring, int c, int k, double sg)
 {
     double sx = 0.0, sy = 0.0;
     for (int m = k; m <= P.mmax; m += P.nphi) {
@@ -487,7 +489,7 @@ __device__ __forceinline__ cpx<T> load_X(const FftParams& P, double2* row, int r
         const double2 a = *phase_elem(P, row, ring, c, m), r = P.phi0tw[m];
         sx += a.x * r.x - a.y * r.y; sy -= a.x * r.y + a.y * r.x;
     }
-    cpx<T> v; v.x = (T)sx; v.y = (T)sy;
+    cpx<T> v; v.x = (T)(sg * sx); v.y = (T)(sg * sy);
     return v;
 }
 
@@ -543,6 +545,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
     const int n = P.n, N = P.nphi;
     T* out = reinterpret_cast<T*>(P.maps[c]);
     const bool vec = (P.nx == P.nphi) && P.packed;
+    const double sg = ((P.neg_mask >> c) & 1) ? -1.0 : 1.0;
 
     for (int rl = blockIdx.x; rl < P.ring_count; rl += gridDim.x) {
         const int ring = P.ring_begin + rl;
@@ -556,7 +559,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
                     for (int u = 0; u < FFT_IO_UNROLL; ++u) {
                         const int k = k0 + u * blockDim.x;
                         a[u] = make_double2(0.0, 0.0); r[u] = a[u];
-                        if (k <= P.mmax) { a[u] = *phase_elem(P, row, ring, c, k); r[u] = P.phi0tw[k]; }
+                        if (k <= P.mmax) { a[u] = *phase_elem(P, row, ring, c, k); r[u] = P.phi0tw[k]; r[u].x *= sg; r[u].y *= sg; }
                     }
 #pragma unroll
                     for (int u = 0; u < FFT_IO_UNROLL; ++u) {
@@ -570,7 +573,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
                     }
                 }
             } else {
-                for (int k = threadIdx.x; k <= n; k += blockDim.x) buf[k] = load_X<T>(P, row, ring, c, k);
+                for (int k = threadIdx.x; k <= n; k += blockDim.x) buf[k] = load_X<T>(P, row, ring, c, k, sg);
             }
             __syncthreads();
 
@@ -595,7 +598,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
         } else {
             // odd ring length: the full Hermitian spectrum Z[k] = X[k], Z[N-k] = conj X[k] of the real ring
             for (int k = threadIdx.x; k <= N / 2; k += blockDim.x) {
-                cpx<T> x = load_X<T>(P, row, ring, c, k);
+                cpx<T> x = load_X<T>(P, row, ring, c, k, sg);
                 if (k == 0) { x.y = (T)0; buf[0] = x; }
                 else { buf[k] = x; buf[N - k] = cconj(x); }
             }
@@ -641,6 +644,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams 
     const int n = P.n, N = P.nphi;
     const T* in = reinterpret_cast<const T*>(P.maps[c]);
     const bool vec = (P.nx == P.nphi) && P.packed;
+    const double sg = ((P.neg_mask >> c) & 1) ? -1.0 : 1.0;
 
     for (int rl = blockIdx.x; rl < P.ring_count; rl += gridDim.x) {
         const int ring = P.ring_begin + rl;
@@ -699,7 +703,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams 
         }
 
         // phase_m = w * e^{-i m phi0} * F[m mod N]  (packed: conjugate symmetric upper half); coalesced row write
-        const double w = P.wgt[ring];
+        const double w = sg * P.wgt[ring];
         double2* row = P.phase + ((long long)rl * P.ncomp + c) * P.MP;
         for (int m0 = threadIdx.x; m0 <= P.mmax; m0 += FFT_IO_UNROLL * blockDim.x) {
             double2 r[FFT_IO_UNROLL];

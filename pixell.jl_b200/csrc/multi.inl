@@ -62,6 +62,7 @@ struct pixsht_multi {
 
 static pixsht_plan* multi_first_sub(pixsht_multi* M) { return M->dev[0].sub; }
 static int multi_ndev(const pixsht_multi* M) { return M->ndev; }
+static void multi_set_polconv(pixsht_multi* M, int iau) { for (auto& D : M->dev) if (D.sub) D.sub->polconv_iau = iau; }
 
 // ---- partition -------------------------------------------------------------------------------------------------
 // ndev * S contiguous segments of equal work, boundaries multiples of 8, dealt boustrophedon

@@ -106,6 +106,7 @@ struct pixsht_plan {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t kev[4] = {nullptr, nullptr, nullptr, nullptr};   // around the spin-0 / spin-2 Legendre kernel of the device path
     bool kev_on = false;
+    int polconv_iau = 0;                   // 1: the caller's U maps follow the IAU sign convention (pixsht_plan_set_polconv)
     double timings[8] = {0};
     int launches = 0;
     std::mutex mu;
@@ -117,6 +118,7 @@ static void multi_destroy(pixsht_multi* M);
 static void multi_quiesce(pixsht_multi* M);
 static pixsht_plan* multi_first_sub(pixsht_multi* M);
 static int multi_ndev(const pixsht_multi* M);
+static void multi_set_polconv(pixsht_multi* M, int iau);
 static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* alms, void* const* maps, bool sharded);
 static int execute_batch_multi(pixsht_plan* P, int direction, int nbatch, void* const* alms, void* const* maps, int location);
 
@@ -766,7 +768,7 @@ static int stage_phase2alm(pixsht_plan* P, int ncomp, PhaseRef ph, int nm, const
 // FFT stage for components [c_begin, c_begin+c_count) of band rings [ring_begin, ring_begin+ring_count); `phase` points at the
 // row of (ring_begin, component 0) in a buffer with ncomp components per ring
 static int stage_fft(pixsht_plan* P, int dir, int ncomp, int c_begin, int c_count, double2* phase, int ring_begin, int ring_count,
-                     void* const* maps, cudaStream_t st, const long long* mtab = nullptr)
+                     void* const* maps, cudaStream_t st, const long long* mtab = nullptr, bool stokes = true)
 {
     if (ring_count <= 0 || c_count <= 0) return PIXSHT_OK;
     FftParams F;
@@ -780,6 +782,7 @@ static int stage_fft(pixsht_plan* P, int dir, int ncomp, int c_begin, int c_coun
     F.ring_begin = ring_begin; F.ring_count = ring_count;
     F.nx = P->nx; F.ny = P->ny; F.flipx = P->flipx; F.flipy = P->flipy;
     for (int c = 0; c < ncomp; ++c) F.maps[c] = maps[c];
+    F.neg_mask = (stokes && P->polconv_iau && ncomp >= 2) ? (1 << (ncomp - 1)) : 0;   // U is the last Stokes component
     F.packed = P->fft_packed; F.pt = P->fft_pt;
     if (P->fft_rows) {
         if (c_count > 4) return fail(PIXSHT_ERR_ARG, "at most 4 components per FFT launch");
@@ -1213,9 +1216,9 @@ static int batch_group(pixsht_plan* P, int direction, double2* const* alm64, voi
         PIXSHT_LAUNCH((leg_synth_b<RS, NB>), grid, LEG_NT, 0, st, L);
         P->launches += 2;
         CU(cudaGetLastError());
-        return stage_fft(P, PIXSHT_ALM2MAP, NB, 0, NB, P->d_phase.p, 0, P->nrings, dmap, st);
+        return stage_fft(P, PIXSHT_ALM2MAP, NB, 0, NB, P->d_phase.p, 0, P->nrings, dmap, st, nullptr, false);
     }
-    rc = stage_fft(P, PIXSHT_MAP2ALM, NB, 0, NB, P->d_phase.p, 0, P->nrings, dmap, st); if (rc) return rc;
+    rc = stage_fft(P, PIXSHT_MAP2ALM, NB, 0, NB, P->d_phase.p, 0, P->nrings, dmap, st, nullptr, false); if (rc) return rc;
     for (int b = 0; b < NB; ++b) CU(cudaMemsetAsync(alm64[b], 0, (size_t)P->nalm * sizeof(double2), st));
     PIXSHT_LAUNCH((leg_anal_b<RA, NB>), grid, LEG_NT, 0, st, L, A);
     P->launches++;
@@ -1296,9 +1299,9 @@ static int execute_batch_locked(pixsht_plan* P, int direction, int nbatch, void*
             if (direction == PIXSHT_ALM2MAP) {
                 const double2* a1[3] = {alm64[0], nullptr, nullptr};
                 rc = stage_alm2phase(P, 1, a1, P->mmax + 1, nullptr, {P->d_phase.p, 0, 0}, st);
-                if (!rc) rc = stage_fft(P, PIXSHT_ALM2MAP, 1, 0, 1, P->d_phase.p, 0, P->nrings, dmap, st);
+                if (!rc) rc = stage_fft(P, PIXSHT_ALM2MAP, 1, 0, 1, P->d_phase.p, 0, P->nrings, dmap, st, nullptr, false);
             } else {
-                rc = stage_fft(P, PIXSHT_MAP2ALM, 1, 0, 1, P->d_phase.p, 0, P->nrings, dmap, st);
+                rc = stage_fft(P, PIXSHT_MAP2ALM, 1, 0, 1, P->d_phase.p, 0, P->nrings, dmap, st, nullptr, false);
                 if (!rc) rc = cudaMemsetAsync(alm64[0], 0, (size_t)P->nalm * sizeof(double2), st) == cudaSuccess ? PIXSHT_OK : PIXSHT_ERR_CUDA;
                 double2* a1[3] = {alm64[0], nullptr, nullptr};
                 if (!rc) rc = stage_phase2alm(P, 1, {P->d_phase.p, 0, 0}, P->mmax + 1, nullptr, a1, st);
@@ -1365,6 +1368,42 @@ static void stage_components(const pixsht_plan* P, int ncomp, int& cb, int& cn)
     else if (h0) { cb = 0; cn = 1; }
     else if (h2) { cb = c0; cn = 2; }
     else { cb = 0; cn = 0; }
+}
+
+// Stokes-U sign convention of the caller's maps (src/enmap.jl:178-196, 209-215 of the reference: read_map flips U of an IAU file
+// on the host): here a flag of the plan, applied inside the FFT kernels' row I/O in both directions (fft.cuh: neg_mask).
+extern "C" int pixsht_plan_set_polconv(pixsht_plan* P, int polconv)
+{
+    if (!P) return fail(PIXSHT_ERR_ARG, "null plan");
+    if (polconv != PIXSHT_POLCONV_COSMO && polconv != PIXSHT_POLCONV_IAU) return fail(PIXSHT_ERR_ARG, "polconv must be PIXSHT_POLCONV_COSMO or PIXSHT_POLCONV_IAU");
+    std::lock_guard<std::mutex> lock(P->mu);
+    P->polconv_iau = polconv == PIXSHT_POLCONV_IAU;
+    if (P->multi) multi_set_polconv(P->multi, P->polconv_iau);
+    return PIXSHT_OK;
+}
+
+// Pixel areas of the band's rows (steradians), map row order: (sin(dec_hi) - sin(dec_lo)) * |d alpha| with the row edges half a
+// pixel either side of the ring and clipped at the poles -- pixareamap! of the reference (src/enmap_ops.jl:124-138), one value per
+// row because CAR pixel areas do not depend on RA.  O(nrings) host arithmetic, no device needed.
+extern "C" int pixsht_ring_pixarea(const pixsht_geom* g, double* area)
+{
+    if (!g || !area) return fail(PIXSHT_ERR_ARG, "null argument");
+    if (g->nphi < 1 || g->nrings_total < 1 || g->nrings < 0 || g->ring_first < 0 || g->ring_first + g->nrings > g->nrings_total)
+        return fail(PIXSHT_ERR_ARG, "inconsistent geometry");
+    const long double pi = 3.14159265358979323846264338327950288L;
+    const bool fejer = g->ring_scheme == PIXSHT_RINGS_FEJER1;
+    if (!fejer && g->nrings_total < 2) return fail(PIXSHT_ERR_ARG, "a Clenshaw-Curtis grid has at least two rings");
+    const long double dth = fejer ? pi / g->nrings_total : pi / (g->nrings_total - 1);
+    const long double dal = 2 * pi / g->nphi;
+    for (int r = 0; r < g->nrings; ++r) {
+        const int k = g->ring_first + r;
+        const long double th = fejer ? dth * (k + 0.5L) : dth * k;
+        long double d2 = pi / 2 - (th - dth / 2), d1 = pi / 2 - (th + dth / 2);
+        if (d2 > pi / 2) d2 = pi / 2;
+        if (d1 < -pi / 2) d1 = -pi / 2;
+        area[g->flipy ? (g->nrings - 1 - r) : r] = (double)((sinl(d2) - sinl(d1)) * dal);
+    }
+    return PIXSHT_OK;
 }
 
 extern "C" int pixsht_plan_set_stage_families(pixsht_plan* P, int spin0, int spin2)

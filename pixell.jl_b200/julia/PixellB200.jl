@@ -19,6 +19,7 @@ const libpixsht = get(ENV, "PIXSHT_LIB", joinpath(@__DIR__, "..", "lib", "libpix
 const PIXSHT_F64, PIXSHT_F32 = Cint(0), Cint(1)
 const PIXSHT_MAP2ALM, PIXSHT_ALM2MAP = Cint(0), Cint(1)
 const PIXSHT_HOST = Cint(0)
+const PIXSHT_POLCONV_COSMO, PIXSHT_POLCONV_IAU = Cint(0), Cint(1)
 
 # mirrors `struct pixsht_geom` of include/pixsht.h (field order and widths matter)
 struct PixshtGeom
@@ -102,6 +103,16 @@ function plan_for(shape, wcs, lmax::Int, mmax::Int, ::Type{T}) where {T<:Union{F
     end
 end
 
+# Stokes-U sign convention of the maps handed to the next calls on this plan (pixsht_plan_set_polconv).  Pixell's read_map
+# negates U of a POLCCONV = "IAU" file on the host (resolve_polcconv!, src/enmap.jl:178-196); `read_map(...)` followed by
+# `map2alm(m)` therefore keeps working unchanged.  To skip that host pass over the map, keep the file's values
+# (`read_map(path; wcs=...)` or FITSIO directly) and call `map2alm(m; polcconv="IAU")`: the sign is applied inside the FFT kernels.
+function set_polconv!(p::Plan, polcconv::AbstractString)
+    c = polcconv == "IAU" ? PIXSHT_POLCONV_IAU : polcconv == "COSMO" ? PIXSHT_POLCONV_COSMO :
+        throw(ArgumentError("polcconv must be \"COSMO\" or \"IAU\""))
+    check(ccall((:pixsht_plan_set_polconv, libpixsht), Cint, (Ptr{Cvoid}, Cint), p.ptr, c))
+end
+
 function execute!(p::Plan, dir::Cint, alms::Vector{<:AbstractVector}, maps::Vector{<:AbstractArray})
     ncomp = length(alms)
     GC.@preserve alms maps begin
@@ -160,12 +171,13 @@ dense(m::AbstractArray{T}, ::Type{T}) where {T} = is_dense(m) ? m : Array(m)
 dense(m::AbstractArray, ::Type{T}) where {T} = Array{T}(m)
 
 # ---- map2alm: src/transforms.jl:88-165 -------------------------------------------------------------------------
-function _map2alm(maps::Vector, wcs, shape; lmax=nothing, mmax=lmax)
+function _map2alm(maps::Vector, wcs, shape; lmax=nothing, mmax=lmax, polcconv="COSMO")
     if isnothing(lmax)
         lmax = getlmax(wcs); mmax = lmax
     end
     T = compute_type(eltype(maps[1]))
     p = plan_for(shape, wcs, lmax, mmax, T)
+    set_polconv!(p, polcconv)
     planes = [dense(m, T) for m in maps]
     alms = [pinned_zeros(Complex{T}, p.nalm) for _ in planes]
     execute!(p, PIXSHT_MAP2ALM, alms, planes)
@@ -175,28 +187,29 @@ end
 map2alm(m::Enmap{T,2}; lmax=nothing, mmax=lmax) where {T} =
     _map2alm([parent(m)], getwcs(m), size(m); lmax=lmax, mmax=mmax)[1]
 
-function map2alm(ms::NTuple{2,Enmap{T,2}}; lmax=nothing, mmax=lmax) where {T}
-    e, b = _map2alm([parent(ms[1]), parent(ms[2])], getwcs(ms[1]), size(ms[1]); lmax=lmax, mmax=mmax)
+function map2alm(ms::NTuple{2,Enmap{T,2}}; lmax=nothing, mmax=lmax, polcconv="COSMO") where {T}
+    e, b = _map2alm([parent(ms[1]), parent(ms[2])], getwcs(ms[1]), size(ms[1]); lmax=lmax, mmax=mmax, polcconv=polcconv)
     (e, b)
 end
 
-function map2alm(ms::NTuple{3,Enmap{T,2}}; lmax=nothing, mmax=lmax) where {T}
-    t, e, b = _map2alm([parent(m) for m in ms], getwcs(ms[1]), size(ms[1]); lmax=lmax, mmax=mmax)
+function map2alm(ms::NTuple{3,Enmap{T,2}}; lmax=nothing, mmax=lmax, polcconv="COSMO") where {T}
+    t, e, b = _map2alm([parent(m) for m in ms], getwcs(ms[1]), size(ms[1]); lmax=lmax, mmax=mmax, polcconv=polcconv)
     (t, e, b)
 end
 
-function map2alm(m::Enmap{T,3}; lmax=nothing, mmax=lmax) where {T}
+function map2alm(m::Enmap{T,3}; lmax=nothing, mmax=lmax, polcconv="COSMO") where {T}
     ncomp = size(m, 3)
     1 <= ncomp <= 3 || throw(ArgumentError("SHTs require shape (nx,ny,ncomp) with 1 ≤ ncomp ≤ 3, for I, QU, and IQU."))
     planes = [view(parent(m), :, :, c) for c in 1:ncomp]   # contiguous column-major planes: no copy for Array storage
-    out = _map2alm(planes, getwcs(m), size(m)[1:2]; lmax=lmax, mmax=mmax)
+    out = _map2alm(planes, getwcs(m), size(m)[1:2]; lmax=lmax, mmax=mmax, polcconv=polcconv)
     ncomp == 1 ? out[1] : Tuple(out)
 end
 
 # ---- alm2map: src/transforms.jl:206-265 (return types of SURVEY.md F11 preserved) -------------------------------------
-function _alm2map(alms::Vector{<:Alm}, shape, wcs)
+function _alm2map(alms::Vector{<:Alm}, shape, wcs; polcconv="COSMO")
     lmax, mmax = alms[1].lmax, alms[1].mmax
     p = plan_for(shape[1:2], wcs, lmax, mmax, Float64)
+    set_polconv!(p, polcconv)
     vecs = [as_complex(a.alm) for a in alms]
     maps = [pinned_zeros(Float64, shape[1], shape[2]) for _ in alms]
     execute!(p, PIXSHT_ALM2MAP, vecs, maps)
@@ -204,15 +217,31 @@ function _alm2map(alms::Vector{<:Alm}, shape, wcs)
 end
 
 alm2map(alm::Alm, shape, wcs) = _alm2map([alm], shape, wcs)[1]
-alm2map(alms::NTuple{2,<:Alm}, shape, wcs) = _alm2map(collect(alms), shape, wcs)            # Vector of 2 Enmaps (:251)
-alm2map(alms::NTuple{3,<:Alm}, shape, wcs) = Tuple(_alm2map(collect(alms), shape, wcs))     # Tuple (:254-255)
-function alm2map(alms::Vector{<:Alm}, shape, wcs)
+alm2map(alms::NTuple{2,<:Alm}, shape, wcs; polcconv="COSMO") = _alm2map(collect(alms), shape, wcs; polcconv=polcconv)          # Vector of 2 Enmaps (:251)
+alm2map(alms::NTuple{3,<:Alm}, shape, wcs; polcconv="COSMO") = Tuple(_alm2map(collect(alms), shape, wcs; polcconv=polcconv))   # Tuple (:254-255)
+function alm2map(alms::Vector{<:Alm}, shape, wcs; polcconv="COSMO")
     n = length(alms)
     n == 1 && return alm2map(alms[1], shape, wcs)
-    n == 2 && return alm2map((alms[1], alms[2]), shape, wcs)
-    n == 3 && return alm2map((alms[1], alms[2], alms[3]), shape, wcs)
+    n == 2 && return alm2map((alms[1], alms[2]), shape, wcs; polcconv=polcconv)
+    n == 3 && return alm2map((alms[1], alms[2], alms[3]), shape, wcs; polcconv=polcconv)
     throw(ArgumentError("1, 2 or 3 Alm are supported"))
 end
+
+# ---- pixel areas: pixareamap / pixareamap! (src/projections/car_proj.jl:265-273, src/enmap_ops.jl:124-138) -----------------
+"Pixel area (steradians) of every map row, in the map's row order (pixsht_ring_pixarea); CAR areas do not depend on RA."
+function ring_pixarea(shape, wcs)
+    g = sht_geom(shape, wcs)
+    area = Vector{Float64}(undef, shape[2])
+    check(ccall((:pixsht_ring_pixarea, libpixsht), Cint, (Ref{PixshtGeom}, Ptr{Float64}), g, area))
+    area
+end
+function pixareamap!(pixareas::Enmap)
+    area = ring_pixarea(size(pixareas), getwcs(pixareas))
+    parent(pixareas) .= reshape(area, 1, :)
+    pixareas
+end
+pixareamap(shape, wcs) = pixareamap!(Enmap(Array{Float64}(undef, shape[1], shape[2]), wcs))
+pixareamap(m::Enmap) = pixareamap!(similar(m))
 
 # ---- simulation sweeps: many spin-0 maps on one geometry (no counterpart upstream, where this is a loop over map2alm) ----
 # Up to four maps share one Legendre recurrence inside the library (pixsht_execute_batch).
@@ -250,6 +279,6 @@ function alm2map_batch(alms::Vector{<:Alm}, shape, wcs)
     [Enmap(m, wcs) for m in maps]
 end
 
-export map2alm, alm2map, map2alm_batch, alm2map_batch, with_registered
+export map2alm, alm2map, map2alm_batch, alm2map_batch, with_registered, pixareamap, pixareamap!, ring_pixarea
 
 end # module

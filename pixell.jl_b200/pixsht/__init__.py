@@ -7,11 +7,12 @@ from .geometry import (CarClenshawCurtis, CarFejer1, fullsky_geometry, geometry,
                        fullringsize, fullringnum, getlmax, first_last_rings_in_fullsky, get_flip_slices, sht_band,
                        ShtBand, degree, arcminute, radian, getcdelt, getcrpix, getcrval, getunit)
 from .enmap import Enmap, Alm, alm2cl  # noqa: F401
+from .fits_io import read_map, write_map, resolve_polcconv  # noqa: F401
 
 
 def __getattr__(name):
     # transforms import the ctypes binding lazily so that geometry-only users never touch the native library
-    if name in ("map2alm", "alm2map", "Plan", "get_lib", "PixshtError", "PixshtLib"):
+    if name in ("map2alm", "alm2map", "Plan", "get_lib", "PixshtError", "PixshtLib", "pixareamap", "pixareamap_", "ring_pixarea"):
         from . import transforms
         return getattr(transforms, name)
     raise AttributeError(name)

@@ -94,6 +94,13 @@ class Plan:
         """alm_ptrs / map_ptrs: flat lists [shard][component] of device pointers (pixsht_execute_sharded)."""
         self.lib.check(self.lib.lib.pixsht_execute_sharded(self.handle, direction, ncomp, _ptr_array(alm_ptrs), _ptr_array(map_ptrs)))
 
+    def set_polconv(self, polcconv):
+        """Stokes-U sign convention of the maps handed to this plan: "COSMO" (default; the convention the transforms compute in)
+        or "IAU" (U negated inside the ring-FFT kernels' row I/O, both directions): pixsht_plan_set_polconv."""
+        if polcconv not in ("COSMO", "IAU"):
+            raise ValueError("polcconv must be 'COSMO' or 'IAU'")
+        self.lib.check(self.lib.lib.pixsht_plan_set_polconv(self.handle, 1 if polcconv == "IAU" else 0))
+
     def timings(self):
         t = (ctypes.c_double * 8)()
         self.lib.check(self.lib.lib.pixsht_get_timings(self.handle, t))
@@ -182,12 +189,42 @@ def _compute_dtype(dt, precision=None):
     return np.float64
 
 
-def map2alm(m, lmax=None, mmax=None, lib=None, precision=None, devices=None):
+def pixareamap(shape_or_map, wcs=None, lib=None):
+    """pixareamap(shape, wcs) / pixareamap(m::Enmap): an Enmap whose pixel values are the pixel areas in steradians
+    (src/projections/car_proj.jl:265-273, src/enmap_ops.jl:124-138).  The per-row areas come from pixsht_ring_pixarea."""
+    if isinstance(shape_or_map, Enmap):
+        shape, wcs, dtype = shape_or_map.shape, shape_or_map.wcs, shape_or_map.dtype
+    else:
+        shape, dtype = tuple(shape_or_map), np.float64
+    out = Enmap(np.empty(tuple(shape[:2]), dtype=dtype, order="F"), wcs)
+    return pixareamap_(out, lib=lib)
+
+
+def ring_pixarea(shape, wcs, lib=None):
+    """Pixel area of each map row (ny values, the map's row order)."""
+    lib = get_lib() if lib is None else lib
+    band = sht_band(tuple(shape[:2]), wcs)
+    g = Geom(band.nphi, band.nrings_total, band.ring_first, band.nrings, band.nx, int(band.flipx), int(band.flipy), int(getattr(band, "ring_scheme", 0)),
+             band.phi0)
+    area = np.empty(band.nrings)
+    lib.check(lib.lib.pixsht_ring_pixarea(ctypes.byref(g), area.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+    return area
+
+
+def pixareamap_(pixareas, lib=None):
+    """pixareamap!(pixareas::Enmap): in-place (src/enmap_ops.jl:124-138)."""
+    area = ring_pixarea(pixareas.shape, pixareas.wcs, lib=lib)
+    pixareas.data[...] = area.reshape((1, -1) + (1,) * (pixareas.data.ndim - 2))
+    return pixareas
+
+
+def map2alm(m, lmax=None, mmax=None, lib=None, precision=None, devices=None, polcconv=None):
     """map2alm(::Enmap{T,2}) / (::NTuple{2}) / (::NTuple{3}) / (::Enmap{T,3})  (src/transforms.jl:88-165).
 
     Returns an Alm (spin 0), or a tuple (E, B) / (T, E, B) of Alm -- the reference's return types; the alm are complex128
     whatever the map's element type, as the reference's (ComplexF64).  precision: see _compute_dtype.  devices: list of GPUs
-    for a multi-GPU plan (default: the PIXSHT_DEVICES environment variable, else one GPU)."""
+    for a multi-GPU plan (default: the PIXSHT_DEVICES environment variable, else one GPU).  polcconv: "COSMO" | "IAU", the sign
+    convention of the U map (default: the Enmap's tag from read_map(..., defer_polcconv=True), else COSMO)."""
     if isinstance(m, (tuple, list)):
         maps = list(m)
         if len(maps) not in (2, 3) or any(x.ndim != 2 for x in maps):
@@ -207,11 +244,13 @@ def map2alm(m, lmax=None, mmax=None, lib=None, precision=None, devices=None):
         mmax = lmax
     mmax = lmax if mmax is None else mmax
     plan = _plan_for(first.shape, first.wcs, lmax, mmax, _compute_dtype(first.dtype, precision), lib, devices)
+    # U sign convention of the input: an explicit keyword, else the tag read_map(..., defer_polcconv=True) left on the Enmap
+    plan.set_polconv(polcconv if polcconv is not None else getattr(first if not isinstance(m, (tuple, list)) else maps[-1], "polcconv", "COSMO"))
     alms = [Alm(lmax, mmax, np.asarray(a, dtype=np.complex128)) for a in plan.map2alm(arrays)]
     return alms[0] if len(alms) == 1 else tuple(alms)
 
 
-def alm2map(alm, shape, wcs, dtype=np.float64, lib=None, devices=None):
+def alm2map(alm, shape, wcs, dtype=np.float64, lib=None, devices=None, polcconv="COSMO"):
     """alm2map(::Alm, shape, wcs) -> Enmap;  (::NTuple{2,Alm}) -> list of 2 Enmaps;  (::NTuple{3,Alm}) / Vector -> tuple
     (src/transforms.jl:206-265, return-type quirks of SURVEY.md F11 kept)."""
     alms = [alm] if isinstance(alm, Alm) else list(alm)
@@ -219,7 +258,10 @@ def alm2map(alm, shape, wcs, dtype=np.float64, lib=None, devices=None):
         raise ValueError("1, 2 or 3 Alm are supported")
     lmax, mmax = alms[0].lmax, alms[0].mmax
     plan = _plan_for(shape, wcs, lmax, mmax, dtype, lib, devices)
+    plan.set_polconv(polcconv)   # "IAU": the U map comes out with the IAU sign (tagged on the Enmap for write_map)
     maps = [Enmap(x, wcs) for x in plan.alm2map([a.alm for a in alms])]
+    for x in maps:
+        x.polcconv = polcconv
     if len(maps) == 1:
         return maps[0]
     if len(maps) == 2:

@@ -18,3 +18,12 @@ for f in FILES:
 np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_alm_golden.npz"), **out)
 for k, v in out.items():
     print(k, v.shape)
+
+# pixel-area vectors (python pixell's pixsizemap rows; test/test_geometry.jl:287-316 compares pixareamap against them) and the
+# reference's FITS I/O fixture (test/test_io.jl:4-14: a 100x100x3 Float64 CAR map), kept byte for byte
+import shutil
+HERE = os.path.dirname(os.path.abspath(__file__))
+np.savez_compressed(os.path.join(HERE, "ref_pixareas.npz"), fullsky=np.loadtxt(os.path.join(SRC, "fullsky_pixareas.dat")),
+                    box=np.loadtxt(os.path.join(SRC, "box_pixareas.dat")))
+shutil.copyfile(os.path.join(SRC, "test.fits"), os.path.join(HERE, "ref_test.fits"))
+os.chmod(os.path.join(HERE, "ref_test.fits"), 0o644)

@@ -851,3 +851,79 @@ def test_batched_spin0_equals_single_transforms(nbatch, dtype, res_deg=1.0, lmax
         ref = oracle_map2alm(Enmap(xs[1].astype(np.float64), wcs), lmax)[0]
         assert rel_rms(back[1], ref) < TOL64
     plan.close()
+
+
+# ---- the U-sign convention in the kernels, pixel-area ring weights -------------------------------
+@pytest.mark.parametrize("nshard", [1, 3])
+def test_polconv_iau(nshard, res_deg=1.0, lmax=120):
+    """pixsht_plan_set_polconv(IAU): the caller's U has the IAU sign (src/enmap.jl:178-196 flips it on the host at read time; here
+    the FFT kernels' row I/O does).  map2alm of (T, Q, -U) under IAU == map2alm of (T, Q, U), bit for bit; alm2map under IAU
+    returns -U; host and device pointers, single- and multi-GPU plans, QU alone; batches are untouched by the flag."""
+    import torch
+    shape, wcs = fullsky_geometry(res_deg * degree)
+    band = pixsht.sht_band(shape, wcs)
+    plan = Plan(band, lmax) if nshard == 1 else Plan(band, lmax, devices=_shard_devices(nshard))
+    alms = [synth_alm(lmax, lmax, 900 + c, spin2=c > 0) for c in range(3)]
+    plan.set_polconv("COSMO")
+    ref = plan.alm2map(alms)
+    back_ref = plan.map2alm(ref)
+    plan.set_polconv("IAU")
+    got = plan.alm2map(alms)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], -ref[2])
+    back = plan.map2alm(got)
+    for a, b in zip(back, back_ref):
+        assert rel_rms(a, b) < 1e-13          # the same sums; analysis accumulates atomically, so only to rounding
+    qu = plan.alm2map(alms[1:])
+    assert np.array_equal(qu[0], ref[1]) and np.array_equal(qu[1], -ref[2])
+    t = plan.alm2map(alms[:1])
+    assert np.array_equal(t[0], ref[0])       # a single component is never U
+    if nshard == 1:
+        d_alm = [torch.from_numpy(a).cuda() for a in alms]
+        d_map = [torch.empty(band.nx * band.nrings, dtype=torch.float64, device="cuda") for _ in range(3)]
+        plan.execute_ptrs(_lib.ALM2MAP, [a.data_ptr() for a in d_alm], [m.data_ptr() for m in d_map], _lib.DEVICE)
+        assert np.array_equal(d_map[2].cpu().numpy().reshape(band.nrings, band.nx).T, -ref[2])
+        bm = plan.alm2map_batch([alms[0], alms[0]])
+        assert np.array_equal(bm[1], ref[0])
+    plan.set_polconv("COSMO")
+    assert np.array_equal(plan.alm2map(alms)[2], ref[2])
+    with pytest.raises(PixshtError):
+        get_lib().check(get_lib().lib.pixsht_plan_set_polconv(plan.handle, 7))
+    plan.close()
+    # the Enmap front end: tag left by read_map(..., defer_polcconv=True), and the explicit keyword
+    if nshard == 1:
+        m = Enmap(np.asfortranarray(np.dstack([ref[0], ref[1], -ref[2]])), wcs)
+        a_kw = map2alm(m, lmax=lmax, polcconv="IAU")
+        m.polcconv = "IAU"
+        a_tag = map2alm(m, lmax=lmax)
+        a_ref = map2alm(Enmap(np.asfortranarray(np.dstack(ref)), wcs), lmax=lmax)
+        for x, y, z in zip(a_kw, a_tag, a_ref):
+            assert rel_rms(x.alm, z.alm) < 1e-13 and rel_rms(y.alm, z.alm) < 1e-13
+
+
+def test_pixel_area_weights_as_ring_weights(res_deg=2.0, lmax=60):
+    """pixareamap weights (src/projections/car_proj.jl:265-273, src/enmap_ops.jl:124-138) from pixsht_ring_pixarea, used as the ring
+    weights of a plan (pixsht_plan_create_rings): the pixel-area-weighted analysis, against the oracle with the same weights."""
+    from pixsht.transforms import ring_pixarea, pixareamap
+    shape, wcs = fullsky_geometry(res_deg * degree)
+    band = pixsht.sht_band(shape, wcs)
+    area = ring_pixarea(shape, wcs)                      # map row order
+    assert abs(np.sum(area) * shape[0] - 4 * np.pi) < 1e-12
+    assert np.array_equal(pixareamap(shape, wcs).data[5, :], area)
+    area_band = area[::-1] if band.flipy else area       # ascending colatitude, as the plan wants them
+    theta, wcc = cc_geometry(band.nrings_total, band.nphi)
+    lib = get_lib()
+    h = ctypes.c_void_p()
+    dp = ctypes.POINTER(ctypes.c_double)
+    th = np.ascontiguousarray(theta); wa = np.ascontiguousarray(area_band)
+    lib.check(lib.lib.pixsht_plan_create_rings(ctypes.byref(h), band.nrings, th.ctypes.data_as(dp), wa.ctypes.data_as(dp), band.nphi, band.phi0,
+                                               lmax, lmax, _lib.F64, 0))
+    rng = np.random.default_rng(17)
+    ring_major = np.ascontiguousarray(rng.standard_normal((band.nrings, band.nphi)))     # rings ascending in theta, no flips
+    out = np.zeros(nalm(lmax, lmax), dtype=np.complex128)
+    lib.check(lib.lib.pixsht_execute(h, _lib.MAP2ALM, 1, (ctypes.c_void_p * 1)(out.ctypes.data), (ctypes.c_void_p * 1)(ring_major.ctypes.data), _lib.HOST))
+    lib.lib.pixsht_plan_destroy(h)
+    ref = get_oracle("ld").map2alm(ring_major[None], theta, area_band, band.phi0, lmax, spin=0)[0]
+    assert rel_rms(out, ref) < TOL64
+    # and it is a different (lower-order) quadrature than Clenshaw-Curtis: close, not equal
+    ref_cc = get_oracle("ld").map2alm(ring_major[None], theta, wcc, band.phi0, lmax, spin=0)[0]
+    assert 1e-6 < rel_rms(out, ref_cc) < 0.2

@@ -61,8 +61,8 @@ __global__ void __launch_bounds__(LEG_NT) leg_synth_b(const LegParams P)
     __shared__ __align__(16) double sbuf[2 * STEPS * ND];
     __shared__ __align__(8) unsigned long long sbar[2];
     const int lane = threadIdx.x;
-    const int row = blockIdx.x / P.nchunks;
-    const int chunk = P.chunk_begin + P.nchunks - 1 - (int)(blockIdx.x % P.nchunks);
+    int row, chunk;
+    leg_unit(P, row, chunk);
     const int m = P.m_list ? P.m_list[row] : (P.m_begin + row);
     const int l0 = m;
     const int pair0 = chunk * (32 * R);
@@ -148,8 +148,8 @@ __global__ void __launch_bounds__(LEG_NT) leg_anal_b(const LegParams P, const Ba
     __shared__ __align__(16) double2 red[NV * G * 33];
     __shared__ __align__(8) unsigned long long sbar[2];
     const int lane = threadIdx.x;
-    const int row = blockIdx.x / P.nchunks;
-    const int chunk = P.chunk_begin + P.nchunks - 1 - (int)(blockIdx.x % P.nchunks);
+    int row, chunk;
+    leg_unit(P, row, chunk);
     const int m = P.m_list ? P.m_list[row] : (P.m_begin + row);
     const int l0 = m;
     const int pair0 = chunk * (32 * R);

@@ -106,6 +106,7 @@ struct pixsht_plan {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t kev[4] = {nullptr, nullptr, nullptr, nullptr};   // around the spin-0 / spin-2 Legendre kernel of the device path
     bool kev_on = false;
+    int leg_order = 1;                     // grid order of the Legendre work units (legendre.cuh: leg_unit; PIXSHT_LEG_ORDER)
     int polconv_iau = 0;                   // 1: the caller's U maps follow the IAU sign convention (pixsht_plan_set_polconv)
     double timings[8] = {0};
     int launches = 0;
@@ -463,6 +464,7 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     P->h_ringN = ringN; P->h_ringS = ringS;
     { int v = env_int("PIXSHT_SPLITS", 8); P->nsplit = (v >= 1 && v <= 8) ? v : 8; }
     P->batch_overlap = env_int("PIXSHT_BATCH_OVERLAP", 1) ? 1 : 0;
+    { const int v = env_int("PIXSHT_LEG_ORDER", 1); P->leg_order = v >= 0 ? v : 1; }   // chunk-major by default (measured, profiles/r02/legbench_order*.txt)
     { const int a = env_int("PIXSHT_ACT_LOG2", ACT_LOG2); P->seek_thr_log2 = (a <= -40 && a >= -200) ? a + SEEK_QUANT : SEEK_THR_LOG2; }
     P->stream = P->own_stream;
     for (auto& e : P->ev) CU(cudaEventCreate(&e));
@@ -641,6 +643,7 @@ static LegParams leg_params(pixsht_plan* P, const LegJob& J, int R)
     else { L.lact = P->d_lact2.p; L.st = P->d_st2.p; L.ad = P->d_ad2.p; L.gamma = P->d_gamma2.p; L.rec = P->d_rec2.p; }
     L.MP = J.ph.MP > 0 ? J.ph.MP : P->MP; L.col_is_row = J.ph.col_is_row;
     L.phase = J.ph.phase; L.ring_stride = (long long)J.ncomp * L.MP; L.c0 = J.c0;
+    L.order = P->leg_order;
     return L;
 }
 

@@ -474,9 +474,21 @@ def main():
         if rank == 0 and not args.no_e2e:
             import time
             mplan = Plan(band, lmax, dtype=npdt, devices=list(range(world)))
-            h_alm = [torch.empty(nalm, dtype=cdt).pin_memory() for _ in range(nc)]
-            h_out = [torch.empty(nalm, dtype=cdt).pin_memory() for _ in range(nc)]
-            h_map = [torch.empty(band.nx * band.nrings, dtype=rdt).pin_memory() for _ in range(nc)]
+            # page-locked host arrays from the library's own allocator (pixsht_host_alloc: what the Julia binding hands out;
+            # NUMA-interleaved on a multi-socket host because every GPU pulls its own columns / rows)
+            host_ptrs = []
+
+            def host_array(n, np_dtype):
+                ptr = ctypes.c_void_p()
+                lib.check(lib.lib.pixsht_host_alloc(ctypes.byref(ptr), int(n) * np.dtype(np_dtype).itemsize))
+                host_ptrs.append(ptr)
+                arr = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(int(n) * np.dtype(np_dtype).itemsize,)).view(np_dtype)
+                return torch.from_numpy(arr)
+
+            npc = np.complex128 if f64 else np.complex64
+            h_alm = [host_array(nalm, npc) for _ in range(nc)]
+            h_out = [host_array(nalm, npc) for _ in range(nc)]
+            h_map = [host_array(band.nx * band.nrings, npdt) for _ in range(nc)]
             for h, d in zip(h_alm, d_alm):
                 h.copy_(d)
             torch.cuda.synchronize(device)
@@ -500,8 +512,9 @@ def main():
                    "device_span_ms": span / args.steps,
                    "timing": "host wall clock around the blocking calls (they return when the caller's arrays are complete); "
                              "device_span_ms = max over the GPUs of the CUDA-event span of each call",
-                   "api": "pixsht_execute on a pixsht_plan_create_multi plan: one process, %d GPUs, whole pinned host arrays "
-                          "(each GPU copies its alm columns / map rows itself); no torch, no NCCL on this path" % world}
+                   "api": "pixsht_execute on a pixsht_plan_create_multi plan: one process, %d GPUs, whole page-locked host arrays from "
+                          "pixsht_host_alloc (each GPU copies its alm columns / map rows itself); no torch, no NCCL on this path" % world,
+                   "host_numa": os.environ.get("PIXSHT_HOST_NUMA", "interleave")}
             # the same plan with the data already distributed over the GPUs (nothing copied): pixsht_execute_sharded
             try:
                 sh = mplan.shards()
@@ -538,6 +551,9 @@ def main():
                 np.save(shm + "map%d.npy" % c, h_map[c].numpy())
                 np.save(shm + "alm%d.npy" % c, h_out[c].numpy())
             mplan.close()
+            del h_alm, h_out, h_map
+            for ptr in host_ptrs:
+                lib.lib.pixsht_host_free(ptr)
         dist.barrier(group=gloo)
         # ---- every rank: its device-resident slab / alm columns (the torchrun pipeline timed as `value`) against the one-process
         # result: the same (m, ring) sums wherever they run -> maps bit for bit, alm to rounding (atomic accumulation order)

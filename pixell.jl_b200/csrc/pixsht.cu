@@ -13,7 +13,13 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
+#ifndef PIXSHT_EMU
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+#endif
 
 using namespace pixsht;
 
@@ -1558,6 +1564,24 @@ extern "C" int pixsht_shared_free(void* dptr)
 // ---------------------------------------------------------------------------------------------------------------
 // page-locked host memory for the caller's arrays
 // ---------------------------------------------------------------------------------------------------------------
+// On a multi-socket host the pages of an allocation are interleaved over the NUMA nodes (mmap + mbind(MPOL_INTERLEAVE) +
+// cudaHostRegister): the GPUs of a multi-GPU plan hang off different sockets and each pulls its own alm columns / map rows, so a
+// buffer that lives on one node sends half of the traffic over the inter-socket link.  PIXSHT_HOST_NUMA=local keeps the
+// allocating thread's node (plain cudaHostAlloc); single-node hosts always take that path.
+#ifndef PIXSHT_EMU
+static std::mutex g_hostmu;
+static std::unordered_map<void*, size_t> g_host_mmaps;   // allocations made by mmap + register: address -> length
+static int numa_node_count()
+{
+    int n = 0;
+    for (int i = 0; i < 64; ++i) {
+        char path[64];
+        snprintf(path, sizeof(path), "/sys/devices/system/node/node%d", i);
+        if (access(path, F_OK) == 0) n = i + 1;
+    }
+    return n;
+}
+#endif
 extern "C" int pixsht_host_alloc(void** ptr, size_t bytes)
 {
     if (!ptr || bytes == 0) return fail(PIXSHT_ERR_ARG, "bad argument");
@@ -1567,12 +1591,45 @@ extern "C" int pixsht_host_alloc(void** ptr, size_t bytes)
 #ifdef PIXSHT_EMU
     if (cudaMallocHost(ptr, bytes) != cudaSuccess) return fail(PIXSHT_ERR_NOMEM, "host allocation failed");
 #else
+    const char* mode = getenv("PIXSHT_HOST_NUMA");
+    const int nodes = numa_node_count();
+    if (nodes > 1 && !(mode && strcmp(mode, "local") == 0)) {
+        const size_t page = 2u << 20, len = (bytes + page - 1) / page * page;
+        void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (p != MAP_FAILED) {
+            unsigned long mask[2] = {nodes >= 64 ? ~0ul : ((1ul << nodes) - 1), 0};
+            (void)syscall(SYS_mbind, p, len, 3 /* MPOL_INTERLEAVE */, mask, (unsigned long)(nodes + 1), 0u);   // best effort: a refused policy leaves the default
+            if (cudaHostRegister(p, len, cudaHostRegisterPortable) == cudaSuccess) {
+                std::lock_guard<std::mutex> lock(g_hostmu);
+                g_host_mmaps[p] = len;
+                *ptr = p;
+                return PIXSHT_OK;
+            }
+            (void)cudaGetLastError();
+            munmap(p, len);
+        }
+    }
     if (cudaHostAlloc(ptr, bytes, cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); return fail(PIXSHT_ERR_NOMEM, "page-locked host allocation failed"); }
 #endif
     return PIXSHT_OK;
 }
 extern "C" int pixsht_host_free(void* ptr)
 {
+#ifndef PIXSHT_EMU
+    if (ptr) {
+        size_t len = 0;
+        {
+            std::lock_guard<std::mutex> lock(g_hostmu);
+            auto it = g_host_mmaps.find(ptr);
+            if (it != g_host_mmaps.end()) { len = it->second; g_host_mmaps.erase(it); }
+        }
+        if (len) {
+            if (cudaHostUnregister(ptr) != cudaSuccess) (void)cudaGetLastError();
+            munmap(ptr, len);
+            return PIXSHT_OK;
+        }
+    }
+#endif
     if (ptr && cudaFreeHost(ptr) != cudaSuccess) { (void)cudaGetLastError(); return fail(PIXSHT_ERR_CUDA, "cudaFreeHost failed"); }
     return PIXSHT_OK;
 }

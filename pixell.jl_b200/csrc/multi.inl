@@ -50,6 +50,8 @@ struct pixsht_multi {
     std::vector<MultiDev> dev;
     std::vector<double> work_m;          // Legendre work per m (partition weight)
     int pieces = 3;                      // pieces of the first input / last output of a call (PIXSHT_MULTI_PIECES)
+    int ring_pieces = 3;                 // alm2map: ring-range pieces of the last family's Legendre launches (PIXSHT_MULTI_RING_PIECES)
+    int ring_pieces_anal = 1;            // map2alm: the same for the analysis (PIXSHT_MULTI_RING_PIECES_M2A; measured slower at 2 GPUs: 192 vs 179 ms)
     double last_ms_device = 0;
 };
 
@@ -149,6 +151,8 @@ extern "C" int pixsht_plan_create_multi(pixsht_plan** out, const pixsht_geom* g,
     M->ndev = ndev;
     M->dev.resize(ndev);
     { const int v = env_int("PIXSHT_MULTI_PIECES", 3); M->pieces = (v >= 1 && v <= 16) ? v : 3; }
+    { const int v = env_int("PIXSHT_MULTI_RING_PIECES", 3); M->ring_pieces = (v >= 1 && v <= 16) ? v : 3; }
+    { const int v = env_int("PIXSHT_MULTI_RING_PIECES_M2A", 1); M->ring_pieces_anal = (v >= 1 && v <= 16) ? v : 1; }
     auto bail = [&](int rc) { std::string keep = g_err; multi_destroy(M); g_err = keep; return rc; };
     for (int d = 0; d < ndev; ++d) {
         M->dev[d].device = devices[d];
@@ -242,8 +246,7 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
     std::vector<MultiFam> fams;
     if (ncomp == 1) fams = {{0, 0, 1}};
     else if (ncomp == 2) fams = {{2, 0, 2}};
-    else if (direction == PIXSHT_ALM2MAP) fams = {{2, 1, 2}, {0, 0, 1}};
-    else fams = {{0, 0, 1}, {2, 1, 2}};
+    else fams = {{0, 0, 1}, {2, 1, 2}};   // T first in both directions: its copies and stages are short, the polarisation pipelines behind it
     const int nf = (int)fams.size();
 
     // per shard: device-side views
@@ -282,8 +285,41 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
     bool pg_alm[3] = {false, false, false}, pg_map[3] = {false, false, false};   // pageable arrays: staged by each shard's copy threads
     if (!sharded) for (int c = 0; c < ncomp; ++c) { pg_alm[c] = host_is_pageable(alms[c]); pg_map[c] = host_is_pageable(maps[c]); }
 
+    // Ring-range pieces of a family's Legendre launches (host-pointer calls): chunk range [c0, c1) of the spin family's kernel and
+    // the band rings it covers, north [rn0, rn1) and south [rs0, rs1).  With them the rows of a family leave (alm2map) or arrive
+    // (map2alm) piece by piece under the Legendre launches of the other pieces, at the price of one cross-GPU barrier per piece.
+    struct RingPiece { int c0, c1, rn0, rn1, rs0, rs1; };
+    auto ring_pieces = [&](int spin, bool anal, int Q) -> std::vector<RingPiece> {
+        pixsht_plan* S0 = M->dev[0].sub;
+        const int R = leg_R(S0, spin, anal), nch = leg_total_chunks(S0, R);
+        Q = std::max(1, std::min(Q, nch));
+        std::vector<int> cb(Q + 1);
+        for (int k = 0; k <= Q; ++k) {
+            // chunks are numbered from the pole to the equator.  Synthesis: equal Legendre work (~ sin theta per pair), polar side
+            // first, so that the last (exposed) piece of the output has the fewest rows; analysis: equal row counts.
+            cb[k] = anal ? (int)((long long)nch * k / Q)
+                         : (int)std::lround(nch * (2.0 / 3.14159265358979323846) * std::acos(1.0 - (double)k / Q));
+        }
+        cb[0] = 0; cb[Q] = nch;
+        for (int k = 1; k <= Q; ++k) cb[k] = std::max(cb[k], cb[k - 1]);
+        std::vector<RingPiece> out;
+        for (int k = 0; k < Q; ++k) {
+            if (cb[k + 1] <= cb[k]) continue;
+            int rng[2][2];
+            if (!pair_range_rings(S0, std::min(S0->npairs, cb[k] * 32 * R), std::min(S0->npairs, cb[k + 1] * 32 * R), rng))
+                return {{0, nch, 0, P->nrings, 0, 0}};
+            out.push_back({cb[k], cb[k + 1], rng[0][0], rng[0][1], rng[1][0], rng[1][1]});
+        }
+        if (anal) std::reverse(out.begin(), out.end());   // analysis: equator (most work per row) first, polar caps last
+        if (out.empty()) out.push_back({0, nch, 0, P->nrings, 0, 0});
+        return out;
+    };
+    // the part of band rings [ra, rb) that lies in shard d's slab
+    auto clip = [&](const MultiDev& D, int ra, int rb, int& a, int& b) { a = std::max(ra, D.r0); b = std::min(rb, D.r1); return b > a; };
+    const int Q = sharded ? 1 : (direction == PIXSHT_ALM2MAP ? M->ring_pieces : M->ring_pieces_anal);
+
     if (direction == PIXSHT_ALM2MAP) {
-        // ---- inputs: each shard's alm columns, family by family; the first family in m pieces of equal work ----
+        // ---- inputs: each shard's alm columns, family by family (T first); the first family in m pieces of equal work ----
         std::vector<std::vector<std::vector<std::pair<int, int>>>> segs(nd, std::vector<std::vector<std::pair<int, int>>>(nf));
         std::vector<std::vector<std::vector<cudaEvent_t>>> ev_in(nd, std::vector<std::vector<cudaEvent_t>>(nf));
         for (int d = 0; d < nd; ++d) {
@@ -309,9 +345,29 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
                 }
             }
         }
+        // rows [ra, rb) of family F on shard d: FFT (every m fetched from its owner's phase buffer), then the copy out
+        auto emit_rows = [&](int d, const MultiFam& F, int ra, int rb) -> int {
+            MultiDev& D = M->dev[d];
+            pixsht_plan* S = D.sub;
+            int a, b;
+            if (!clip(D, ra, rb, a, b)) return PIXSHT_OK;
+            int rc2 = stage_fft(S, PIXSHT_ALM2MAP, ncomp, F.cb, F.cn, nullptr, a, b - a, V[d].dmap_virtual, S->stream, D.d_mtab.p);
+            if (rc2) return rc2;
+            if (!sharded) {
+                cudaEvent_t e = D.next_ev();
+                MCU(cudaEventRecord(e, S->stream));
+                MCU(cudaStreamWaitEvent(S->s_d2h, e, 0));
+                size_t off, nb; ring_rows(P, a, b, esz, off, nb);
+                for (int c = F.cb; c < F.cb + F.cn; ++c)
+                    MCU(host_copy_out(S, pg_map[c], (char*)maps[c] + off, (char*)V[d].dslab[c] + (off - V[d].row_off), nb, S->s_d2h));
+            }
+            return PIXSHT_OK;
+        };
         for (int fi = 0; fi < nf; ++fi) {
             const MultiFam& F = fams[fi];
-            // ---- Legendre stage on the shard's own m values, all rings ----
+            // the last family leaves in ring-range pieces (its rows go out under its own Legendre launches); the others in one
+            const std::vector<RingPiece> rp = ring_pieces(F.spin, false, fi == nf - 1 ? Q : 1);
+            // ---- inputs of the family on each shard: conversion + record preparation of its m values as they arrive ----
             for (int d = 0; d < nd; ++d) {
                 MultiDev& D = M->dev[d];
                 pixsht_plan* S = D.sub;
@@ -329,111 +385,147 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
                         }
                     }
                     rc = synth_prep(S, F.spin, V[d].dalm64[F.cb], V[d].dalm64[F.cb + F.cn - 1], sc, 0, -1, ml, j1 - j0); if (rc) return rc;
-                    const LegJob J = {F.spin, ncomp, F.cb, 0, j1 - j0, ml, 0, leg_total_chunks(S, leg_R(S, F.spin, false)),
-                                      {D.d_phase.p + j0, D.row_len, 1}};
-                    rc = synth_launch(S, J, sc); if (rc) return rc;
+                    if (rp.size() == 1) {
+                        // Legendre stage of this m piece, all rings
+                        const LegJob J = {F.spin, ncomp, F.cb, 0, j1 - j0, ml, 0, leg_total_chunks(S, leg_R(S, F.spin, false)),
+                                          {D.d_phase.p + j0, D.row_len, 1}};
+                        rc = synth_launch(S, J, sc); if (rc) return rc;
+                    }
                 }
-                MCU(cudaEventRecord(D.e_stage[fi], sc));
             }
-            // ---- barrier across the shards, then the ring FFTs of the shard's slab (all m, fetched from their owners) ----
-            for (int d = 0; d < nd; ++d) {
-                MultiDev& D = M->dev[d];
-                pixsht_plan* S = D.sub;
-                MCU(cudaSetDevice(D.device));
-                cudaStream_t sc = S->stream;
-                for (int e = 0; e < nd; ++e) if (e != d) MCU(cudaStreamWaitEvent(sc, M->dev[e].e_stage[fi], 0));
-                rc = stage_fft(S, PIXSHT_ALM2MAP, ncomp, F.cb, F.cn, nullptr, D.r0, D.r1 - D.r0, V[d].dmap_virtual, sc, D.d_mtab.p); if (rc) return rc;
-                if (!sharded && D.r1 > D.r0) {
-                    cudaEvent_t e = D.next_ev();
-                    MCU(cudaEventRecord(e, sc));
-                    MCU(cudaStreamWaitEvent(S->s_d2h, e, 0));
-                    for (int c = F.cb; c < F.cb + F.cn; ++c)
-                        MCU(host_copy_out(S, pg_map[c], (char*)maps[c] + V[d].row_off, V[d].dslab[c], V[d].slab_bytes, S->s_d2h));
+            for (size_t q = 0; q < rp.size(); ++q) {
+                std::vector<cudaEvent_t> e_q(nd, nullptr);
+                for (int d = 0; d < nd; ++d) {
+                    MultiDev& D = M->dev[d];
+                    pixsht_plan* S = D.sub;
+                    MCU(cudaSetDevice(D.device));
+                    if (rp.size() > 1 && !D.m_list.empty()) {
+                        // Legendre stage of the shard's m values on the ring pairs of this piece
+                        const LegJob J = {F.spin, ncomp, F.cb, 0, (int)D.m_list.size(), D.d_m_list.p, rp[q].c0, rp[q].c1 - rp[q].c0,
+                                          {D.d_phase.p, D.row_len, 1}};
+                        rc = synth_launch(S, J, S->stream); if (rc) return rc;
+                    }
+                    e_q[d] = D.next_ev();
+                    MCU(cudaEventRecord(e_q[d], S->stream));
+                }
+                // ---- barrier across the shards, then the ring FFTs of the piece's rows in each shard's slab ----
+                for (int d = 0; d < nd; ++d) {
+                    MultiDev& D = M->dev[d];
+                    MCU(cudaSetDevice(D.device));
+                    int a, b;
+                    const bool any = clip(D, rp[q].rn0, rp[q].rn1, a, b) || clip(D, rp[q].rs0, rp[q].rs1, a, b);
+                    if (!any) continue;
+                    for (int e = 0; e < nd; ++e) if (e != d) MCU(cudaStreamWaitEvent(D.sub->stream, e_q[e], 0));
+                    rc = emit_rows(d, F, rp[q].rn0, rp[q].rn1); if (rc) return rc;
+                    rc = emit_rows(d, F, rp[q].rs0, rp[q].rs1); if (rc) return rc;
                 }
             }
         }
     } else {
-        // ---- inputs: each shard's rows, family by family; the first family in ring pieces ----
+        // ---- inputs: each shard's rows, family by family (T first).  The first family arrives in plain pieces of its slab, the
+        // last one in the ring-range pieces of its analysis launches (equator first) ----
         struct RingSeg { int ra, rb; cudaEvent_t ev; };
-        std::vector<std::vector<std::vector<RingSeg>>> rsegs(nd, std::vector<std::vector<RingSeg>>(nf));
+        std::vector<std::vector<RingPiece>> rps(nf);
+        std::vector<std::vector<std::vector<std::vector<RingSeg>>>> rsegs(nd);   // [d][fi][piece] -> row ranges of the shard
+        for (int fi = 0; fi < nf; ++fi) rps[fi] = ring_pieces(fams[fi].spin, true, (fi == nf - 1 && nf > 1) || nf == 1 ? Q : 1);
         for (int d = 0; d < nd; ++d) {
             MultiDev& D = M->dev[d];
             pixsht_plan* S = D.sub;
             MCU(cudaSetDevice(D.device));
+            rsegs[d].resize(nf);
             const int nloc = D.r1 - D.r0;
             for (int fi = 0; fi < nf; ++fi) {
-                const int kk = std::max(1, std::min(fi == 0 ? K : 1, std::max(nloc, 1)));
-                for (int k = 0; k < kk; ++k) {
-                    const int ra = D.r0 + (int)((long long)nloc * k / kk), rb = D.r0 + (int)((long long)nloc * (k + 1) / kk);
-                    if (rb <= ra) continue;
-                    if (!sharded) {
-                        size_t off, nb; ring_rows(P, ra, rb, esz, off, nb);
-                        for (int c = fams[fi].cb; c < fams[fi].cb + fams[fi].cn; ++c)
-                            MCU(host_copy_in(S, pg_map[c], (char*)V[d].dslab[c] + (off - V[d].row_off), (const char*)maps[c] + off, nb, S->s_h2d));
+                rsegs[d][fi].resize(rps[fi].size());
+                for (size_t q = 0; q < rps[fi].size(); ++q) {
+                    std::vector<std::pair<int, int>> ranges;
+                    if (rps[fi].size() == 1) {
+                        const int kk = std::max(1, std::min(fi == 0 ? K : 1, std::max(nloc, 1)));
+                        for (int k = 0; k < kk; ++k) ranges.push_back({D.r0 + (int)((long long)nloc * k / kk), D.r0 + (int)((long long)nloc * (k + 1) / kk)});
+                    } else {
+                        int a, b;
+                        if (clip(D, rps[fi][q].rn0, rps[fi][q].rn1, a, b)) ranges.push_back({a, b});
+                        if (clip(D, rps[fi][q].rs0, rps[fi][q].rs1, a, b)) ranges.push_back({a, b});
                     }
-                    cudaEvent_t e = D.next_ev();
-                    MCU(cudaEventRecord(e, S->s_h2d));
-                    rsegs[d][fi].push_back({ra, rb, e});
+                    for (auto& rg : ranges) {
+                        if (rg.second <= rg.first) continue;
+                        if (!sharded) {
+                            size_t off, nb; ring_rows(P, rg.first, rg.second, esz, off, nb);
+                            for (int c = fams[fi].cb; c < fams[fi].cb + fams[fi].cn; ++c)
+                                MCU(host_copy_in(S, pg_map[c], (char*)V[d].dslab[c] + (off - V[d].row_off), (const char*)maps[c] + off, nb, S->s_h2d));
+                        }
+                        cudaEvent_t e = D.next_ev();
+                        MCU(cudaEventRecord(e, S->s_h2d));
+                        rsegs[d][fi][q].push_back({rg.first, rg.second, e});
+                    }
                 }
             }
         }
         for (int fi = 0; fi < nf; ++fi) {
             const MultiFam& F = fams[fi];
-            // ---- ring FFTs of the shard's rows; every m goes to its owner's phase buffer ----
-            for (int d = 0; d < nd; ++d) {
-                MultiDev& D = M->dev[d];
-                pixsht_plan* S = D.sub;
-                MCU(cudaSetDevice(D.device));
-                cudaStream_t sc = S->stream;
-                for (auto& sg : rsegs[d][fi]) {
-                    MCU(cudaStreamWaitEvent(sc, sg.ev, 0));
-                    rc = stage_fft(S, PIXSHT_MAP2ALM, ncomp, F.cb, F.cn, nullptr, sg.ra, sg.rb - sg.ra, V[d].dmap_virtual, sc, D.d_mtab.p); if (rc) return rc;
-                }
-                MCU(cudaEventRecord(D.e_stage[fi], sc));
-            }
-            // ---- barrier, then the Legendre analysis of the shard's own m values; the last family's alm leave in m pieces ----
-            for (int d = 0; d < nd; ++d) {
-                MultiDev& D = M->dev[d];
-                pixsht_plan* S = D.sub;
-                MCU(cudaSetDevice(D.device));
-                cudaStream_t sc = S->stream;
-                for (int e = 0; e < nd; ++e) if (e != d) MCU(cudaStreamWaitEvent(sc, M->dev[e].e_stage[fi], 0));
-                const int nm = (int)D.m_list.size();
-                if (nm == 0) continue;
-                {
-                    // the analysis kernels accumulate atomically: zero the shard's columns
-                    const dim3 grid((unsigned)std::max(1, std::min(8, (2 * P->lmax + 512) / 256)), (unsigned)nm);
-                    for (int c = F.cb; c < F.cb + F.cn; ++c) {
-                        PIXSHT_LAUNCH((k_cvt_rows<double, double, true>), grid, 256, 0, sc, D.d_m_list.p, P->lmax, (const double*)nullptr, (double*)V[d].dalm64[c]);
-                        S->launches++;
-                    }
-                }
-                const auto pieces = multi_m_pieces(M, D, fi == nf - 1 ? K : 1);
-                for (auto& pc : pieces) {
-                    const int j0 = pc.first, j1 = pc.second;
-                    const int* ml = D.d_m_list.p + j0;
-                    const LegJob J = {F.spin, ncomp, F.cb, 0, j1 - j0, ml, 0, leg_total_chunks(S, leg_R(S, F.spin, true)),
-                                      {D.d_phase.p + j0, D.row_len, 1}};
-                    rc = anal_launch(S, J, V[d].dalm64[F.cb], F.cn == 2 ? V[d].dalm64[F.cb + 1] : nullptr, sc); if (rc) return rc;
-                    if (f32) {
-                        const dim3 grid((unsigned)std::max(1, std::min(8, (2 * P->lmax + 512) / 256)), (unsigned)(j1 - j0));
+            const std::vector<RingPiece>& rp = rps[fi];
+            for (size_t q = 0; q < rp.size(); ++q) {
+                // ---- ring FFTs of the piece's rows on each shard; every m goes to its owner's phase buffer ----
+                std::vector<cudaEvent_t> e_q(nd, nullptr);
+                for (int d = 0; d < nd; ++d) {
+                    MultiDev& D = M->dev[d];
+                    pixsht_plan* S = D.sub;
+                    MCU(cudaSetDevice(D.device));
+                    cudaStream_t sc = S->stream;
+                    if (q == 0 && !D.m_list.empty()) {
+                        // the analysis kernels accumulate atomically (also across the ring pieces): zero the shard's columns once
+                        const dim3 grid((unsigned)std::max(1, std::min(8, (2 * P->lmax + 512) / 256)), (unsigned)D.m_list.size());
                         for (int c = F.cb; c < F.cb + F.cn; ++c) {
-                            PIXSHT_LAUNCH((k_cvt_rows<double, float, false>), grid, 256, 0, sc, ml, P->lmax, (const double*)V[d].dalm64[c], (float*)V[d].dalm[c]);
+                            PIXSHT_LAUNCH((k_cvt_rows<double, double, true>), grid, 256, 0, sc, D.d_m_list.p, P->lmax, (const double*)nullptr, (double*)V[d].dalm64[c]);
                             S->launches++;
                         }
                     }
-                    if (!sharded) {
-                        cudaEvent_t e = D.next_ev();
-                        MCU(cudaEventRecord(e, sc));
-                        MCU(cudaStreamWaitEvent(S->s_d2h, e, 0));
-                        for (int c = F.cb; c < F.cb + F.cn; ++c) {
-                            cudaError_t ce = cudaSuccess;
-                            multi_for_runs(P, D, j0, j1, [&](long long i0, long long i1) {
-                                if (ce == cudaSuccess)
-                                    ce = host_copy_out(S, pg_alm[c], (char*)alms[c] + (size_t)i0 * 2 * esz, (const char*)V[d].dalm[c] + (size_t)i0 * 2 * esz,
-                                                       (size_t)(i1 - i0) * 2 * esz, S->s_d2h);
-                            });
-                            MCU(ce);
+                    for (auto& sg : rsegs[d][fi][q]) {
+                        MCU(cudaStreamWaitEvent(sc, sg.ev, 0));
+                        rc = stage_fft(S, PIXSHT_MAP2ALM, ncomp, F.cb, F.cn, nullptr, sg.ra, sg.rb - sg.ra, V[d].dmap_virtual, sc, D.d_mtab.p); if (rc) return rc;
+                    }
+                    e_q[d] = D.next_ev();
+                    MCU(cudaEventRecord(e_q[d], sc));
+                }
+                // ---- barrier, then the Legendre analysis of the shard's own m values on the piece's ring pairs; on the last piece
+                // of the last family the m values are done in pieces whose alm columns leave one by one ----
+                const bool last = (q + 1 == rp.size());
+                for (int d = 0; d < nd; ++d) {
+                    MultiDev& D = M->dev[d];
+                    pixsht_plan* S = D.sub;
+                    MCU(cudaSetDevice(D.device));
+                    cudaStream_t sc = S->stream;
+                    const int nm = (int)D.m_list.size();
+                    if (nm == 0) continue;
+                    for (int e = 0; e < nd; ++e) if (e != d) MCU(cudaStreamWaitEvent(sc, e_q[e], 0));
+                    const int nch_all = leg_total_chunks(S, leg_R(S, F.spin, true));
+                    const int cq0 = rp.size() == 1 ? 0 : rp[q].c0, cq1 = rp.size() == 1 ? nch_all : rp[q].c1;
+                    const auto pieces = multi_m_pieces(M, D, (last && fi == nf - 1) ? K : 1);
+                    for (auto& pc : pieces) {
+                        const int j0 = pc.first, j1 = pc.second;
+                        const int* ml = D.d_m_list.p + j0;
+                        const LegJob J = {F.spin, ncomp, F.cb, 0, j1 - j0, ml, cq0, cq1 - cq0, {D.d_phase.p + j0, D.row_len, 1}};
+                        rc = anal_launch(S, J, V[d].dalm64[F.cb], F.cn == 2 ? V[d].dalm64[F.cb + 1] : nullptr, sc); if (rc) return rc;
+                        if (!last) continue;
+                        if (f32) {
+                            const dim3 grid((unsigned)std::max(1, std::min(8, (2 * P->lmax + 512) / 256)), (unsigned)(j1 - j0));
+                            for (int c = F.cb; c < F.cb + F.cn; ++c) {
+                                PIXSHT_LAUNCH((k_cvt_rows<double, float, false>), grid, 256, 0, sc, ml, P->lmax, (const double*)V[d].dalm64[c], (float*)V[d].dalm[c]);
+                                S->launches++;
+                            }
+                        }
+                        if (!sharded) {
+                            cudaEvent_t e = D.next_ev();
+                            MCU(cudaEventRecord(e, sc));
+                            MCU(cudaStreamWaitEvent(S->s_d2h, e, 0));
+                            for (int c = F.cb; c < F.cb + F.cn; ++c) {
+                                cudaError_t ce = cudaSuccess;
+                                multi_for_runs(P, D, j0, j1, [&](long long i0, long long i1) {
+                                    if (ce == cudaSuccess)
+                                        ce = host_copy_out(S, pg_alm[c], (char*)alms[c] + (size_t)i0 * 2 * esz, (const char*)V[d].dalm[c] + (size_t)i0 * 2 * esz,
+                                                           (size_t)(i1 - i0) * 2 * esz, S->s_d2h);
+                                });
+                                MCU(ce);
+                            }
                         }
                     }
                 }

@@ -56,6 +56,9 @@ struct FftParams {
     int ring_begin, ring_count; // band rings handled by this launch; ringlocal = ring - ring_begin
     int nx, ny, flipx, flipy;   // caller's map layout (column-major nx x ny), see pixsht_geom
     void* maps[4];              // up to 3 Stokes components, or a batch of up to 4 spin-0 maps
+    int vec_ok;                 // 1: every map pointer of the launch is aligned to two elements, so that a full even-length row can be
+                                // read / written as (x[2j], x[2j+1]) pairs in one access; 0: element-wise accesses (odd start offsets of
+                                // caller views would otherwise fault on the vector path)
     int neg_mask;               // bit c set: component c of the caller's maps carries the opposite sign (IAU <-> COSMO Stokes U,
                                 // src/enmap.jl:178-196 of the reference): negated here in the row I/O, no extra pass over the map
 };
@@ -544,7 +547,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
     const int c = P.c_begin + blockIdx.y;
     const int n = P.n, N = P.nphi;
     T* out = reinterpret_cast<T*>(P.maps[c]);
-    const bool vec = (P.nx == P.nphi) && P.packed;
+    const bool vec = (P.nx == P.nphi) && P.packed && P.vec_ok;
     const double sg = ((P.neg_mask >> c) & 1) ? -1.0 : 1.0;
 
     for (int rl = blockIdx.x; rl < P.ring_count; rl += gridDim.x) {
@@ -643,7 +646,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams 
     const int c = P.c_begin + blockIdx.y;
     const int n = P.n, N = P.nphi;
     const T* in = reinterpret_cast<const T*>(P.maps[c]);
-    const bool vec = (P.nx == P.nphi) && P.packed;
+    const bool vec = (P.nx == P.nphi) && P.packed && P.vec_ok;
     const double sg = ((P.neg_mask >> c) & 1) ? -1.0 : 1.0;
 
     for (int rl = blockIdx.x; rl < P.ring_count; rl += gridDim.x) {

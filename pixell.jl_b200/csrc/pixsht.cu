@@ -792,6 +792,12 @@ static int stage_fft(pixsht_plan* P, int dir, int ncomp, int c_begin, int c_coun
     F.nx = P->nx; F.ny = P->ny; F.flipx = P->flipx; F.flipy = P->flipy;
     for (int c = 0; c < ncomp; ++c) F.maps[c] = maps[c];
     F.neg_mask = (stokes && P->polconv_iau && ncomp >= 2) ? (1 << (ncomp - 1)) : 0;   // U is the last Stokes component
+    {
+        // the row start (rowy * nx elements past the base) is pair-aligned when the base is and nx is even (nx == nphi, packed)
+        const size_t al = 2 * (P->dtype == PIXSHT_F64 ? sizeof(double) : sizeof(float));
+        F.vec_ok = 1;
+        for (int c = c_begin; c < c_begin + c_count; ++c) if (reinterpret_cast<uintptr_t>(maps[c]) % al != 0) F.vec_ok = 0;
+    }
     F.packed = P->fft_packed; F.pt = P->fft_pt;
     if (P->fft_rows) {
         if (c_count > 4) return fail(PIXSHT_ERR_ARG, "at most 4 components per FFT launch");

@@ -927,3 +927,26 @@ def test_pixel_area_weights_as_ring_weights(res_deg=2.0, lmax=60):
     # and it is a different (lower-order) quadrature than Clenshaw-Curtis: close, not equal
     ref_cc = get_oracle("ld").map2alm(ring_major[None], theta, wcc, band.phi0, lmax, spin=0)[0]
     assert 1e-6 < rel_rms(out, ref_cc) < 0.2
+
+
+def test_device_views_at_odd_element_offsets(res_deg=2.0, lmax=60):
+    """Device pointers that start at an odd element offset (a torch / CUDA.jl view): the FFT kernels' two-element row accesses need
+    pair alignment, so such launches take the element-wise path instead of faulting (misaligned-address is sticky)."""
+    import torch
+    shape, wcs = fullsky_geometry(res_deg * degree)
+    band = pixsht.sht_band(shape, wcs)
+    for dt, tdt, cdt in ((np.float64, torch.float64, np.complex128), (np.float32, torch.float32, np.complex64)):
+        plan = Plan(band, lmax, dtype=dt)
+        alm = synth_alm(lmax, lmax, 41).astype(cdt)
+        ref = plan.alm2map([alm])[0]
+        npix = band.nx * band.nrings
+        buf = torch.zeros(npix + 3, dtype=tdt, device="cuda")
+        d_alm = torch.from_numpy(alm).cuda()
+        for off in (1, 3):
+            view = buf[off:off + npix]
+            plan.execute_ptrs(_lib.ALM2MAP, [d_alm.data_ptr()], [view.data_ptr()], _lib.DEVICE)
+            assert np.array_equal(view.cpu().numpy().reshape(band.nrings, band.nx).T, ref)
+            out = torch.zeros_like(d_alm)
+            plan.execute_ptrs(_lib.MAP2ALM, [out.data_ptr()], [view.data_ptr()], _lib.DEVICE)
+            assert rel_rms(out.cpu().numpy(), plan.map2alm([ref])[0]) < (1e-13 if dt == np.float64 else 1e-6)
+        plan.close()

@@ -40,8 +40,25 @@ struct MultiDev {
     std::vector<cudaEvent_t> pool; size_t npool = 0;
     cudaEvent_t next_ev()
     {
-        if (npool == pool.size()) { cudaEvent_t e = nullptr; if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr; pool.push_back(e); }
+        if (npool == pool.size()) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreateWithFlags(&e, trace ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            pool.push_back(e);
+        }
         return pool[npool++];
+    }
+    // PIXSHT_TRACE=1: a timeline of the shard's copies and stages (ms since the start of the call), printed to stderr after every
+    // multi-GPU execute -- the tool that shows which copy a host-pointer call is waiting for
+    bool trace = false;
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    void mark(cudaStream_t st, const char* fmt, int a = 0, int b = 0)
+    {
+        if (!trace) return;
+        cudaEvent_t e = next_ev();
+        if (!e || cudaEventRecord(e, st) != cudaSuccess) return;
+        char buf[64];
+        snprintf(buf, sizeof(buf), fmt, a, b);
+        marks.emplace_back(buf, e);
     }
 };
 
@@ -49,9 +66,13 @@ struct pixsht_multi {
     int ndev = 0;
     std::vector<MultiDev> dev;
     std::vector<double> work_m;          // Legendre work per m (partition weight)
-    int pieces = 3;                      // pieces of the first input / last output of a call (PIXSHT_MULTI_PIECES)
+    bool trace = false;                  // PIXSHT_TRACE
+    int pieces = 5;                      // pieces of the first input / last output of a call (PIXSHT_MULTI_PIECES)
     int ring_pieces = 3;                 // alm2map: ring-range pieces of the last family's Legendre launches (PIXSHT_MULTI_RING_PIECES)
-    int ring_pieces_anal = 1;            // map2alm: the same for the analysis (PIXSHT_MULTI_RING_PIECES_M2A; measured slower at 2 GPUs: 192 vs 179 ms)
+    int ring_pieces_anal = 2;            // map2alm: ring-range pieces of the last family's analysis (PIXSHT_MULTI_RING_PIECES_M2A): 2 = the equatorial
+                                         // third of the rows for all m, then the rest in m pieces (3 equal pieces measured slower at 2 GPUs: the alm
+                                         // can only leave after the last ring piece)
+    int ring_pieces_first = 5;           // map2alm: ring-range pieces of a family that is not the last (T of IQU; PIXSHT_MULTI_RING_PIECES_T)
     double last_ms_device = 0;
 };
 
@@ -150,9 +171,11 @@ extern "C" int pixsht_plan_create_multi(pixsht_plan** out, const pixsht_geom* g,
     pixsht_multi* M = new pixsht_multi();
     M->ndev = ndev;
     M->dev.resize(ndev);
-    { const int v = env_int("PIXSHT_MULTI_PIECES", 3); M->pieces = (v >= 1 && v <= 16) ? v : 3; }
+    { const int v = env_int("PIXSHT_MULTI_PIECES", 5); M->pieces = (v >= 1 && v <= 16) ? v : 5; }
+    M->trace = env_int("PIXSHT_TRACE", 0) != 0;
     { const int v = env_int("PIXSHT_MULTI_RING_PIECES", 3); M->ring_pieces = (v >= 1 && v <= 16) ? v : 3; }
-    { const int v = env_int("PIXSHT_MULTI_RING_PIECES_M2A", 1); M->ring_pieces_anal = (v >= 1 && v <= 16) ? v : 1; }
+    { const int v = env_int("PIXSHT_MULTI_RING_PIECES_M2A", 2); M->ring_pieces_anal = (v >= 1 && v <= 16) ? v : 2; }
+    { const int v = env_int("PIXSHT_MULTI_RING_PIECES_T", 5); M->ring_pieces_first = (v >= 1 && v <= 16) ? v : 5; }
     auto bail = [&](int rc) { std::string keep = g_err; multi_destroy(M); g_err = keep; return rc; };
     for (int d = 0; d < ndev; ++d) {
         M->dev[d].device = devices[d];
@@ -256,7 +279,7 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
         MultiDev& D = M->dev[d];
         pixsht_plan* S = D.sub;
         MCU(cudaSetDevice(D.device));
-        D.npool = 0; S->launches = 0;
+        D.npool = 0; S->launches = 0; D.trace = M->trace; D.marks.clear();
         View& v = V[d];
         size_t off, nb; ring_rows(P, D.r0, D.r1, esz, off, nb);
         v.row_off = off; v.slab_bytes = nb;
@@ -297,7 +320,9 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
         for (int k = 0; k <= Q; ++k) {
             // chunks are numbered from the pole to the equator.  Synthesis: equal Legendre work (~ sin theta per pair), polar side
             // first, so that the last (exposed) piece of the output has the fewest rows; analysis: equal row counts.
-            cb[k] = anal ? (int)((long long)nch * k / Q)
+            // Analysis with two pieces: the equatorial third of the rows (half of the Legendre work) and the polar rest -- the first is
+            // analysed for all m while the second is still on the wire, the second in m pieces whose alm columns leave one by one.
+            cb[k] = anal ? (Q == 2 ? (k == 1 ? (int)std::lround(nch * 2.0 / 3.0) : (int)((long long)nch * k / Q)) : (int)((long long)nch * k / Q))
                          : (int)std::lround(nch * (2.0 / 3.14159265358979323846) * std::acos(1.0 - (double)k / Q));
         }
         cb[0] = 0; cb[Q] = nch;
@@ -342,6 +367,7 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
                     cudaEvent_t e = D.next_ev();
                     MCU(cudaEventRecord(e, S->s_h2d));
                     ev_in[d][fi].push_back(e);
+                    D.mark(S->s_h2d, "h2d alm fam%d piece%d", fi, (int)ev_in[d][fi].size() - 1);
                 }
             }
         }
@@ -353,6 +379,7 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
             if (!clip(D, ra, rb, a, b)) return PIXSHT_OK;
             int rc2 = stage_fft(S, PIXSHT_ALM2MAP, ncomp, F.cb, F.cn, nullptr, a, b - a, V[d].dmap_virtual, S->stream, D.d_mtab.p);
             if (rc2) return rc2;
+            D.mark(S->stream, "fft rows %d..%d", a, b);
             if (!sharded) {
                 cudaEvent_t e = D.next_ev();
                 MCU(cudaEventRecord(e, S->stream));
@@ -360,6 +387,7 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
                 size_t off, nb; ring_rows(P, a, b, esz, off, nb);
                 for (int c = F.cb; c < F.cb + F.cn; ++c)
                     MCU(host_copy_out(S, pg_map[c], (char*)maps[c] + off, (char*)V[d].dslab[c] + (off - V[d].row_off), nb, S->s_d2h));
+                D.mark(S->s_d2h, "d2h rows %d..%d", a, b);
             }
             return PIXSHT_OK;
         };
@@ -390,6 +418,7 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
                         const LegJob J = {F.spin, ncomp, F.cb, 0, j1 - j0, ml, 0, leg_total_chunks(S, leg_R(S, F.spin, false)),
                                           {D.d_phase.p + j0, D.row_len, 1}};
                         rc = synth_launch(S, J, sc); if (rc) return rc;
+                        D.mark(sc, "legendre fam%d mpiece%d", fi, (int)k);
                     }
                 }
             }
@@ -404,6 +433,7 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
                         const LegJob J = {F.spin, ncomp, F.cb, 0, (int)D.m_list.size(), D.d_m_list.p, rp[q].c0, rp[q].c1 - rp[q].c0,
                                           {D.d_phase.p, D.row_len, 1}};
                         rc = synth_launch(S, J, S->stream); if (rc) return rc;
+                        D.mark(S->stream, "legendre fam%d ringpiece%d", fi, (int)q);
                     }
                     e_q[d] = D.next_ev();
                     MCU(cudaEventRecord(e_q[d], S->stream));
@@ -427,7 +457,10 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
         struct RingSeg { int ra, rb; cudaEvent_t ev; };
         std::vector<std::vector<RingPiece>> rps(nf);
         std::vector<std::vector<std::vector<std::vector<RingSeg>>>> rsegs(nd);   // [d][fi][piece] -> row ranges of the shard
-        for (int fi = 0; fi < nf; ++fi) rps[fi] = ring_pieces(fams[fi].spin, true, (fi == nf - 1 && nf > 1) || nf == 1 ? Q : 1);
+        // the last family: Q pieces (default 2: equatorial third for all m, then the rest in m pieces); a family before it (T of an IQU
+        // set): ring pieces too, so that its analysis starts when the first third of its rows is in (trace at 2 GPUs: the call waited
+        // 17 ms for the T rows) -- its alm leave in one go under the next family's stages
+        for (int fi = 0; fi < nf; ++fi) rps[fi] = ring_pieces(fams[fi].spin, true, sharded ? 1 : (fi == nf - 1 ? Q : M->ring_pieces_first));
         for (int d = 0; d < nd; ++d) {
             MultiDev& D = M->dev[d];
             pixsht_plan* S = D.sub;
@@ -456,6 +489,7 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
                         cudaEvent_t e = D.next_ev();
                         MCU(cudaEventRecord(e, S->s_h2d));
                         rsegs[d][fi][q].push_back({rg.first, rg.second, e});
+                        D.mark(S->s_h2d, "h2d rows %d..%d", rg.first, rg.second);
                     }
                 }
             }
@@ -482,6 +516,7 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
                     for (auto& sg : rsegs[d][fi][q]) {
                         MCU(cudaStreamWaitEvent(sc, sg.ev, 0));
                         rc = stage_fft(S, PIXSHT_MAP2ALM, ncomp, F.cb, F.cn, nullptr, sg.ra, sg.rb - sg.ra, V[d].dmap_virtual, sc, D.d_mtab.p); if (rc) return rc;
+                        D.mark(sc, "fft rows %d..%d", sg.ra, sg.rb);
                     }
                     e_q[d] = D.next_ev();
                     MCU(cudaEventRecord(e_q[d], sc));
@@ -505,6 +540,7 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
                         const int* ml = D.d_m_list.p + j0;
                         const LegJob J = {F.spin, ncomp, F.cb, 0, j1 - j0, ml, cq0, cq1 - cq0, {D.d_phase.p + j0, D.row_len, 1}};
                         rc = anal_launch(S, J, V[d].dalm64[F.cb], F.cn == 2 ? V[d].dalm64[F.cb + 1] : nullptr, sc); if (rc) return rc;
+                        D.mark(sc, "legendre fam%d ringpiece%d", fi, (int)q);
                         if (!last) continue;
                         if (f32) {
                             const dim3 grid((unsigned)std::max(1, std::min(8, (2 * P->lmax + 512) / 256)), (unsigned)(j1 - j0));
@@ -526,6 +562,7 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
                                 });
                                 MCU(ce);
                             }
+                            D.mark(S->s_d2h, "d2h alm fam%d m %d..", fi, j0);
                         }
                     }
                 }
@@ -552,6 +589,15 @@ static int execute_multi(pixsht_plan* P, int direction, int ncomp, void* const* 
         }
         host_copies_done(S);
         P->launches += S->launches;
+        if (D.trace && status == PIXSHT_OK) {
+            std::vector<std::pair<float, std::string>> tl;
+            for (auto& mk : D.marks) { float ms = 0; if (cudaEventElapsedTime(&ms, D.e_t0, mk.second) == cudaSuccess) tl.emplace_back(ms, mk.first); }
+            (void)cudaGetLastError();
+            std::sort(tl.begin(), tl.end());
+            fprintf(stderr, "[pixsht trace] %s shard %d (GPU %d):", direction == PIXSHT_ALM2MAP ? "alm2map" : "map2alm", d, D.device);
+            for (auto& t : tl) fprintf(stderr, " | %.1f %s", t.first, t.second.c_str());
+            fprintf(stderr, "\n");
+        }
     }
     for (auto& t : P->timings) t = 0;
     P->timings[5] = dev_ms;

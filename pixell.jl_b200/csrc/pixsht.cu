@@ -768,6 +768,18 @@ static int stage_phase2alm(pixsht_plan* P, int ncomp, PhaseRef ph, int nm, const
     }
     if (ncomp >= 2 && fam2) {
         const int c0 = ncomp == 3 ? 1 : 0;
+#ifdef PIXSHT_PROBES
+        // profiling aid: the spin-2 analysis as Q launches over chunk ranges (equator first), as the multi-GPU ring pieces do
+        if (const int Q = env_int("PIXSHT_DBG_ANAL_SPLIT", 0); Q > 1) {
+            const int nch = leg_total_chunks(P, P->R2a);
+            for (int k = Q - 1; k >= 0; --k) {
+                const int a = (int)((long long)nch * k / Q), b = (int)((long long)nch * (k + 1) / Q);
+                const LegJob J = {2, ncomp, c0, 0, nm, d_m_list, a, b - a, ph};
+                int rc = anal_launch(P, J, alm[c0], alm[c0 + 1], st); if (rc) return rc;
+            }
+            return PIXSHT_OK;
+        }
+#endif
         const LegJob J = {2, ncomp, c0, 0, nm, d_m_list, 0, leg_total_chunks(P, P->R2a), ph};
         int rc = anal_launch(P, J, alm[c0], alm[c0 + 1], st); if (rc) return rc;
     }

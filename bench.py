@@ -454,9 +454,13 @@ def main():
         s1, s2 = sht.stage_ms("alm2map"), sht.stage_ms("map2alm")
         leg_ms, fft_ms, a2a_ms = s1[0] + s2[2], s1[2] + s2[0], s1[1] + s2[1]
         t = torch.tensor([leg_ms, fft_ms, a2a_ms], device=device, dtype=torch.float64)
+        per_rank = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(per_rank, t)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         leg_ms, fft_ms, a2a_ms = [float(x) for x in t.tolist()]
         stage = {"legendre_ms": leg_ms, "fft_ms": fft_ms, "exchange_ms": a2a_ms,
+                 "per_rank": {"legendre_ms": [round(float(x[0]), 3) for x in per_rank], "fft_ms": [round(float(x[1]), 3) for x in per_rank],
+                              "barrier_ms": [round(float(x[2]), 3) for x in per_rank], "m_per_rank": None},
                  "exchange": "fused: the FFT kernels' row loads/stores fetch/put every m in the phase buffer of the GPU that owns it "
                              "(peer memory over NVLink, 256-byte runs); exchange_ms is the stage-ordering barrier (includes waiting "
                              "for the slowest rank)"}

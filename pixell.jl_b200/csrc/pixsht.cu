@@ -294,7 +294,8 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     {
         // ring pairs per thread: more pairs amortise the per-step operand loads (DESIGN.md "operand bandwidth") but widen a
         // warp's spread of activation degrees; the wide setting pays off once a chunk is < 5 % of the pairs
-        const bool wide = (nr + 1) / 2 >= 4096;
+        // (with the chunk-major grid order of round 2 the wide setting also wins at 2701 pairs: C3 78.3 -> 77.1 ms)
+        const bool wide = (nr + 1) / 2 >= 2048;
         int v = env_int("PIXSHT_R0", wide ? 8 : 4); P->R0 = (v == 1 || v == 2 || v == 3 || v == 4 || v == 6 || v == 8) ? v : 4;
         v = env_int("PIXSHT_R2", wide ? 4 : 2); P->R2 = (v == 1 || v == 2 || v == 3 || v == 4 || v == 6) ? v : 2;
         v = env_int("PIXSHT_R0A", P->R0); P->R0a = (v == 1 || v == 2 || v == 3 || v == 4 || v == 6 || v == 8) ? v : 4;

@@ -4,6 +4,7 @@
 #include "tables.cuh"
 #include "legendre.cuh"
 #include "legendre_batch.cuh"
+#include "legendre_2s.cuh"
 #include "fft.cuh"
 #include "../../include/pixsht.h"
 
@@ -99,6 +100,15 @@ struct pixsht_plan {
     DevBuf<int> d_lact0, d_lact2;          // activation table: first contributing l per (m, ring pair), built lazily per spin family
     DevBuf<double> d_st0, d_st2;           // recurrence state at l_act
     bool have_seek0 = false, have_seek2 = false;
+    // two-step spin-0 sequence (legendre_2s.cuh): tables built on first use
+    int twostep = 1;                       // PIXSHT_TWOSTEP=0 turns it off
+    int p_eq = 0;                          // first ring pair (pole -> equator) with |cos theta| < TWOSTEP_XMIN: from its chunk on, the standard kernels
+    int p_pole = 0;                        // ring pairs within TWOSTEP_POLE_DEG of a pole: their chunks stay with the standard kernels too
+    DevBuf<double> d_lg1_hi, d_lg1_lo;     // log2 of the seed prefactor sqrt(2m+3) lambda_mm
+    DevBuf<double2> d_ad1, d_wg1;          // (alpha_k, beta_k), (gamma_k c_{l_k+1}, gamma_k c_{l_k+2}) at alm_index(lmax, 0, m) + m + k
+    DevBuf<double> d_gam1, d_rec1;         // gamma_k; synthesis records (6 doubles per k)
+    DevBuf<int> d_lact1; DevBuf<double> d_st1;
+    bool have_seek1 = false;
     DevBuf<double2> d_tw, d_phi0tw;
     DevBuf<unsigned short> d_perm;
     // work buffers (grown on demand)
@@ -368,6 +378,19 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
         }
     }
 
+    // two-step spin-0 sequence: seed h_0 = sqrt(2m+3) lambda_mm; chunks that hold pairs with |cos theta| < TWOSTEP_XMIN stay standard
+    std::vector<double> lg1_hi(mmax + 1), lg1_lo(mmax + 1);
+    for (int m = 0; m <= mmax; ++m) {
+        const long double v = (long double)lg0_hi[m] + (long double)lg0_lo[m] + 0.5L * log2l(2.0L * m + 3.0L);
+        split_dd(v, lg1_hi[m], lg1_lo[m]);
+    }
+    P->p_eq = P->npairs;
+    for (int i = 0; i < P->npairs; ++i) if (std::fabs(hx[i]) < TWOSTEP_XMIN) { P->p_eq = i; break; }
+    for (int i = P->p_eq; i < P->npairs; ++i) if (std::fabs(hx[i]) >= TWOSTEP_XMIN) { P->p_eq = 0; break; }   // pairs not ordered pole -> equator: no two-step chunks
+    P->p_pole = 0;
+    while (P->p_pole < P->npairs && thn[P->p_pole] < (long double)TWOSTEP_POLE_DEG * LPI / 180.0L) ++P->p_pole;
+    P->twostep = env_int("PIXSHT_TWOSTEP", 1) ? 1 : 0;
+
     // ---- e^{+i m phi0} ----
     std::vector<double2> ph0(mmax + 1);
     for (int m = 0; m <= mmax; ++m) {
@@ -458,6 +481,7 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
     rc |= P->d_lch_hi.upload(lch_hi); rc |= P->d_lch_lo.upload(lch_lo); rc |= P->d_mlim.upload(mlim);
     rc |= P->d_ringN.upload(ringN); rc |= P->d_ringS.upload(ringS);
     rc |= P->d_lg0_hi.upload(lg0_hi); rc |= P->d_lg0_lo.upload(lg0_lo); rc |= P->d_lg2_hi.upload(lg2_hi); rc |= P->d_lg2_lo.upload(lg2_lo);
+    rc |= P->d_lg1_hi.upload(lg1_hi); rc |= P->d_lg1_lo.upload(lg1_lo);
     rc |= P->d_phi0tw.upload(ph0); rc |= P->d_perm.upload(perm);
     rc |= P->d_wgt.alloc(nr); rc |= P->d_tw.alloc(P->nphi);
     rc |= P->d_ad0.alloc(P->nalm); rc |= P->d_gamma0.alloc(P->nalm);
@@ -591,6 +615,8 @@ extern "C" void pixsht_plan_destroy(pixsht_plan* P)
     P->d_ad0.release(); P->d_gamma0.release(); P->d_ad2.release(); P->d_gamma2.release(); P->d_rec0.release(); P->d_rec2.release();
     P->d_tw.release(); P->d_phi0tw.release(); P->d_phase.release(); P->d_perm.release(); P->d_fftbuf.release();
     P->d_lact0.release(); P->d_lact2.release(); P->d_st0.release(); P->d_st2.release();
+    P->d_lg1_hi.release(); P->d_lg1_lo.release(); P->d_ad1.release(); P->d_wg1.release(); P->d_gam1.release(); P->d_rec1.release();
+    P->d_lact1.release(); P->d_st1.release();
     for (int c = 0; c < 8; ++c) { P->d_map[c].release(); P->d_alm[c].release(); P->d_alm64[c].release(); }
     for (auto& e : P->ev) if (e) cudaEventDestroy(e);
     for (auto& e : P->kev) if (e) cudaEventDestroy(e);
@@ -630,6 +656,37 @@ static int ensure_seek(pixsht_plan* P, int spin, cudaStream_t st)
     return PIXSHT_OK;
 }
 
+// Tables of the two-step spin-0 sequence (legendre_2s.cuh): coefficients and activation table, built on first use.
+static int ensure_twostep(pixsht_plan* P, cudaStream_t st)
+{
+    if (P->have_seek1) return PIXSHT_OK;
+    const size_t n = (size_t)(P->mmax + 1) * P->npairs;
+    if (P->d_ad1.alloc(P->nalm) || P->d_wg1.alloc(P->nalm) || P->d_gam1.alloc(P->nalm) || P->d_lact1.alloc(n) || P->d_st1.alloc(n * 2))
+        return fail(PIXSHT_ERR_NOMEM, "two-step table allocation failed");
+    PIXSHT_LAUNCH(k_coef_tables_2s, (P->mmax + 64) / 64, 64, 0, st, P->lmax, P->mmax, P->d_ad1.p, P->d_wg1.p, P->d_gam1.p);
+    SeekParams K;
+    memset(&K, 0, sizeof(K));
+    K.lmax = P->lmax; K.mmax = P->mmax; K.npairs = P->npairs; K.x = P->d_x.p;
+    K.lsh_hi = P->d_lsh_hi.p; K.lsh_lo = P->d_lsh_lo.p; K.lch_hi = P->d_lch_hi.p; K.lch_lo = P->d_lch_lo.p; K.mlim = P->d_mlim.p;
+    K.lgpref_hi = P->d_lg1_hi.p; K.lgpref_lo = P->d_lg1_lo.p; K.ad = P->d_ad1.p;
+    K.lact = P->d_lact1.p; K.st = P->d_st1.p;
+    K.thr_log2 = P->seek_thr_log2;
+    dim3 grid((P->npairs + 127) / 128, P->mmax + 1);
+    PIXSHT_LAUNCH(k_seek_table_2s, grid, 128, 0, st, K);
+    CU(cudaGetLastError());
+    P->have_seek1 = true;
+    return PIXSHT_OK;
+}
+// Chunks [lo, hi) (of 32 R pairs, pole -> equator) take the two-step spin-0 kernels; the polar chunk(s) and the equatorial one(s)
+// stay with the standard kernels (accuracy, legendre_2s.cuh).  hi <= lo: no two-step chunks (small maps).
+static void twostep_range(const pixsht_plan* P, int R, int& lo, int& hi)
+{
+    lo = (P->p_pole + 32 * R - 1) / (32 * R);
+    hi = P->twostep ? P->p_eq / (32 * R) : 0;
+    if (hi <= lo) { lo = 0; hi = 0; }
+}
+static bool twostep_any(const pixsht_plan* P, int R) { int lo, hi; twostep_range(P, R, lo, hi); return hi > lo; }
+
 // where the phase rows of a Legendre launch live: ring r at phase + r*ncomp*MP; columns are m (single GPU) or launch rows (m-sharded)
 struct PhaseRef { double2* phase; long long MP; int col_is_row; };   // MP = 0: the plan's own row length
 
@@ -652,6 +709,42 @@ static LegParams leg_params(pixsht_plan* P, const LegJob& J, int R)
     L.phase = J.ph.phase; L.ring_stride = (long long)J.ncomp * L.MP; L.c0 = J.c0;
     L.order = P->leg_order;
     return L;
+}
+// the same launch on the tables of the two-step spin-0 sequence (legendre_2s.cuh); anal: `rec` carries the output weights
+static LegParams leg_params_2s(pixsht_plan* P, const LegJob& J, int R, bool anal)
+{
+    LegParams L = leg_params(P, J, R);
+    L.lact = P->d_lact1.p; L.st = P->d_st1.p; L.ad = P->d_ad1.p; L.gamma = P->d_gam1.p;
+    L.rec = anal ? reinterpret_cast<const double*>(P->d_wg1.p) : P->d_rec1.p;
+    return L;
+}
+template <int R> static void launch_2s(bool anal, int grid, const LegParams& L, cudaStream_t st)
+{
+    if (anal) PIXSHT_LAUNCH(leg_anal_2s<R>, grid, LEG_NT, 0, st, L);
+    else PIXSHT_LAUNCH(leg_synth_2s<R>, grid, LEG_NT, 0, st, L);
+}
+static void launch_twostep(pixsht_plan* P, bool anal, int R, const LegParams& L, cudaStream_t st)
+{
+    const int grid = L.nm * L.nchunks;
+    if (grid <= 0) return;
+    switch (R) {
+        case 1: launch_2s<1>(anal, grid, L, st); break;
+        case 2: launch_2s<2>(anal, grid, L, st); break;
+        case 3: launch_2s<3>(anal, grid, L, st); break;
+        case 6: launch_2s<6>(anal, grid, L, st); break;
+        case 8: launch_2s<8>(anal, grid, L, st); break;
+        default: launch_2s<4>(anal, grid, L, st); break;
+    }
+    P->launches++;
+}
+// m range [ma, mb) whose alm columns are exactly the index range [first, first + count) (the callers pass whole columns)
+static void alm_range_to_m(const pixsht_plan* P, long long first, long long count, int& ma, int& mb)
+{
+    auto col = [&](int m) { return m > P->mmax ? P->nalm : alm_index(P->lmax, m, m); };
+    ma = 0;
+    while (ma <= P->mmax && col(ma) < first) ++ma;
+    mb = ma;
+    while (mb <= P->mmax && col(mb) < first + count) ++mb;
 }
 
 template <int SPIN>
@@ -692,6 +785,18 @@ static int synth_prep(pixsht_plan* P, int spin, const double2* a0, const double2
         if (P->d_rec0.n < (size_t)P->nalm * 4 && P->d_rec0.alloc((size_t)P->nalm * 4)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
         if (m_list) PIXSHT_LAUNCH(k_prep_synth_rows<0>, row_grid, 256, 0, st, m_list, P->lmax, P->d_ad0.p, P->d_gamma0.p, a0, a0, P->d_rec0.p);
         else PIXSHT_LAUNCH(k_prep_synth<0>, prep_grid, 256, 0, st, first, count, P->lmax, P->d_ad0.p, P->d_gamma0.p, a0, a0, P->d_rec0.p);
+        if (twostep_any(P, P->R0)) {
+            // the records of the two-step kernels for the same columns
+            rc = ensure_twostep(P, st); if (rc) return rc;
+            if (P->d_rec1.n < (size_t)P->nalm * 6 && P->d_rec1.alloc((size_t)P->nalm * 6)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
+            int ma = 0, mb = nm;
+            if (!m_list) alm_range_to_m(P, first, count, ma, mb);
+            if (mb > ma) {
+                const dim3 g2((unsigned)std::max(1, std::min(8, (P->lmax / 2 + 256) / 256)), (unsigned)(mb - ma));
+                PIXSHT_LAUNCH(k_prep_synth_2s, g2, 256, 0, st, m_list, ma, P->lmax, P->d_ad1.p, P->d_wg1.p, P->d_gam1.p, a0, P->d_rec1.p);
+                P->launches++;
+            }
+        }
     } else {
         if (P->d_rec2.n < (size_t)P->nalm * 6 && P->d_rec2.alloc((size_t)P->nalm * 6)) return fail(PIXSHT_ERR_NOMEM, "record buffer allocation failed");
         if (m_list) PIXSHT_LAUNCH(k_prep_synth_rows<2>, row_grid, 256, 0, st, m_list, P->lmax, P->d_ad2.p, P->d_gamma2.p, a0, a1, P->d_rec2.p);
@@ -722,7 +827,19 @@ static int synth_launch(pixsht_plan* P, const LegJob& J, cudaStream_t st)
     LegParams L = leg_params(P, J, R);
     dbg_restrict(L);
     if (P->kev_on) CU(cudaEventRecord(P->kev[J.spin == 0 ? 0 : 2], st));
-    if (J.spin == 0) launch_synth<0>(P, R, L, st); else launch_synth<2>(P, R, L, st);
+    if (J.spin == 0) {
+        // the chunks of the launch that lie in [lo, hi) go through the two-step kernels, the polar and equatorial rest through the standard ones
+        int lo, hi; twostep_range(P, R, lo, hi);
+        const int cb = L.chunk_begin, ce = L.chunk_begin + L.nchunks;
+        const int t0 = std::max(cb, lo), t1 = std::min(ce, hi);
+        if (t1 > t0) {
+            LegParams L2 = leg_params_2s(P, J, R, false);
+            L2.nm = L.nm; L2.chunk_begin = t0; L2.nchunks = t1 - t0;
+            launch_twostep(P, false, R, L2, st);
+            if (t0 > cb) { LegParams La = L; La.chunk_begin = cb; La.nchunks = t0 - cb; launch_synth<0>(P, R, La, st); }
+            if (ce > t1) { LegParams Lb = L; Lb.chunk_begin = t1; Lb.nchunks = ce - t1; launch_synth<0>(P, R, Lb, st); }
+        } else launch_synth<0>(P, R, L, st);
+    } else launch_synth<2>(P, R, L, st);
     if (P->kev_on) CU(cudaEventRecord(P->kev[J.spin == 0 ? 1 : 3], st));
     CU(cudaGetLastError());
     return PIXSHT_OK;
@@ -736,7 +853,20 @@ static int anal_launch(pixsht_plan* P, const LegJob& J, double2* out0, double2* 
     dbg_restrict(L);
     L.alm_out0 = out0; L.alm_out1 = out1;
     if (P->kev_on) CU(cudaEventRecord(P->kev[J.spin == 0 ? 0 : 2], st));
-    if (J.spin == 0) launch_anal<0>(P, R, L, st); else launch_anal<2>(P, R, L, st);
+    if (J.spin == 0) {
+        int lo, hi; twostep_range(P, R, lo, hi);
+        const int cb = L.chunk_begin, ce = L.chunk_begin + L.nchunks;
+        const int t0 = std::max(cb, lo), t1 = std::min(ce, hi);
+        if (t1 > t0) {
+            rc = ensure_twostep(P, st); if (rc) return rc;
+            LegParams L2 = leg_params_2s(P, J, R, true);
+            L2.alm_out0 = out0;
+            L2.nm = L.nm; L2.chunk_begin = t0; L2.nchunks = t1 - t0;
+            launch_twostep(P, true, R, L2, st);
+            if (t0 > cb) { LegParams La = L; La.chunk_begin = cb; La.nchunks = t0 - cb; launch_anal<0>(P, R, La, st); }
+            if (ce > t1) { LegParams Lb = L; Lb.chunk_begin = t1; Lb.nchunks = ce - t1; launch_anal<0>(P, R, Lb, st); }
+        } else launch_anal<0>(P, R, L, st);
+    } else launch_anal<2>(P, R, L, st);
     if (P->kev_on) CU(cudaEventRecord(P->kev[J.spin == 0 ? 1 : 3], st));
     CU(cudaGetLastError());
     return PIXSHT_OK;
@@ -1689,18 +1819,26 @@ extern "C" int pixsht_plan_info(const pixsht_plan* P, int32_t info[16])
 }
 
 // executed vs nominal (l, m, ring pair) steps of one spin family: the activation table decides what runs
-__global__ void k_count_work(int lmax, int mmax, int npairs, int s, const int* __restrict__ lact, unsigned long long* out)
+// pairs [p1, p2) run the two-step spin-0 kernels (table lact2s, steps of two degrees): their steps are counted in out[2]
+__global__ void k_count_work(int lmax, int mmax, int npairs, int s, const int* __restrict__ lact, unsigned long long* out, int p1 = 0, int p2 = 0,
+                             const int* __restrict__ lact2s = nullptr)
 {
     const long long n = (long long)(mmax + 1) * npairs;
-    unsigned long long exec = 0, nominal = 0;
+    unsigned long long exec = 0, nominal = 0, exec2 = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int m = (int)(i / npairs);
         const int l0 = m > s ? m : s;
         if (l0 <= lmax) nominal += (unsigned long long)(lmax - l0 + 1);
-        const int la = lact[i];
-        if (la <= lmax) exec += (unsigned long long)(lmax - la + 1);
+        const int pr = (int)(i - (long long)m * npairs);
+        if (pr >= p1 && pr < p2) {
+            const int la = lact2s[i], lmaxp = twostep_lmax(lmax, m);
+            if (la <= lmaxp) exec2 += (unsigned long long)(lmaxp - la + 1);
+        } else {
+            const int la = lact[i];
+            if (la <= lmax) exec += (unsigned long long)(lmax - la + 1);
+        }
     }
-    atomicAdd(&out[0], exec); atomicAdd(&out[1], nominal);
+    atomicAdd(&out[0], exec); atomicAdd(&out[1], nominal); atomicAdd(&out[2], exec2);
 }
 
 // executed steps per m (one CTA per m): the load-balancing weight of the m-sharded multi-GPU partition
@@ -1753,14 +1891,19 @@ extern "C" int pixsht_plan_work(pixsht_plan* P, int spin, double out[2])
     int rc = check_device(P->device); if (rc) return rc;
     rc = ensure_seek(P, spin, P->stream); if (rc) return rc;
     DevBuf<unsigned long long> d;
-    if (d.alloc(2)) return fail(PIXSHT_ERR_NOMEM, "allocation failed");
-    CU(cudaMemsetAsync(d.p, 0, 16, P->stream));
-    PIXSHT_LAUNCH(k_count_work, 1024, 256, 0, P->stream, P->lmax, P->mmax, P->npairs, spin, spin == 0 ? P->d_lact0.p : P->d_lact2.p, d.p);
-    unsigned long long h[2] = {0, 0};
-    CU(cudaMemcpyAsync(h, d.p, 16, cudaMemcpyDeviceToHost, P->stream));
+    if (d.alloc(3)) return fail(PIXSHT_ERR_NOMEM, "allocation failed");
+    CU(cudaMemsetAsync(d.p, 0, 24, P->stream));
+    // spin 0: the pairs of the two-step chunks execute steps of two degrees at 6 FP64 ops each = 1.5 steps of the 4-op count
+    int p1 = 0, p2 = 0;
+    if (spin == 0) { int lo, hi; twostep_range(P, P->R0, lo, hi); p1 = std::min(P->npairs, lo * 32 * P->R0); p2 = std::min(P->npairs, hi * 32 * P->R0); }
+    if (p2 > p1) { rc = ensure_twostep(P, P->stream); if (rc) return rc; }
+    PIXSHT_LAUNCH(k_count_work, 1024, 256, 0, P->stream, P->lmax, P->mmax, P->npairs, spin, spin == 0 ? P->d_lact0.p : P->d_lact2.p, d.p, p1, p2,
+                  p2 > p1 ? P->d_lact1.p : (const int*)nullptr);
+    unsigned long long h[3] = {0, 0, 0};
+    CU(cudaMemcpyAsync(h, d.p, 24, cudaMemcpyDeviceToHost, P->stream));
     CU(cudaStreamSynchronize(P->stream));
     d.release();
-    out[0] = (double)h[0]; out[1] = (double)h[1];
+    out[0] = (double)h[0] + 1.5 * (double)h[2]; out[1] = (double)h[1];
     return PIXSHT_OK;
 }
 

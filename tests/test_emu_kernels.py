@@ -179,3 +179,41 @@ def test_emu_ring_length_sweep(emu):
         x = np.asfortranarray(np.random.default_rng(nphi).standard_normal(shape))
         assert rel_rms(plan.map2alm([x])[0], oracle_map2alm(Enmap(x, wcs), lmax, kind="d")[0]) < 1e-12, nphi
         plan.close()
+
+
+def test_emu_two_step_spin0_kernels(emu, monkeypatch):
+    """The two-step spin-0 kernels (legendre_2s.cuh) on the emulation build.  At test sizes every ring pair would fall into the
+    chunks that stay with the standard kernels, so the ring tile is shrunk to one pair per lane (32 pairs per chunk): at 1 degree
+    (91 pairs) chunk 1 then runs the two-step kernels, chunk 0 (within 3 degrees of the pole) and chunk 2 (|cos theta| < 0.05)
+    the standard ones.  Checks: against the oracle, against the same plan with PIXSHT_TWOSTEP=0, an m-limited alm with the other
+    parity at the top of the columns, a cut-sky band."""
+    monkeypatch.setenv("PIXSHT_R0", "1"); monkeypatch.setenv("PIXSHT_R0A", "1")
+    shape, wcs = fullsky_geometry(1.0 * degree)
+    band = pixsht.sht_band(shape, wcs)
+    lmax = 90
+    alm = synth_alm(lmax, lmax, 300)
+    res = {}
+    for two in ("1", "0"):
+        monkeypatch.setenv("PIXSHT_TWOSTEP", two)
+        p = Plan(band, lmax, lib=emu)
+        ex, nom = p.work(0)
+        mp = p.alm2map([alm])[0]
+        res[two] = (mp, p.map2alm([mp])[0], ex / nom)
+        p.close()
+    assert res["1"][2] < 0.97 * res["0"][2]                      # fewer FP64 operations are executed
+    assert rel_rms(res["1"][0], oracle_alm2map(alm[None], shape, wcs, lmax)[:, :, 0]) < 1e-12
+    assert rel_rms(res["1"][0], res["0"][0]) < 1e-13
+    assert rel_rms(res["1"][1], res["0"][1]) < 1e-13
+    assert rel_rms(res["1"][1], oracle_map2alm(Enmap(res["0"][0], wcs), lmax)[0]) < 1e-12
+    monkeypatch.setenv("PIXSHT_TWOSTEP", "1")
+    p = Plan(band, 77, 40, lib=emu)
+    a = synth_alm(77, 40, 77)
+    mp = p.alm2map([a])[0]
+    assert rel_rms(mp, oracle_alm2map(a[None], shape, wcs, 77, mmax=40)[:, :, 0]) < 1e-12
+    assert rel_rms(p.map2alm([mp])[0], oracle_map2alm(Enmap(mp, wcs), 77, mmax=40)[0]) < 1e-12
+    p.close()
+    # a cut-sky, flipped band: single rings without a mirror partner
+    full = Enmap(gen_spin0(shape, 1.5), wcs)
+    sub = full[40:-25, 12:150]
+    got = map2alm(sub, lmax=60, lib=emu)
+    assert rel_rms(got.alm, oracle_map2alm(sub, 60)[0]) < 1e-12

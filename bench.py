@@ -465,7 +465,11 @@ def main():
                              "(peer memory over NVLink, 256-byte runs); exchange_ms is the stage-ordering barrier (includes waiting "
                              "for the slowest rank)"}
         nfam = 2 if nc == 3 else 1   # spin families: each costs a prep + a synthesis launch one way and an analysis launch back
-        launches = (3 * nfam + 2) * args.steps   # + one FFT launch per direction; per rank
+        # per rank and step, counted from the stage calls: per spin family a record preparation + its synthesis launch(es) one way and
+        # its analysis launch(es) back (T: up to three each -- two-step kernels plus the polar and equatorial chunks on the standard
+        # ones -- and a second preparation), one FFT launch per direction
+        nT = 3 if nc != 2 else 0
+        launches = ((2 + 2 * nT if nT else 0) + (3 if nc >= 2 else 0) + 2) * args.steps
         # ---- the ONE-PROCESS path (include/pixsht.h: pixsht_plan_create_multi): rank 0 alone drives all N GPUs through the
         # blocking C-ABI call on whole host arrays -- what a Julia caller gets.  The other ranks idle at a host-side (gloo)
         # barrier meanwhile, so that nothing of theirs runs on the GPUs.
@@ -624,8 +628,8 @@ def main():
         # per kernel: algorithmic flop = 2 * (4 | 12) * nominal (l, m, ring pair) steps; "executed" is the share
         # of those steps the activation table lets the kernel run, so achieved * executed / peak is the FP64 pipe utilisation
         kernels = []
-        for name, spin, key in (("leg_synth<0,%d>" % plan_info["R0"], 0, "synth0"), ("leg_synth<2,%d>" % plan_info["R2"], 2, "synth2"),
-                                ("leg_anal<0,%d>" % plan_info["R0a"], 0, "anal0"), ("leg_anal<2,%d>" % plan_info["R2a"], 2, "anal2")):
+        for name, spin, key in (("leg_synth_2s<%d> + leg_synth<0,%d>" % (plan_info["R0"], plan_info["R0"]), 0, "synth0"), ("leg_synth<2,%d>" % plan_info["R2"], 2, "synth2"),
+                                ("leg_anal_2s<%d> + leg_anal<0,%d>" % (plan_info["R0a"], plan_info["R0a"]), 0, "anal0"), ("leg_anal<2,%d>" % plan_info["R2a"], 2, "anal2")):
             if spin not in work:
                 continue
             ex, nom = work[spin]
@@ -633,7 +637,7 @@ def main():
             tf = fl / (kern_ms[key] * 1e-3) / 1e12
             kernels.append({"kernel": name, "ms": kern_ms[key], "algorithmic_flop": fl, "achieved": tf, "frac": tf / fp64_peak,
                             "executed_share": ex / nom, "fp64_pipe_utilisation": tf * ex / nom / fp64_peak,
-                            "traffic": traffic.get(name.split(",")[0] + ">")})
+                            "traffic": traffic.get(name.split(" + ")[-1].split(",")[0] + ">")})
         dom = max(kernels, key=lambda k: k["ms"])
         roofline = {"bound": "fp64_fma", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": fp64_peak, "unit": "TFLOP/s",
                     "frac": dom["frac"], "traffic": dom["traffic"], "peak_source": peak_src,

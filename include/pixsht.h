@@ -175,7 +175,9 @@ int64_t pixsht_nalm(int lmax, int mmax);
 int pixsht_plan_info(const pixsht_plan *plan, int32_t info[16]);
 /* info: [0] nphi [1] nrings [2] lmax [3] mmax [4] dtype [5] device [6] npairs (north/south folded ring pairs)
  *       [7] SM count [8] FFT length [9] kernels launched by the last execute [10..13] ring pairs per thread of the
- *       spin-0 / spin-2 synthesis and spin-0 / spin-2 analysis kernels [14] number of GPUs (shards) of the plan [15] reserved */
+ *       spin-0 / spin-2 synthesis and spin-0 / spin-2 analysis kernels [14] number of GPUs (shards) of the plan
+ *       [15] ring-FFT plan: threads per CTA | bit 16: outer passes fused into the row I/O (fft_edge.cuh) | bit 17: work buffers in
+ *            global memory | bits 20+: number of super-passes */
 /* (l, m, ring pair) steps of one spin family (0 or 2): out[0] = executed by the kernels (the plan-time activation table
  * skips what stays below 2^-90), out[1] = nominal count of SURVEY.md 8(d) (every l >= max(m,|s|) for every pair) */
 int pixsht_plan_work(pixsht_plan *plan, int spin, double out[2]);

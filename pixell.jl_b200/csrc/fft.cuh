@@ -26,9 +26,28 @@
 
 namespace pixsht {
 
+// Per-phase cycle counters of the FFT kernels (profiling builds only: -DPIXSHT_FFT_PROF; read by tools/legbench)
+#ifdef PIXSHT_FFT_PROF
+__device__ unsigned long long g_fft_prof[32];
+#define FFT_PROF_DECL long long prof_t_ = clock64()
+#define FFT_PROF_MARK(slot) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&g_fft_prof[slot], (unsigned long long)(t_ - prof_t_)); prof_t_ = t_; } } while (0)
+#define FFT_PROF_ARG , long long& prof_t_, int prof_base_
+#define FFT_PROF_PASS(b) , prof_t_, b
+#define FFT_PROF_MARK_PASS(ss) FFT_PROF_MARK(prof_base_ + (ss))
+#else
+#define FFT_PROF_DECL
+#define FFT_PROF_MARK(slot)
+#define FFT_PROF_ARG
+#define FFT_PROF_PASS(b)
+#define FFT_PROF_MARK_PASS(ss)
+#endif
+
 constexpr int FFT_MAXFAC = 24;
 constexpr int FFT_MAXRADIX = 64;       // largest radix done in registers / local memory; larger primes take pass_direct
-constexpr int FFT_MAXTHREADS = 640;
+#ifndef PIXSHT_FFT_MAXTHREADS
+#define PIXSHT_FFT_MAXTHREADS 640
+#endif
+constexpr int FFT_MAXTHREADS = PIXSHT_FFT_MAXTHREADS;
 
 struct FftParams {
     int nphi, n;                // ring length, complex FFT length: nphi/2 (even nphi, two real samples per complex), else nphi
@@ -59,12 +78,17 @@ struct FftParams {
     int vec_ok;                 // 1: every map pointer of the launch is aligned to two elements, so that a full even-length row can be
                                 // read / written as (x[2j], x[2j+1]) pairs in one access; 0: element-wise accesses (odd start offsets of
                                 // caller views would otherwise fault on the vector path)
+    int edge;                   // 1: kernels of fft_edge.cuh (first and last super-pass fused into the row I/O)
     int neg_mask;               // bit c set: component c of the caller's maps carries the opposite sign (IAU <-> COSMO Stokes U,
                                 // src/enmap.jl:178-196 of the reference): negated here in the row I/O, no extra pass over the map
 };
 
-template <class T> struct cpx { T x, y; };
+template <class T> struct alignas(2 * sizeof(T)) cpx { T x, y; };   // one 8- / 16-byte access in shared and global memory
+#ifdef PIXSHT_FFT_NOMATH   // timing experiment only (results are wrong): no arithmetic in the passes
+template <class T> __device__ __forceinline__ cpx<T> cmul(cpx<T> a, cpx<T> b) { return a; }
+#else
 template <class T> __device__ __forceinline__ cpx<T> cmul(cpx<T> a, cpx<T> b) { cpx<T> r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
+#endif
 template <class T> __device__ __forceinline__ cpx<T> cadd(cpx<T> a, cpx<T> b) { cpx<T> r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
 template <class T> __device__ __forceinline__ cpx<T> csub(cpx<T> a, cpx<T> b) { cpx<T> r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
 template <class T> __device__ __forceinline__ cpx<T> cconj(cpx<T> a) { cpx<T> r; r.x = a.x; r.y = -a.y; return r; }
@@ -193,37 +217,47 @@ __device__ __forceinline__ void dft5(cpx<T>* a)
 template <class T, int SIGN, int Q>
 __device__ __forceinline__ void dftq(cpx<T>* a)
 {
+#ifdef PIXSHT_FFT_NOMATH
+    return;
+#endif
     if constexpr (Q == 2) dft2<T, SIGN>(a);
     else if constexpr (Q == 3) dft3<T, SIGN>(a);
     else if constexpr (Q == 4) dft4<T, SIGN>(a);
     else dft5<T, SIGN>(a);
 }
-// one butterfly of a radix-Q pass at element pointer e (stride L); tk = kk, the index into the pass's twiddle table.
+// one butterfly of a radix-Q pass on registers; w1 = the pass twiddle W^kk (ignored when !tw).
 // DIF == false: decimation in time (twiddle, then DFT);  DIF == true: the transpose (DFT, then twiddle).
+template <class T, int SIGN, int Q, bool DIF>
+__device__ __forceinline__ void butterfly_regs(cpx<T>* a, cpx<T> w1, bool tw)
+{
+    cpx<T> w2, w3, w4;
+    w2.x = w3.x = w4.x = (T)1; w2.y = w3.y = w4.y = (T)0;
+    if (tw) {
+        if (Q > 2) w2 = cmul(w1, w1);   // squaring instead of a second table lookup (shared-memory pipe is the busier one)
+        if (Q > 3) w3 = cmul(w1, w2);
+        if (Q > 4) w4 = cmul(w2, w2);
+    }
+    auto WW = [&](int j) { return j == 1 ? w1 : (j == 2 ? w2 : (j == 3 ? w3 : w4)); };
+    if (!DIF && tw) {
+#pragma unroll
+        for (int j = 1; j < Q; ++j) a[j] = cmul(a[j], WW(j));
+    }
+    dftq<T, SIGN, Q>(a);
+    if (DIF && tw) {
+#pragma unroll
+        for (int j = 1; j < Q; ++j) a[j] = cmul(a[j], WW(j));
+    }
+}
+// the same at element pointer e (stride L); tk = kk, the index into the pass's twiddle table
 template <class T, int SIGN, int Q, bool DIF>
 __device__ __forceinline__ void butterfly(const cpx<T>* ptab, cpx<T>* e, int L, int tk)
 {
     cpx<T> a[Q];
 #pragma unroll
     for (int j = 0; j < Q; ++j) a[j] = e[(size_t)j * L];
-    cpx<T> w1, w2, w3, w4;
-    w1.x = w2.x = w3.x = w4.x = (T)1; w1.y = w2.y = w3.y = w4.y = (T)0;
-    if (tk) {
-        w1 = twp<T, SIGN>(ptab, tk, L > 128);
-        if (Q > 2) w2 = cmul(w1, w1);   // squaring instead of a second table lookup (shared-memory pipe is the busier one)
-        if (Q > 3) w3 = cmul(w1, w2);
-        if (Q > 4) w4 = cmul(w2, w2);
-    }
-    auto WW = [&](int j) { return j == 1 ? w1 : (j == 2 ? w2 : (j == 3 ? w3 : w4)); };
-    if (!DIF && tk) {
-#pragma unroll
-        for (int j = 1; j < Q; ++j) a[j] = cmul(a[j], WW(j));
-    }
-    dftq<T, SIGN, Q>(a);
-    if (DIF && tk) {
-#pragma unroll
-        for (int j = 1; j < Q; ++j) a[j] = cmul(a[j], WW(j));
-    }
+    cpx<T> w1; w1.x = (T)1; w1.y = (T)0;
+    if (tk) w1 = twp<T, SIGN>(ptab, tk, L > 128);
+    butterfly_regs<T, SIGN, Q, DIF>(a, w1, tk != 0);
 #pragma unroll
     for (int j = 0; j < Q; ++j) e[(size_t)j * L] = a[j];
 }
@@ -252,24 +286,20 @@ __device__ void butterfly_generic(const FftParams& P, const TwTab<T>& W, cpx<T>*
 //   DIT: x *= WA^{j1};  DFT_Q1 over j1;  y(j2,u1) *= WB^{j2} * W_{Q1Q2}^{j2 u1};  DFT_Q2 over j2;   DIF: the transpose.
 // TA / TB: the pass tables for the roots Q1*L and Q1*Q2*L, both indexed by kk.
 // TW == false: the super-pass at sub-length 1 (kk == 0 everywhere), no pass twiddles at all
+// the fused pair on registers a[j2][j1]; wa / wb = the pass twiddles W^kk of the roots Q1*L and Q1*Q2*L (ignored when !TW)
 template <class T, int SIGN, int Q1, int Q2, bool DIF, bool TW>
-__device__ __forceinline__ void butterfly2(const cpx<T>* TA, const cpx<T>* TB, cpx<T>* e, int L, int kk)
+__device__ __forceinline__ void butterfly2_regs(cpx<T> (*a)[Q1], cpx<T> wa, cpx<T> wb)
 {
     constexpr int S = Q1 * Q2;
-    cpx<T> a[Q2][Q1];
-#pragma unroll
-    for (int j2 = 0; j2 < Q2; ++j2)
-#pragma unroll
-        for (int j1 = 0; j1 < Q1; ++j1) a[j2][j1] = e[(size_t)(j2 * Q1 + j1) * L];
     // pass twiddles W^kk .. W^{4 kk} of the two roots as scalars (arrays that are only conditionally written end up in
     // local memory); for kk == 0 they are exactly 1
     cpx<T> wa1, wa2, wa3, wa4, wb1, wb2, wb3, wb4;
     wa1.x = wa2.x = wa3.x = wa4.x = wb1.x = wb2.x = wb3.x = wb4.x = (T)1;
     wa1.y = wa2.y = wa3.y = wa4.y = wb1.y = wb2.y = wb3.y = wb4.y = (T)0;
     if (TW) {
-        wa1 = twp<T, SIGN>(TA, kk, L > 128); wa2 = cmul(wa1, wa1);
+        wa1 = wa; wa2 = cmul(wa1, wa1);
         if (Q1 > 3) { wa3 = cmul(wa1, wa2); } if (Q1 > 4) { wa4 = cmul(wa2, wa2); }
-        wb1 = twp<T, SIGN>(TB, kk, L > 128); wb2 = cmul(wb1, wb1);
+        wb1 = wb; wb2 = cmul(wb1, wb1);
         if (Q2 > 3) { wb3 = cmul(wb1, wb2); } if (Q2 > 4) { wb4 = cmul(wb2, wb2); }
     }
     auto WA = [&](int j) { return j == 1 ? wa1 : (j == 2 ? wa2 : (j == 3 ? wa3 : wa4)); };
@@ -323,6 +353,19 @@ __device__ __forceinline__ void butterfly2(const cpx<T>* TA, const cpx<T>* TB, c
             }
         }
     }
+}
+template <class T, int SIGN, int Q1, int Q2, bool DIF, bool TW>
+__device__ __forceinline__ void butterfly2(const cpx<T>* TA, const cpx<T>* TB, cpx<T>* e, int L, int kk)
+{
+    cpx<T> a[Q2][Q1];
+#pragma unroll
+    for (int j2 = 0; j2 < Q2; ++j2)
+#pragma unroll
+        for (int j1 = 0; j1 < Q1; ++j1) a[j2][j1] = e[(size_t)(j2 * Q1 + j1) * L];
+    cpx<T> wa, wb;
+    wa.x = wb.x = (T)1; wa.y = wb.y = (T)0;
+    if (TW) { wa = twp<T, SIGN>(TA, kk, L > 128); wb = twp<T, SIGN>(TB, kk, L > 128); }
+    butterfly2_regs<T, SIGN, Q1, Q2, DIF, TW>(a, wa, wb);
 #pragma unroll
     for (int j2 = 0; j2 < Q2; ++j2)
 #pragma unroll
@@ -410,17 +453,18 @@ __device__ void pass_direct(const FftParams& P, const TwTab<T>& W, const cpx<T>*
 // DIF == false: digit-reversed input -> natural output (super-passes in order); DIF == true: natural input -> digit-reversed
 // output (super-passes in reverse order).  SIGN = -1 forward.  Returns the buffer that holds the result.
 // ptabs: 2 x 2 pass tables, double buffered; the tables of the FIRST super-pass were built by the caller before its last barrier.
+// Runs the super-passes sp_lo .. sp_lo + sp_cnt - 1 (all of them in the plain kernels; the inner ones in fft_edge.cuh).
 template <class T, int SIGN, bool DIF>
-__device__ cpx<T>* fft_passes(const FftParams& P, const TwTab<T>& W, cpx<T>* buf, cpx<T>* alt, cpx<T>* ptabs)
+__device__ cpx<T>* fft_passes(const FftParams& P, const TwTab<T>& W, cpx<T>* buf, cpx<T>* alt, cpx<T>* ptabs, int sp_lo, int sp_cnt FFT_PROF_ARG)
 {
     const int n = P.n;
-    for (int ss = 0; ss < P.nsp; ++ss) {
-        const int sp = DIF ? (P.nsp - 1 - ss) : ss;
+    for (int ss = 0; ss < sp_cnt; ++ss) {
+        const int sp = DIF ? (sp_lo + sp_cnt - 1 - ss) : (sp_lo + ss);
         const int t = P.sp_first[sp], q1 = P.fac[t];
         const int L = superpass_L(P, sp);
         const unsigned magic = P.magic[t];
         const cpx<T>* cur = ptabs + (ss & 1) * 2 * P.pt;
-        if (ss + 1 < P.nsp) {   // next super-pass's tables (read only after the barrier below)
+        if (ss + 1 < sp_cnt) {   // next super-pass's tables (read only after the barrier below)
             const int sp2 = DIF ? (sp - 1) : (sp + 1);
             superpass_tables<T>(P, ptabs + ((ss + 1) & 1) * 2 * P.pt, sp2, superpass_L(P, sp2));
         }
@@ -449,6 +493,7 @@ __device__ cpx<T>* fft_passes(const FftParams& P, const TwTab<T>& W, cpx<T>* buf
             }
         }
         __syncthreads();
+        FFT_PROF_MARK_PASS(ss);
     }
     return buf;
 }
@@ -549,6 +594,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
     T* out = reinterpret_cast<T*>(P.maps[c]);
     const bool vec = (P.nx == P.nphi) && P.packed && P.vec_ok;
     const double sg = ((P.neg_mask >> c) & 1) ? -1.0 : 1.0;
+    FFT_PROF_DECL;
 
     for (int rl = blockIdx.x; rl < P.ring_count; rl += gridDim.x) {
         const int ring = P.ring_begin + rl;
@@ -579,6 +625,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
                 for (int k = threadIdx.x; k <= n; k += blockDim.x) buf[k] = load_X<T>(P, row, ring, c, k, sg);
             }
             __syncthreads();
+            FFT_PROF_MARK(0);
 
             // pre-processing in place: Z[k] = (X[k] + conj X[n-k]) + i (X[k] - conj X[n-k]) e^{+2 pi i k/nphi}
             for (int k = threadIdx.x; k <= n / 2; k += blockDim.x) {
@@ -608,9 +655,10 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
         }
         superpass_tables<T>(P, ptabs, P.nsp - 1, superpass_L(P, P.nsp - 1));
         __syncthreads();
+        FFT_PROF_MARK(1);
         if (P.prefetch && !P.mtab && rl + (int)gridDim.x < P.ring_count)
             prefetch_row(P.phase + ((long long)(rl + gridDim.x) * P.ncomp + c) * P.MP, (size_t)(P.mmax + 1) * sizeof(double2));
-        const cpx<T>* res = fft_passes<T, +1, true>(P, W, buf, alt, ptabs);
+        const cpx<T>* res = fft_passes<T, +1, true>(P, W, buf, alt, ptabs, 0, P.nsp FFT_PROF_PASS(4));
         if (!GLOBAL) res = buf;   // no out-of-place pass without the global buffers: keeps the pointer provably shared
 
         // store into the caller's array (flips / partial rings by index arithmetic): packed x[2j] = Re z[j], x[2j+1] = Im z[j]
@@ -631,6 +679,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_phase2map(const FftParams 
             for (int j = threadIdx.x; j < P.nx; j += blockDim.x) orow[P.flipx ? (P.nx - 1 - j) : j] = res[P.perm[j]].x;
         }
         __syncthreads();   // the buffer is reused by this CTA's next ring
+        FFT_PROF_MARK(2);
     }
 }
 
@@ -648,6 +697,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams 
     const T* in = reinterpret_cast<const T*>(P.maps[c]);
     const bool vec = (P.nx == P.nphi) && P.packed && P.vec_ok;
     const double sg = ((P.neg_mask >> c) & 1) ? -1.0 : 1.0;
+    FFT_PROF_DECL;
 
     for (int rl = blockIdx.x; rl < P.ring_count; rl += gridDim.x) {
         const int ring = P.ring_begin + rl;
@@ -674,11 +724,12 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams 
         }
         superpass_tables<T>(P, ptabs, 0, 1);
         __syncthreads();
+        FFT_PROF_MARK(16);
         if (P.prefetch && rl + (int)gridDim.x < P.ring_count) {
             const int ringn = ring + (int)gridDim.x;
             prefetch_row(in + (size_t)(P.flipy ? (P.ny - 1 - ringn) : ringn) * P.nx, (size_t)P.nx * sizeof(T));
         }
-        cpx<T>* res = fft_passes<T, -1, false>(P, W, buf, alt, ptabs);
+        cpx<T>* res = fft_passes<T, -1, false>(P, W, buf, alt, ptabs, 0, P.nsp FFT_PROF_PASS(20));
         if (!GLOBAL) res = buf;   // no out-of-place pass without the global buffers: keeps the pointer provably shared
 
         if (P.packed) {
@@ -703,6 +754,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams 
                 }
             }
             __syncthreads();
+            FFT_PROF_MARK(17);
         }
 
         // phase_m = w * e^{-i m phi0} * F[m mod N]  (packed: conjugate symmetric upper half); coalesced row write
@@ -723,6 +775,7 @@ __global__ void __launch_bounds__(FFT_MAXTHREADS) fft_map2phase(const FftParams 
             }
         }
         __syncthreads();   // the buffer is reused by this CTA's next ring
+        FFT_PROF_MARK(18);
     }
 }
 

@@ -6,6 +6,7 @@
 #include "legendre_batch.cuh"
 #include "legendre_2s.cuh"
 #include "fft.cuh"
+#include "fft_edge.cuh"
 #include "../../include/pixsht.h"
 
 #include <algorithm>
@@ -79,6 +80,7 @@ struct pixsht_plan {
     size_t fft_smem = 0;
     int fft_packed = 1, fft_pt = FFT_PT;   // even nphi: real ring packed into nphi/2 complex samples; entries per pass table
     int fft_rows = 0;                      // > 0: ring work buffers in global memory, this many CTAs per component (fft.cuh FftParams::gbuf)
+    int fft_edge = 0;                      // 1: the kernels of fft_edge.cuh (outer super-passes fused into the row I/O; PIXSHT_FFT_EDGE=0 turns it off)
     int fft_persist = 0;                   // > 0 (default; PIXSHT_FFT_PERSIST=0 turns it off): shared-memory FFT CTAs loop over rings, this many
                                            //      resident per SM, and prefetch the next ring's input row into L2 during the passes
     long long fft_gslot = 0; int fft_galt = 0;
@@ -410,12 +412,19 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
         // super-passes: neighbouring radices from {2,3,4,5} whose product is <= PIXSHT_FFT_FUSE (default 16) share one
         // shared-memory round trip
         const int lim = std::min(env_int("PIXSHT_FFT_FUSE", FFT_FUSE_MAX), FFT_FUSE_MAX);
+        // Edge-fused kernels (fft_edge.cuh): the last pass stays a single radix (it is done on butterfly pairs in the phase-row
+        // I/O), the first super-pass is done in the map-row I/O.  Needs an even ring, radices 2..5 at both ends, no aliasing.
+        bool edge = P->fft_packed && P->nfac >= 2 && P->mmax <= P->nfft && env_int("PIXSHT_FFT_EDGE", 1) != 0
+                    && P->fac[0] >= 2 && P->fac[0] <= 5 && P->fac[P->nfac - 1] >= 2 && P->fac[P->nfac - 1] <= 5;
+        const int ngroup = edge ? P->nfac - 1 : P->nfac;   // factors grouped greedily; the edge plan keeps the last one apart
         P->nsp = 0;
-        for (int t = 0; t < P->nfac;) {
-            const bool small = P->fac[t] <= 5 && t + 1 < P->nfac && P->fac[t + 1] <= 5;
+        for (int t = 0; t < ngroup;) {
+            const bool small = P->fac[t] <= 5 && t + 1 < ngroup && P->fac[t + 1] <= 5;
             const int cnt = (small && P->fac[t] * P->fac[t + 1] <= lim && P->fac[t] * P->fac[t + 1] <= FFT_CST_MAX) ? 2 : 1;
             P->sp_first[P->nsp] = (unsigned char)t; P->sp_count[P->nsp] = (unsigned char)cnt; ++P->nsp; t += cnt;
         }
+        if (edge) { P->sp_first[P->nsp] = (unsigned char)(P->nfac - 1); P->sp_count[P->nsp] = 1; ++P->nsp; }
+        P->fft_edge = edge ? 1 : 0;
         std::vector<double2> cst((FFT_CST_MAX + 1) * FFT_CST_MAX);
         for (int S = 1; S <= FFT_CST_MAX; ++S)
             for (int k = 0; k < S; ++k) { const long double a = 2.0L * LPI * k / S; cst[S * FFT_CST_MAX + k] = make_double2((double)cosl(a), (double)(-sinl(a))); }
@@ -432,6 +441,13 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
         for (int i = 0; i < P->nfac; ++i) { if (P->fac[i] > FFT_MAXRADIX) big_prime = true; if (P->fac[i] <= 5) Lmax = std::max(Lmax, L); L *= P->fac[i]; }
         P->fft_smem = (size_t)(P->nfft + 1 + fft_tw_entries(P->nphi) + 4 * FFT_PT) * elem;
         const bool in_smem = !big_prime && P->fft_smem <= prop.sharedMemPerBlockOptin && Lmax <= 128 * (FFT_PT - 128) && !env_int("PIXSHT_FFT_GLOBAL", 0);
+        if (!in_smem) P->fft_edge = 0;
+        else if (P->fft_edge) {
+            const size_t tot = (elem == 16 ? ef_rot_offset<double>(P->nfft, P->nphi, FFT_PT) : ef_rot_offset<float>(P->nfft, P->nphi, FFT_PT))
+                               + (size_t)ef_rot_entries(P->mmax) * sizeof(double2);
+            if (tot <= prop.sharedMemPerBlockOptin) P->fft_smem = tot;
+            else P->fft_edge = 0;   // (the grouping with a single last radix stays: it is a valid plan for the plain kernels too)
+        }
         if (!in_smem) {
             P->fft_pt = 128 + std::max(FFT_PT - 128, (Lmax + 127) / 128);
             P->fft_smem = (size_t)(fft_tw_entries(P->nphi) + 4 * P->fft_pt) * elem;
@@ -450,7 +466,8 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
         ctas = std::max(1, std::min(ctas, 4));
         if (P->fft_rows) ctas = 1;   // global-memory work buffers: one large CTA per SM
         else if (env_int("PIXSHT_FFT_PERSIST", 1)) P->fft_persist = ctas;
-        const int tcap = std::max(64, std::min(FFT_MAXTHREADS, (FFT_MAXTHREADS / ctas) / 32 * 32));
+        const int maxthreads = P->fft_edge ? EF_MAXTHREADS : FFT_MAXTHREADS;
+        const int tcap = std::max(64, std::min(maxthreads, (maxthreads / ctas) / 32 * 32));
         const int tmax = std::max(64, std::min(tcap, (P->nfft / 2 + 31) / 32 * 32));
         const int tmin = std::max(64, tmax * 3 / 4 / 32 * 32);
         long long best = -1; int bt = tmax;
@@ -458,14 +475,15 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
             long long cost = 0;
             for (int i = 0; i < P->nsp; ++i) {
                 int pts = P->fac[P->sp_first[i]]; if (P->sp_count[i] == 2) pts *= P->fac[P->sp_first[i] + 1];
-                const int nb = P->nfft / pts;
+                int nb = P->nfft / pts;
+                if (P->fft_edge && i == P->nsp - 1) { nb = (nb - 1) / 2 + 2; pts *= 2; }   // butterfly pairs kk, L - kk
                 cost += (long long)((nb + t - 1) / t) * (pts + 2);
             }
             cost = cost * 64 + (tmax - t) / 32;   // ties: prefer more threads
             if (best < 0 || cost < best) { best = cost; bt = t; }
         }
         P->fft_threads = env_int("PIXSHT_FFT_THREADS", bt);
-        if (P->fft_threads < 32 || P->fft_threads > FFT_MAXTHREADS || P->fft_threads % 32) P->fft_threads = bt;
+        if (P->fft_threads < 32 || P->fft_threads > maxthreads || P->fft_threads % 32) P->fft_threads = bt;
     }
     std::vector<unsigned short> perm(P->nfft);
     for (int i = 0; i < P->nfft; ++i) perm[i] = (unsigned short)fft_digit_reverse(P->fac, P->nfac, P->nfft, i);
@@ -530,6 +548,10 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
         CU(cudaFuncSetAttribute(fft_map2phase<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
         CU(cudaFuncSetAttribute(fft_phase2map<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
         CU(cudaFuncSetAttribute(fft_map2phase<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(fft_phase2map_edge<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(fft_map2phase_edge<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(fft_phase2map_edge<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        CU(cudaFuncSetAttribute(fft_map2phase_edge<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
     }
 #endif
     return PIXSHT_OK;
@@ -953,7 +975,11 @@ static int stage_fft(pixsht_plan* P, int dir, int ncomp, int c_begin, int c_coun
     }
     dim3 grid(gx, c_count);
     const bool glob = P->fft_rows > 0, fwd = dir != PIXSHT_ALM2MAP;
-    if (P->dtype == PIXSHT_F64) {
+    F.edge = (P->fft_edge && !glob) ? 1 : 0;
+    if (F.edge) {
+        if (P->dtype == PIXSHT_F64) { if (!fwd) PIXSHT_LAUNCH((fft_phase2map_edge<double>), grid, P->fft_threads, P->fft_smem, st, F); else PIXSHT_LAUNCH((fft_map2phase_edge<double>), grid, P->fft_threads, P->fft_smem, st, F); }
+        else { if (!fwd) PIXSHT_LAUNCH((fft_phase2map_edge<float>), grid, P->fft_threads, P->fft_smem, st, F); else PIXSHT_LAUNCH((fft_map2phase_edge<float>), grid, P->fft_threads, P->fft_smem, st, F); }
+    } else if (P->dtype == PIXSHT_F64) {
         if (!glob) { if (!fwd) PIXSHT_LAUNCH((fft_phase2map<double, false>), grid, P->fft_threads, P->fft_smem, st, F); else PIXSHT_LAUNCH((fft_map2phase<double, false>), grid, P->fft_threads, P->fft_smem, st, F); }
         else { if (!fwd) PIXSHT_LAUNCH((fft_phase2map<double, true>), grid, P->fft_threads, P->fft_smem, st, F); else PIXSHT_LAUNCH((fft_map2phase<double, true>), grid, P->fft_threads, P->fft_smem, st, F); }
     } else {
@@ -1815,6 +1841,7 @@ extern "C" int pixsht_plan_info(const pixsht_plan* P, int32_t info[16])
     info[0] = P->nphi; info[1] = P->nrings; info[2] = P->lmax; info[3] = P->mmax; info[4] = P->dtype; info[5] = P->device;
     info[6] = P->npairs; info[7] = P->sm_count; info[8] = P->nfft; info[9] = P->launches; info[10] = P->R0; info[11] = P->R2; info[12] = P->R0a; info[13] = P->R2a;
     info[14] = P->multi ? multi_ndev(P->multi) : 1;
+    info[15] = P->fft_threads | (P->fft_edge ? (1 << 16) : 0) | (P->fft_rows ? (1 << 17) : 0) | (P->nsp << 20);
     return PIXSHT_OK;
 }
 
@@ -2019,5 +2046,17 @@ extern "C" int pixsht_measure_fma_peak(int device, double* fp64_tflops, double* 
     return PIXSHT_OK;
 #endif
 }
+
+#ifdef PIXSHT_FFT_PROF
+// profiling builds only (not declared in include/pixsht.h): per-phase cycle sums of the FFT kernels since the last call
+extern "C" int pixsht_debug_fft_prof(unsigned long long* out32)
+{
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpyFromSymbol(out32, g_fft_prof, 32 * sizeof(unsigned long long)));
+    unsigned long long z[32] = {0};
+    CU(cudaMemcpyToSymbol(g_fft_prof, z, sizeof(z)));
+    return PIXSHT_OK;
+}
+#endif
 
 #include "multi.inl"

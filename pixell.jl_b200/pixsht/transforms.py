@@ -116,7 +116,9 @@ class Plan:
         v = (ctypes.c_int32 * 16)()
         self.lib.check(self.lib.lib.pixsht_plan_info(self.handle, v))
         keys = ["nphi", "nrings", "lmax", "mmax", "dtype", "device", "npairs", "sm_count", "nfft", "launches", "R0", "R2", "R0a", "R2a", "ndev"]
-        return dict(zip(keys, list(v)))
+        d = dict(zip(keys, list(v)))
+        d["fft"] = dict(threads=v[15] & 0xffff, edge_fused=bool(v[15] >> 16 & 1), global_buffers=bool(v[15] >> 17 & 1), super_passes=v[15] >> 20)
+        return d
 
     def weights(self):
         w = np.empty(self.band.nrings)

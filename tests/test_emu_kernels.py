@@ -181,6 +181,59 @@ def test_emu_ring_length_sweep(emu):
         plan.close()
 
 
+def test_emu_edge_fused_fft(emu, monkeypatch):
+    """The edge-fused ring-FFT kernels (fft_edge.cuh: last pass on butterfly pairs in the phase-row I/O, first super-pass in the
+    map-row I/O) on ring lengths with every shape of plan: two super-passes only, single and paired first super-pass, even and
+    odd sub-length of the last pass (with / without the self-mirrored butterfly kk = L/2), every last radix 2..5; band limit at,
+    just below and far below the Nyquist mode of the ring; against the oracle and against the plain kernels (PIXSHT_FFT_EDGE=0)."""
+    import math
+    for nphi, lmaxs in ((12, (6, 5, 2)), (16, (8, 3)), (20, (10, 9)), (24, (12,)), (36, (17,)), (50, (25, 11)), (54, (27,)),
+                        (60, (30, 29)), (100, (50,)), (120, (59,)), (150, (75,)), (360, (180, 100))):
+        shape, wcs = fullsky_geometry((2 * math.pi / nphi, math.pi / 4))
+        band = pixsht.sht_band(shape, wcs)
+        for lmax in lmaxs:
+            res = {}
+            for edge in ("1", "0"):
+                monkeypatch.setenv("PIXSHT_FFT_EDGE", edge)
+                plan = Plan(band, lmax, lib=emu)
+                assert plan.info()["fft"]["edge_fused"] == (edge == "1"), (nphi, lmax, plan.info())
+                alm = synth_alm(lmax, lmax, nphi)
+                x = np.asfortranarray(np.random.default_rng(nphi).standard_normal(shape))
+                res[edge] = (plan.alm2map([alm])[0], plan.map2alm([x])[0])
+                plan.close()
+            ref = oracle_alm2map(alm[None], shape, wcs, lmax, kind="d")[:, :, 0]
+            assert rel_rms(res["1"][0], ref) < 1e-12, (nphi, lmax)
+            assert rel_rms(res["1"][1], oracle_map2alm(Enmap(x, wcs), lmax, kind="d")[0]) < 1e-12, (nphi, lmax)
+            assert rel_rms(res["1"][0], res["0"][0]) < 1e-14 and rel_rms(res["1"][1], res["0"][1]) < 1e-14, (nphi, lmax)
+    monkeypatch.setenv("PIXSHT_FFT_EDGE", "1")
+    # lmax beyond the ring's Nyquist mode (aliasing): stays with the plain kernels
+    shape, wcs = fullsky_geometry((2 * math.pi / 24, math.pi / 40))
+    plan = Plan(pixsht.sht_band(shape, wcs), 30, lib=emu)
+    assert not plan.info()["fft"]["edge_fused"]
+    plan.close()
+    # Float32 boundary, IQU, a cut-sky flipped band (element-wise row access, zero padding), Fejer-1 rings with a phi0 rotation
+    shape, wcs = fullsky_geometry(2.0 * degree, dims=(3,))
+    lmax = 60
+    alms = [synth_alm(lmax, lmax, 40 + c, spin2=c > 0) for c in range(3)]
+    ref = np.concatenate([oracle_alm2map(alms[0][None], shape, wcs, lmax), oracle_alm2map(np.stack(alms[1:]), shape, wcs, lmax, spin=2)], axis=2)
+    for dt, tol in ((np.float64, 1e-12), (np.float32, 2e-6)):
+        plan = Plan(pixsht.sht_band(shape[:2], wcs), lmax, dtype=dt, lib=emu)
+        assert plan.info()["fft"]["edge_fused"]
+        mp = plan.alm2map(alms)
+        assert max(rel_rms(mp[c], ref[:, :, c]) for c in range(3)) < tol
+        out = plan.map2alm([np.asfortranarray(ref[:, :, c], dtype=dt) for c in range(3)])
+        rt = oracle_map2alm(Enmap(ref[:, :, 0], wcs), lmax)[0]
+        reb = oracle_map2alm(Enmap(ref[:, :, 1:], wcs), lmax, spin=2)
+        assert max(rel_rms(out[0], rt), rel_rms(out[1], reb[0]), rel_rms(out[2], reb[1])) < tol
+        plan.close()
+    full = Enmap(gen_spin0(shape[:2], 1.5), wcs)
+    for sub in (full[20:-13, 7:150], full[::-1, ::-1][5:170, 10:80]):
+        got = map2alm(sub, lmax=50, lib=emu)
+        assert rel_rms(got.alm, oracle_map2alm(sub, 50)[0]) < 1e-12
+        back = alm2map(got, sub.data.shape, sub.wcs, lib=emu)
+        assert rel_rms(back.data, oracle_alm2map(got.alm[None], sub.data.shape, sub.wcs, 50)[:, :, 0]) < 1e-12
+
+
 def test_emu_two_step_spin0_kernels(emu, monkeypatch):
     """The two-step spin-0 kernels (legendre_2s.cuh) on the emulation build.  At test sizes every ring pair would fall into the
     chunks that stay with the standard kernels, so the ring tile is shrunk to one pair per lane (32 pairs per chunk): at 1 degree

@@ -89,6 +89,18 @@ int main(int argc, char** argv)
         CK(cudaMemcpy(hs, d_s, sizeof(hs), cudaMemcpyDeviceToHost));
         printf("  comp %d: map sum %.15e sq %.15e | alm sum %.15e sq %.15e\n", c, hs[0], hs[1], hs[2], hs[3]);
     }
+    if (auto prof = (int (*)(unsigned long long*))dlsym(h, "pixsht_debug_fft_prof")) {
+        // -DPIXSHT_FFT_PROF builds: share of each phase in the FFT kernels' CTA time (cycle sums of thread 0 over all CTAs and calls)
+        unsigned long long c[32]; prof(c);
+        const char* names[2][4] = {{"load", "pre", "store", ""}, {"load", "post", "store", ""}};
+        for (int d = 0; d < 2; ++d) {
+            double tot = 0; for (int k = 0; k < 16; ++k) tot += (double)c[16 * d + k];
+            printf("  %s phases:", d ? "fft_map2phase" : "fft_phase2map");
+            for (int k = 0; k < 3; ++k) printf(" %s %.1f%%", names[d][k], 100.0 * c[16 * d + k] / tot);
+            for (int k = 4; k < 12; ++k) if (c[16 * d + k]) printf(" pass%d %.1f%%", k - 4, 100.0 * c[16 * d + k] / tot);
+            printf("  (cycles per ring-call sum %.3e)\n", tot);
+        }
+    }
     p_pixsht_plan_destroy(P);
     return 0;
 }

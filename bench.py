@@ -649,7 +649,7 @@ def main():
     else:
         roofline = dict(stage_roof, bound="fp64_fma", traffic=None, peak_source=peak_src)
     fft_bytes = 2.0 * (nc * band.nx * nrings * esz + nc * (lmax + 1) * nrings * 16)
-    roofline_fft = {"bound": "hbm", "kernel": "fft_phase2map + fft_map2phase", "achieved": fft_bytes / world / (fft_ms * 1e-3) / 1e9,
+    roofline_fft = {"bound": "hbm", "kernel": "fft_phase2map_edge + fft_map2phase_edge" if plan_info.get("fft", {}).get("edge_fused") else "fft_phase2map + fft_map2phase", "achieved": fft_bytes / world / (fft_ms * 1e-3) / 1e9,
                     "peak": hbm_peak, "unit": "GB/s", "traffic": traffic.get("fft"), "peak_source": hbm_src,
                     "algorithmic_bytes_per_step": fft_bytes}
     roofline_fft["frac"] = roofline_fft["achieved"] / hbm_peak

@@ -84,11 +84,7 @@ struct FftParams {
 };
 
 template <class T> struct alignas(2 * sizeof(T)) cpx { T x, y; };   // one 8- / 16-byte access in shared and global memory
-#ifdef PIXSHT_FFT_NOMATH   // timing experiment only (results are wrong): no arithmetic in the passes
-template <class T> __device__ __forceinline__ cpx<T> cmul(cpx<T> a, cpx<T> b) { return a; }
-#else
 template <class T> __device__ __forceinline__ cpx<T> cmul(cpx<T> a, cpx<T> b) { cpx<T> r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
-#endif
 template <class T> __device__ __forceinline__ cpx<T> cadd(cpx<T> a, cpx<T> b) { cpx<T> r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
 template <class T> __device__ __forceinline__ cpx<T> csub(cpx<T> a, cpx<T> b) { cpx<T> r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
 template <class T> __device__ __forceinline__ cpx<T> cconj(cpx<T> a) { cpx<T> r; r.x = a.x; r.y = -a.y; return r; }
@@ -217,9 +213,6 @@ __device__ __forceinline__ void dft5(cpx<T>* a)
 template <class T, int SIGN, int Q>
 __device__ __forceinline__ void dftq(cpx<T>* a)
 {
-#ifdef PIXSHT_FFT_NOMATH
-    return;
-#endif
     if constexpr (Q == 2) dft2<T, SIGN>(a);
     else if constexpr (Q == 3) dft3<T, SIGN>(a);
     else if constexpr (Q == 4) dft4<T, SIGN>(a);

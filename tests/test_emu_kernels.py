@@ -187,24 +187,25 @@ def test_emu_edge_fused_fft(emu, monkeypatch):
     odd sub-length of the last pass (with / without the self-mirrored butterfly kk = L/2), every last radix 2..5; band limit at,
     just below and far below the Nyquist mode of the ring; against the oracle and against the plain kernels (PIXSHT_FFT_EDGE=0)."""
     import math
-    for nphi, lmaxs in ((12, (6, 5, 2)), (16, (8, 3)), (20, (10, 9)), (24, (12,)), (36, (17,)), (50, (25, 11)), (54, (27,)),
-                        (60, (30, 29)), (100, (50,)), (120, (59,)), (150, (75,)), (360, (180, 100))):
+    for nphi, lmaxs, both in ((12, (6, 5), True), (16, (8,), False), (20, (10, 9), False), (50, (25,), True), (54, (27,), False),
+                              (60, (29,), True), (100, (50,), False), (360, (180,), True)):
         shape, wcs = fullsky_geometry((2 * math.pi / nphi, math.pi / 4))
         band = pixsht.sht_band(shape, wcs)
         for lmax in lmaxs:
             res = {}
-            for edge in ("1", "0"):
+            alm = synth_alm(lmax, lmax, nphi)
+            x = np.asfortranarray(np.random.default_rng(nphi).standard_normal(shape))
+            for edge in (("1", "0") if both else ("1",)):
                 monkeypatch.setenv("PIXSHT_FFT_EDGE", edge)
                 plan = Plan(band, lmax, lib=emu)
                 assert plan.info()["fft"]["edge_fused"] == (edge == "1"), (nphi, lmax, plan.info())
-                alm = synth_alm(lmax, lmax, nphi)
-                x = np.asfortranarray(np.random.default_rng(nphi).standard_normal(shape))
                 res[edge] = (plan.alm2map([alm])[0], plan.map2alm([x])[0])
                 plan.close()
             ref = oracle_alm2map(alm[None], shape, wcs, lmax, kind="d")[:, :, 0]
             assert rel_rms(res["1"][0], ref) < 1e-12, (nphi, lmax)
             assert rel_rms(res["1"][1], oracle_map2alm(Enmap(x, wcs), lmax, kind="d")[0]) < 1e-12, (nphi, lmax)
-            assert rel_rms(res["1"][0], res["0"][0]) < 1e-14 and rel_rms(res["1"][1], res["0"][1]) < 1e-14, (nphi, lmax)
+            if both:
+                assert rel_rms(res["1"][0], res["0"][0]) < 1e-14 and rel_rms(res["1"][1], res["0"][1]) < 1e-14, (nphi, lmax)
     monkeypatch.setenv("PIXSHT_FFT_EDGE", "1")
     # lmax beyond the ring's Nyquist mode (aliasing): stays with the plain kernels
     shape, wcs = fullsky_geometry((2 * math.pi / 24, math.pi / 40))
@@ -212,8 +213,8 @@ def test_emu_edge_fused_fft(emu, monkeypatch):
     assert not plan.info()["fft"]["edge_fused"]
     plan.close()
     # Float32 boundary, IQU, a cut-sky flipped band (element-wise row access, zero padding), Fejer-1 rings with a phi0 rotation
-    shape, wcs = fullsky_geometry(2.0 * degree, dims=(3,))
-    lmax = 60
+    shape, wcs = fullsky_geometry(4.0 * degree, dims=(3,))
+    lmax = 40
     alms = [synth_alm(lmax, lmax, 40 + c, spin2=c > 0) for c in range(3)]
     ref = np.concatenate([oracle_alm2map(alms[0][None], shape, wcs, lmax), oracle_alm2map(np.stack(alms[1:]), shape, wcs, lmax, spin=2)], axis=2)
     for dt, tol in ((np.float64, 1e-12), (np.float32, 2e-6)):
@@ -227,11 +228,11 @@ def test_emu_edge_fused_fft(emu, monkeypatch):
         assert max(rel_rms(out[0], rt), rel_rms(out[1], reb[0]), rel_rms(out[2], reb[1])) < tol
         plan.close()
     full = Enmap(gen_spin0(shape[:2], 1.5), wcs)
-    for sub in (full[20:-13, 7:150], full[::-1, ::-1][5:170, 10:80]):
-        got = map2alm(sub, lmax=50, lib=emu)
-        assert rel_rms(got.alm, oracle_map2alm(sub, 50)[0]) < 1e-12
+    for sub in (full[10:-7, 4:40], full[::-1, ::-1][3:85, 5:40]):
+        got = map2alm(sub, lmax=30, lib=emu)
+        assert rel_rms(got.alm, oracle_map2alm(sub, 30)[0]) < 1e-12
         back = alm2map(got, sub.data.shape, sub.wcs, lib=emu)
-        assert rel_rms(back.data, oracle_alm2map(got.alm[None], sub.data.shape, sub.wcs, 50)[:, :, 0]) < 1e-12
+        assert rel_rms(back.data, oracle_alm2map(got.alm[None], sub.data.shape, sub.wcs, 30)[:, :, 0]) < 1e-12
 
 
 def test_emu_two_step_spin0_kernels(emu, monkeypatch):

@@ -80,6 +80,7 @@ struct pixsht_plan {
     size_t fft_smem = 0;
     int fft_packed = 1, fft_pt = FFT_PT;   // even nphi: real ring packed into nphi/2 complex samples; entries per pass table
     int fft_rows = 0;                      // > 0: ring work buffers in global memory, this many CTAs per component (fft.cuh FftParams::gbuf)
+    int fft_edge_multi = 0;                // edge-fused kernels also for the m-sharded phase layout (PIXSHT_FFT_EDGE_MULTI)
     int fft_edge = 0;                      // 1: the kernels of fft_edge.cuh (outer super-passes fused into the row I/O; PIXSHT_FFT_EDGE=0 turns it off)
     int fft_persist = 0;                   // > 0 (default; PIXSHT_FFT_PERSIST=0 turns it off): shared-memory FFT CTAs loop over rings, this many
                                            //      resident per SM, and prefetch the next ring's input row into L2 during the passes
@@ -425,6 +426,7 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
         }
         if (edge) { P->sp_first[P->nsp] = (unsigned char)(P->nfac - 1); P->sp_count[P->nsp] = 1; ++P->nsp; }
         P->fft_edge = edge ? 1 : 0;
+        P->fft_edge_multi = env_int("PIXSHT_FFT_EDGE_MULTI", 0) ? 1 : 0;
         std::vector<double2> cst((FFT_CST_MAX + 1) * FFT_CST_MAX);
         for (int S = 1; S <= FFT_CST_MAX; ++S)
             for (int k = 0; k < S; ++k) { const long double a = 2.0L * LPI * k / S; cst[S * FFT_CST_MAX + k] = make_double2((double)cosl(a), (double)(-sinl(a))); }
@@ -975,7 +977,8 @@ static int stage_fft(pixsht_plan* P, int dir, int ncomp, int c_begin, int c_coun
     }
     dim3 grid(gx, c_count);
     const bool glob = P->fft_rows > 0, fwd = dir != PIXSHT_ALM2MAP;
-    F.edge = (P->fft_edge && !glob) ? 1 : 0;
+    // m-sharded (multi-GPU) phase layout: the row I/O is the NVLink transpose; PIXSHT_FFT_EDGE_MULTI picks the kernels for it
+    F.edge = (P->fft_edge && !glob && (mtab == nullptr || P->fft_edge_multi)) ? 1 : 0;
     if (F.edge) {
         if (P->dtype == PIXSHT_F64) { if (!fwd) PIXSHT_LAUNCH((fft_phase2map_edge<double>), grid, P->fft_threads, P->fft_smem, st, F); else PIXSHT_LAUNCH((fft_map2phase_edge<double>), grid, P->fft_threads, P->fft_smem, st, F); }
         else { if (!fwd) PIXSHT_LAUNCH((fft_phase2map_edge<float>), grid, P->fft_threads, P->fft_smem, st, F); else PIXSHT_LAUNCH((fft_map2phase_edge<float>), grid, P->fft_threads, P->fft_smem, st, F); }

@@ -77,6 +77,7 @@ struct pixsht_plan {
     int nfft = 0, nfac = 0, fac[FFT_MAXFAC] = {0}, fft_threads = 256;
     unsigned fft_magic[FFT_MAXFAC] = {0};
     int nsp = 0; unsigned char sp_first[FFT_MAXFAC] = {0}, sp_count[FFT_MAXFAC] = {0};   // fused super-passes (fft.cuh)
+    int nsp_plain = 0; unsigned char sp_first_plain[FFT_MAXFAC] = {0}, sp_count_plain[FFT_MAXFAC] = {0};   // grouping of the launches that run the plain kernels
     size_t fft_smem = 0;
     int fft_packed = 1, fft_pt = FFT_PT;   // even nphi: real ring packed into nphi/2 complex samples; entries per pass table
     int fft_rows = 0;                      // > 0: ring work buffers in global memory, this many CTAs per component (fft.cuh FftParams::gbuf)
@@ -425,6 +426,14 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
             P->sp_first[P->nsp] = (unsigned char)t; P->sp_count[P->nsp] = (unsigned char)cnt; ++P->nsp; t += cnt;
         }
         if (edge) { P->sp_first[P->nsp] = (unsigned char)(P->nfac - 1); P->sp_count[P->nsp] = 1; ++P->nsp; }
+        // launches of an edge plan that run the plain kernels (m-sharded phase layout) group all factors greedily, exactly as a
+        // plan created with PIXSHT_FFT_EDGE=0 does: their results are then the same bits
+        P->nsp_plain = 0;
+        for (int t = 0; t < P->nfac;) {
+            const bool small = P->fac[t] <= 5 && t + 1 < P->nfac && P->fac[t + 1] <= 5;
+            const int cnt = (small && P->fac[t] * P->fac[t + 1] <= lim && P->fac[t] * P->fac[t + 1] <= FFT_CST_MAX) ? 2 : 1;
+            P->sp_first_plain[P->nsp_plain] = (unsigned char)t; P->sp_count_plain[P->nsp_plain] = (unsigned char)cnt; ++P->nsp_plain; t += cnt;
+        }
         P->fft_edge = edge ? 1 : 0;
         P->fft_edge_multi = env_int("PIXSHT_FFT_EDGE_MULTI", 0) ? 1 : 0;
         std::vector<double2> cst((FFT_CST_MAX + 1) * FFT_CST_MAX);
@@ -448,7 +457,7 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
             const size_t tot = (elem == 16 ? ef_rot_offset<double>(P->nfft, P->nphi, FFT_PT) : ef_rot_offset<float>(P->nfft, P->nphi, FFT_PT))
                                + (size_t)ef_rot_entries(P->mmax) * sizeof(double2);
             if (tot <= prop.sharedMemPerBlockOptin) P->fft_smem = tot;
-            else P->fft_edge = 0;   // (the grouping with a single last radix stays: it is a valid plan for the plain kernels too)
+            else P->fft_edge = 0;
         }
         if (!in_smem) {
             P->fft_pt = 128 + std::max(FFT_PT - 128, (Lmax + 127) / 128);
@@ -475,10 +484,13 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
         long long best = -1; int bt = tmax;
         for (int t = tmin; t <= tmax; t += 32) {
             long long cost = 0;
-            for (int i = 0; i < P->nsp; ++i) {
-                int pts = P->fac[P->sp_first[i]]; if (P->sp_count[i] == 2) pts *= P->fac[P->sp_first[i] + 1];
+            const int nspc = P->fft_edge ? P->nsp : P->nsp_plain;
+            const unsigned char* spf = P->fft_edge ? P->sp_first : P->sp_first_plain;
+            const unsigned char* spc = P->fft_edge ? P->sp_count : P->sp_count_plain;
+            for (int i = 0; i < nspc; ++i) {
+                int pts = P->fac[spf[i]]; if (spc[i] == 2) pts *= P->fac[spf[i] + 1];
                 int nb = P->nfft / pts;
-                if (P->fft_edge && i == P->nsp - 1) { nb = (nb - 1) / 2 + 2; pts *= 2; }   // butterfly pairs kk, L - kk
+                if (P->fft_edge && i == nspc - 1) { nb = (nb - 1) / 2 + 2; pts *= 2; }   // butterfly pairs kk, L - kk
                 cost += (long long)((nb + t - 1) / t) * (pts + 2);
             }
             cost = cost * 64 + (tmax - t) / 32;   // ties: prefer more threads
@@ -951,8 +963,6 @@ static int stage_fft(pixsht_plan* P, int dir, int ncomp, int c_begin, int c_coun
     memset(&F, 0, sizeof(F));
     F.nphi = P->nphi; F.n = P->nfft; F.nfac = P->nfac;
     for (int i = 0; i < P->nfac; ++i) { F.fac[i] = P->fac[i]; F.magic[i] = P->fft_magic[i]; }
-    F.nsp = P->nsp;
-    for (int i = 0; i < P->nsp; ++i) { F.sp_first[i] = P->sp_first[i]; F.sp_count[i] = P->sp_count[i]; }
     F.tw = P->d_tw.p; F.phi0tw = P->d_phi0tw.p; F.wgt = P->d_wgt.p; F.perm = P->d_perm.p; F.mmax = P->mmax;
     F.phase = phase; F.mtab = mtab; F.MP = P->MP; F.ncomp = ncomp; F.c_begin = c_begin;
     F.ring_begin = ring_begin; F.ring_count = ring_count;
@@ -979,6 +989,8 @@ static int stage_fft(pixsht_plan* P, int dir, int ncomp, int c_begin, int c_coun
     const bool glob = P->fft_rows > 0, fwd = dir != PIXSHT_ALM2MAP;
     // m-sharded (multi-GPU) phase layout: the row I/O is the NVLink transpose; PIXSHT_FFT_EDGE_MULTI picks the kernels for it
     F.edge = (P->fft_edge && !glob && (mtab == nullptr || P->fft_edge_multi)) ? 1 : 0;
+    if (F.edge) { F.nsp = P->nsp; for (int i = 0; i < P->nsp; ++i) { F.sp_first[i] = P->sp_first[i]; F.sp_count[i] = P->sp_count[i]; } }
+    else { F.nsp = P->nsp_plain; for (int i = 0; i < P->nsp_plain; ++i) { F.sp_first[i] = P->sp_first_plain[i]; F.sp_count[i] = P->sp_count_plain[i]; } }
     if (F.edge) {
         if (P->dtype == PIXSHT_F64) { if (!fwd) PIXSHT_LAUNCH((fft_phase2map_edge<double>), grid, P->fft_threads, P->fft_smem, st, F); else PIXSHT_LAUNCH((fft_map2phase_edge<double>), grid, P->fft_threads, P->fft_smem, st, F); }
         else { if (!fwd) PIXSHT_LAUNCH((fft_phase2map_edge<float>), grid, P->fft_threads, P->fft_smem, st, F); else PIXSHT_LAUNCH((fft_map2phase_edge<float>), grid, P->fft_threads, P->fft_smem, st, F); }
@@ -1844,7 +1856,7 @@ extern "C" int pixsht_plan_info(const pixsht_plan* P, int32_t info[16])
     info[0] = P->nphi; info[1] = P->nrings; info[2] = P->lmax; info[3] = P->mmax; info[4] = P->dtype; info[5] = P->device;
     info[6] = P->npairs; info[7] = P->sm_count; info[8] = P->nfft; info[9] = P->launches; info[10] = P->R0; info[11] = P->R2; info[12] = P->R0a; info[13] = P->R2a;
     info[14] = P->multi ? multi_ndev(P->multi) : 1;
-    info[15] = P->fft_threads | (P->fft_edge ? (1 << 16) : 0) | (P->fft_rows ? (1 << 17) : 0) | (P->nsp << 20);
+    info[15] = P->fft_threads | (P->fft_edge ? (1 << 16) : 0) | (P->fft_rows ? (1 << 17) : 0) | ((P->fft_edge ? P->nsp : P->nsp_plain) << 20);
     return PIXSHT_OK;
 }
 

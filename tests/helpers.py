@@ -108,3 +108,21 @@ def fejer1_geometry(nrings_total, nphi, ring_first=0, nrings=None):
     w = f * 2.0 * np.pi / nphi
     nrings = N - ring_first if nrings is None else nrings
     return theta[ring_first:ring_first + nrings], w[ring_first:ring_first + nrings]
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def plain_fft_kernels():
+    """Plans created inside use the plain ring-FFT kernels (fft.cuh) instead of the edge-fused ones (fft_edge.cuh): the
+    m-sharded multi-GPU plans run the plain kernels, so a bit-for-bit comparison needs the single-GPU reference on them too."""
+    old = os.environ.get("PIXSHT_FFT_EDGE")
+    os.environ["PIXSHT_FFT_EDGE"] = "0"
+    try:
+        yield
+    finally:
+        if old is None:
+            os.environ.pop("PIXSHT_FFT_EDGE", None)
+        else:
+            os.environ["PIXSHT_FFT_EDGE"] = old

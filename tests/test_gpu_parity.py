@@ -14,7 +14,7 @@ import pixsht
 from pixsht import Enmap, Alm, CarClenshawCurtis, fullsky_geometry, geometry, degree, arcminute
 from pixsht.transforms import Plan, map2alm, alm2map, get_lib, PixshtError
 from pixsht import _lib
-from helpers import (golden_alm, gen_spin0, gen_spin2, oracle_map2alm, oracle_alm2map, rel_rms, synth_alm, band_copy)
+from helpers import (golden_alm, gen_spin0, gen_spin2, oracle_map2alm, oracle_alm2map, rel_rms, synth_alm, band_copy, plain_fft_kernels)
 from oracle import cc_geometry, get_oracle, nalm, alm_index
 
 pytestmark = pytest.mark.gpu
@@ -517,12 +517,17 @@ def _shard_devices(nshard):
 @pytest.mark.parametrize("nshard", [2, 3, 8])
 def test_multi_gpu_plan_equals_single_gpu_plan(nshard, res_arcmin=8.0, lmax=1350, reps=2):
     """The one-process multi-GPU plan against the single-GPU plan on the same inputs: synthesis bit for bit (each (m, ring)
-    sum is the same sequence of FMAs wherever it runs), analysis to rounding (atomic accumulation order); IQU, T alone, QU
-    alone, Float32, partial-sky / flipped bands, and a batch dealt over the shards."""
+    sum is the same sequence of FMAs wherever it runs; both on the plain ring-FFT kernels, which the m-sharded layout uses),
+    analysis to rounding (atomic accumulation order); IQU, T alone, QU alone, Float32, partial-sky / flipped bands, and a batch
+    dealt over the shards.  The default single-GPU plan (edge-fused ring FFTs) agrees to rounding."""
     shape, wcs = fullsky_geometry(res_arcmin * arcminute)
     band = pixsht.sht_band(shape, wcs)
-    single = Plan(band, lmax)
+    with plain_fft_kernels():
+        single = Plan(band, lmax)
+    assert not single.info()["fft"]["edge_fused"]
     multi = Plan(band, lmax, devices=_shard_devices(nshard))
+    default = Plan(band, lmax)
+    assert default.info()["fft"]["edge_fused"]
     assert multi.info()["ndev"] == nshard
     sh = multi.shards()
     assert sorted(np.concatenate([s[3] for s in sh]).tolist()) == list(range(lmax + 1))      # every m exactly once
@@ -538,9 +543,12 @@ def test_multi_gpu_plan_equals_single_gpu_plan(nshard, res_arcmin=8.0, lmax=1350
             back = multi.map2alm(got)
             for a, b in zip(back, back_ref):
                 assert rel_rms(a, b) < 1e-13
-    single.close(); multi.close()
+    for a, b in zip(default.alm2map(alms), multi.alm2map(alms)):
+        assert rel_rms(a, b) < 1e-14
+    single.close(); multi.close(); default.close()
     # Float32 boundary, T only
-    s32 = Plan(band, lmax, dtype=np.float32)
+    with plain_fft_kernels():
+        s32 = Plan(band, lmax, dtype=np.float32)
     m32 = Plan(band, lmax, dtype=np.float32, devices=_shard_devices(nshard))
     a32 = alms[0].astype(np.complex64)
     r = s32.alm2map([a32])[0]; g = m32.alm2map([a32])[0]
@@ -579,7 +587,8 @@ def test_multi_gpu_plan_sharded_device_buffers(res_arcmin=8.0, lmax=1350, nshard
     shape, wcs = fullsky_geometry(res_arcmin * arcminute)
     band = pixsht.sht_band(shape, wcs)
     devs = _shard_devices(nshard)
-    single = Plan(band, lmax)
+    with plain_fft_kernels():       # the kernels of the m-sharded layout: the slabs are compared bit for bit
+        single = Plan(band, lmax)
     multi = Plan(band, lmax, devices=devs)
     alms = [synth_alm(lmax, lmax, 70 + c, spin2=c > 0) for c in range(3)]
     ref = single.alm2map(alms)

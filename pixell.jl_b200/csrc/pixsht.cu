@@ -416,7 +416,10 @@ static int plan_build(pixsht_plan* P, const std::vector<double>& theta, const st
         const int lim = std::min(env_int("PIXSHT_FFT_FUSE", FFT_FUSE_MAX), FFT_FUSE_MAX);
         // Edge-fused kernels (fft_edge.cuh): the last pass stays a single radix (it is done on butterfly pairs in the phase-row
         // I/O), the first super-pass is done in the map-row I/O.  Needs an even ring, radices 2..5 at both ends, no aliasing.
-        bool edge = P->fft_packed && P->nfac >= 2 && P->mmax <= P->nfft && env_int("PIXSHT_FFT_EDGE", 1) != 0
+        // Rings below 32 KB (several CTAs of 128 threads per SM) measured no gain (C2, Float32: 0.191 against 0.185 ms): plain kernels,
+        // unless PIXSHT_FFT_EDGE=2 forces the edge-fused ones (the emulation tests do, to cover every plan shape at small sizes).
+        const int edge_env = env_int("PIXSHT_FFT_EDGE", 1);
+        bool edge = P->fft_packed && P->nfac >= 2 && P->mmax <= P->nfft && edge_env != 0 && ((size_t)P->nfft * elem >= 32768 || edge_env == 2)
                     && P->fac[0] >= 2 && P->fac[0] <= 5 && P->fac[P->nfac - 1] >= 2 && P->fac[P->nfac - 1] <= 5;
         const int ngroup = edge ? P->nfac - 1 : P->nfac;   // factors grouped greedily; the edge plan keeps the last one apart
         P->nsp = 0;

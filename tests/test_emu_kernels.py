@@ -195,18 +195,23 @@ def test_emu_edge_fused_fft(emu, monkeypatch):
             res = {}
             alm = synth_alm(lmax, lmax, nphi)
             x = np.asfortranarray(np.random.default_rng(nphi).standard_normal(shape))
-            for edge in (("1", "0") if both else ("1",)):
+            for edge in (("2", "0") if both else ("2",)):    # 2: also for rings below the 32 KB threshold of the default
                 monkeypatch.setenv("PIXSHT_FFT_EDGE", edge)
                 plan = Plan(band, lmax, lib=emu)
-                assert plan.info()["fft"]["edge_fused"] == (edge == "1"), (nphi, lmax, plan.info())
+                assert plan.info()["fft"]["edge_fused"] == (edge == "2"), (nphi, lmax, plan.info())
                 res[edge] = (plan.alm2map([alm])[0], plan.map2alm([x])[0])
                 plan.close()
             ref = oracle_alm2map(alm[None], shape, wcs, lmax, kind="d")[:, :, 0]
-            assert rel_rms(res["1"][0], ref) < 1e-12, (nphi, lmax)
-            assert rel_rms(res["1"][1], oracle_map2alm(Enmap(x, wcs), lmax, kind="d")[0]) < 1e-12, (nphi, lmax)
+            assert rel_rms(res["2"][0], ref) < 1e-12, (nphi, lmax)
+            assert rel_rms(res["2"][1], oracle_map2alm(Enmap(x, wcs), lmax, kind="d")[0]) < 1e-12, (nphi, lmax)
             if both:
-                assert rel_rms(res["1"][0], res["0"][0]) < 1e-14 and rel_rms(res["1"][1], res["0"][1]) < 1e-14, (nphi, lmax)
+                assert rel_rms(res["2"][0], res["0"][0]) < 1e-14 and rel_rms(res["2"][1], res["0"][1]) < 1e-14, (nphi, lmax)
     monkeypatch.setenv("PIXSHT_FFT_EDGE", "1")
+    shape, wcs = fullsky_geometry((2 * math.pi / 360, math.pi / 4))
+    plan = Plan(pixsht.sht_band(shape, wcs), 100, lib=emu)
+    assert not plan.info()["fft"]["edge_fused"]      # default: small rings keep the plain kernels
+    plan.close()
+    monkeypatch.setenv("PIXSHT_FFT_EDGE", "2")
     # lmax beyond the ring's Nyquist mode (aliasing): stays with the plain kernels
     shape, wcs = fullsky_geometry((2 * math.pi / 24, math.pi / 40))
     plan = Plan(pixsht.sht_band(shape, wcs), 30, lib=emu)

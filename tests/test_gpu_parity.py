@@ -112,6 +112,45 @@ def test_iqu_f64_vs_oracle(res_deg, lmax, mmax):
     assert rel_rms(t.alm, rt) < TOL64 and rel_rms(e.alm, reb[0]) < TOL64 and rel_rms(b.alm, reb[1]) < TOL64
 
 
+def test_edge_fused_fft_forced_on_small_plans(monkeypatch):
+    """The edge-fused ring-FFT kernels (fft_edge.cuh) are the default from 32 KB rings on (C3 / C4 / C5-size tests below run them);
+    here they are forced (PIXSHT_FFT_EDGE=2) on small plans of every kind -- IQU, Float32 boundary, band limit below the Nyquist
+    mode, a cut-sky flipped band with element-wise row access -- against the oracle and against the plain kernels."""
+    shape, wcs = fullsky_geometry(0.5 * degree, dims=(3,))
+    band = pixsht.sht_band(shape[:2], wcs)
+    for lmax, mmax in ((360, 360), (300, 200)):
+        alms = [synth_alm(lmax, mmax, 3100 + c, spin2=c > 0) for c in range(3)]
+        ref = np.concatenate([oracle_alm2map(alms[0][None], shape, wcs, lmax, mmax),
+                              oracle_alm2map(np.stack(alms[1:]), shape, wcs, lmax, mmax, spin=2)], axis=2)
+        rt = oracle_map2alm(Enmap(ref[:, :, 0], wcs), lmax, mmax)[0]
+        reb = oracle_map2alm(Enmap(ref[:, :, 1:], wcs), lmax, mmax, spin=2)
+        res = {}
+        for edge in ("2", "0"):
+            monkeypatch.setenv("PIXSHT_FFT_EDGE", edge)
+            for dt, tol in ((np.float64, TOL64), (np.float32, TOL32)):
+                plan = Plan(band, lmax, mmax, dtype=dt)
+                assert plan.info()["fft"]["edge_fused"] == (edge == "2")
+                mp = plan.alm2map([a.astype(plan.cdtype) for a in alms])
+                assert max(rel_rms(mp[c], ref[:, :, c]) for c in range(3)) < tol
+                out = plan.map2alm([np.asfortranarray(ref[:, :, c], dtype=dt) for c in range(3)])
+                assert max(rel_rms(out[0], rt), rel_rms(out[1], reb[0]), rel_rms(out[2], reb[1])) < tol
+                res[(edge, dt)] = (mp, out)
+                plan.close()
+        for c in range(3):
+            assert rel_rms(res[("2", np.float64)][0][c], res[("0", np.float64)][0][c]) < 1e-14
+            assert rel_rms(res[("2", np.float64)][1][c], res[("0", np.float64)][1][c]) < 1e-13
+    monkeypatch.setenv("PIXSHT_FFT_EDGE", "2")
+    shape, wcs = fullsky_geometry(1.0 * degree)
+    full = Enmap(gen_spin0(shape, 1.5), wcs)
+    for sub in (full[40:300, 30:120], full[::-1, ::-1][13:341, 5:170]):
+        plan = Plan(pixsht.sht_band(sub.data.shape, sub.wcs), 150)
+        assert plan.info()["fft"]["edge_fused"]
+        assert rel_rms(plan.map2alm([sub.data])[0], oracle_map2alm(sub, 150)[0]) < TOL64
+        alm = synth_alm(150, 150, 78)
+        assert rel_rms(plan.alm2map([alm])[0], oracle_alm2map(alm[None], sub.data.shape, sub.wcs, 150)[:, :, 0]) < TOL64
+        plan.close()
+
+
 def test_partial_sky_band_and_unflipped_geometry():
     # a cut-sky band sliced out of a full-sky grid, and a geometry with ascending RA / descending DEC (no flips)
     shape, wcs = fullsky_geometry(1.0 * degree)
@@ -527,7 +566,6 @@ def test_multi_gpu_plan_equals_single_gpu_plan(nshard, res_arcmin=8.0, lmax=1350
     assert not single.info()["fft"]["edge_fused"]
     multi = Plan(band, lmax, devices=_shard_devices(nshard))
     default = Plan(band, lmax)
-    assert default.info()["fft"]["edge_fused"]
     assert multi.info()["ndev"] == nshard
     sh = multi.shards()
     assert sorted(np.concatenate([s[3] for s in sh]).tolist()) == list(range(lmax + 1))      # every m exactly once

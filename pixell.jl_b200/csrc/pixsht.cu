@@ -1045,11 +1045,30 @@ static void ring_rows(const pixsht_plan* P, int r0, int r1, size_t esz, size_t& 
 // Cumulative work fractions f[0] = 0 < ... < f[K] = 1 of the pieces of the pipelined host path: equal pieces, at most `limit`.
 // (Subdividing the first and the last piece further was measured and changed nothing at C4 / C3: the launches of more and
 // smaller pieces cost what the shorter exposed copies save.)
-static std::vector<double> piece_fractions(int nsplit, int limit)
+// Cumulative piece boundaries 0 = f_0 < ... < f_s = 1 of the pipelined host path.  The first piece of an input and the last piece
+// of an output are exposed (nothing runs before the one has arrived / while the other leaves); the pieces in between only have to
+// be short enough for their copy to hide under the neighbouring piece's kernels.
+//   shape 1 (alm2map: the T alm that arrive in m ranges, the polarisation rows that leave in ring ranges): sizes grow by factors
+//            of two from both ends (s = 8: 1 2 4 8 8 4 2 1 thirtieths) -- measured at C4: exposed head + tail 3.3 -> 0.3 ms, call
+//            254.7 -> 250.9 ms;
+//   shape 0 (map2alm): equal pieces -- larger middle pieces measured 8 ms of extra gaps in its ring-range inputs, a tapered end
+//            of its alm outputs 1.6 ms more tail (profiles/r02/e2e_probe_pieces*.txt).
+// PIXSHT_PIECE_SHAPE=0 makes every pipeline use equal pieces.
+static std::vector<double> piece_fractions(int nsplit, int limit, int shape = 0)
 {
     std::vector<double> f;
     const int s = std::max(1, std::min(nsplit, limit));
-    for (int k = 0; k <= s; ++k) f.push_back((double)k / s);
+    static const int allow = env_int("PIXSHT_PIECE_SHAPE", 1);
+    if (shape == 0 || allow == 0 || s < 4) { for (int k = 0; k <= s; ++k) f.push_back((double)k / s); return f; }
+    std::vector<double> w(s);
+    double tot = 0.0;
+    for (int k = 0; k < s; ++k) {
+        w[k] = (double)(1 << std::min(std::min(k, s - 1 - k), 20));
+        tot += w[k];
+    }
+    double acc = 0.0;
+    f.push_back(0.0);
+    for (int k = 0; k < s; ++k) { acc += w[k]; f.push_back(k == s - 1 ? 1.0 : acc / tot); }
     return f;
 }
 
@@ -1106,7 +1125,7 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
     if (direction == PIXSHT_ALM2MAP) {
         // input copies: the spin-0 alm goes first, in m ranges of equal Legendre work, so that its synthesis starts after a
         // fraction of one component has arrived; the polarisation alm follow and arrive under the spin-0 work
-        const std::vector<double> f0 = piece_fractions(P->nsplit, P->mmax + 1);
+        const std::vector<double> f0 = piece_fractions(P->nsplit, P->mmax + 1, 1);
         const int K0 = has0 ? (int)f0.size() - 1 : 0;
         std::vector<int> mb0(K0 + 1, 0);
         std::vector<cudaEvent_t> e_t(K0);
@@ -1160,7 +1179,7 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
             // splits of the ring pairs with equal Legendre work (work per pair ~ sin(theta)): polar side first, so that
             // the last (exposed) piece of the map copy is the one with the fewest rings
             const int R = P->R2, nch = leg_total_chunks(P, R);
-            const std::vector<double> f2 = piece_fractions(P->nsplit, nch);
+            const std::vector<double> f2 = piece_fractions(P->nsplit, nch, 1);
             int K = (int)f2.size() - 1;
             std::vector<int> cb(K + 1);
             for (int k = 0; k <= K; ++k) cb[k] = (int)std::lround(nch * (2.0 / 3.14159265358979323846) * std::acos(1.0 - f2[k]));

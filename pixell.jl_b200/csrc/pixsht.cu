@@ -1206,11 +1206,34 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
         // input copies: the spin-0 map goes first, in ring-pair ranges (north rows + mirrored south rows), so that its FFTs
         // and analysis start after a fraction of one component has arrived; the polarisation maps follow
         const int Ra = P->R0a, nch0 = leg_total_chunks(P, Ra);
-        const std::vector<double> f0 = piece_fractions(P->nsplit, nch0);
-        int K0 = has0 ? (int)f0.size() - 1 : 0;
-        std::vector<int> cb0(K0 + 1, 0);
-        for (int k = 0; k <= K0; ++k) cb0[k] = (k == K0) ? nch0 : (int)std::lround(nch0 * f0[k]);
-        for (int k = 1; k <= K0; ++k) cb0[k] = std::max(cb0[k], cb0[k - 1]);
+        // The pieces go EQUATOR FIRST (piece K0-1 of the pole-to-equator chunk order is copied and analysed first): the equatorial
+        // chunks carry most of the Legendre work (every m is active there), so the compute stream has a backlog after the first
+        // piece and every later copy hides under it; pole first, the bulk of the spin-0 analysis waited for the end of the whole
+        // component's copy.  Sizes from the equator: 1, 2, 3, 3, ... chunks (the first piece is the exposed head of the call).
+        // PIXSHT_PIECE_SHAPE=0: equal pieces, pole first (round-1 order).
+        static const int graded = env_int("PIXSHT_PIECE_SHAPE", 1);
+        std::vector<int> cb0;
+        int K0 = 0;
+        if (has0 && graded && nch0 >= 4 && P->nsplit >= 4) {
+            std::vector<int> sz;
+            int left = nch0;
+            for (int k = 0; left > 0; ++k) {
+                int take = (k == 0) ? 1 : (k == 1 ? 2 : std::max(3, (nch0 - 3 + P->nsplit - 3) / std::max(1, P->nsplit - 2)));
+                if ((int)sz.size() == P->nsplit - 1 || take > left) take = left;
+                sz.push_back(take); left -= take;
+            }
+            K0 = (int)sz.size();
+            cb0.assign(K0 + 1, 0);
+            for (int k = 0; k < K0; ++k) cb0[K0 - 1 - k] = (k == 0 ? nch0 : cb0[K0 - k]) - sz[k];   // sz[0] = the last (equatorial) interval
+            cb0[K0] = nch0;
+        } else {
+            const std::vector<double> f0 = piece_fractions(P->nsplit, nch0);
+            K0 = has0 ? (int)f0.size() - 1 : 0;
+            cb0.assign(K0 + 1, 0);
+            for (int k = 0; k <= K0; ++k) cb0[k] = (k == K0) ? nch0 : (int)std::lround(nch0 * f0[k]);
+            for (int k = 1; k <= K0; ++k) cb0[k] = std::max(cb0[k], cb0[k - 1]);
+        }
+        const bool eq_first = has0 && graded && nch0 >= 4 && P->nsplit >= 4;
         std::vector<std::array<int, 4>> rr0(K0);
         bool ok0 = K0 > 0;
         for (int k = 0; k < K0 && ok0; ++k) {
@@ -1220,7 +1243,8 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
         }
         if (has0 && !ok0) { K0 = 1; cb0 = {0, nch0}; rr0.assign(1, {0, P->nrings, 0, 0}); }
         std::vector<cudaEvent_t> e_t(K0);
-        for (int k = 0; k < K0; ++k) {
+        for (int kk = 0; kk < K0; ++kk) {
+            const int k = (eq_first && K0 > 1) ? K0 - 1 - kk : kk;
             for (int h = 0; h < 2; ++h) {
                 if (rr0[k][2 * h + 1] <= rr0[k][2 * h]) continue;
                 size_t off, nb; ring_rows(P, rr0[k][2 * h], rr0[k][2 * h + 1], esz, off, nb);
@@ -1273,7 +1297,8 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
         };
         for (int c = 0; c < ncomp; ++c) CU(cudaMemsetAsync(dalm64[c], 0, (size_t)P->nalm * sizeof(double2), sc));
         if (has0) {
-            for (int k = 0; k < K0; ++k) {
+            for (int kk = 0; kk < K0; ++kk) {
+                const int k = (eq_first && K0 > 1) ? K0 - 1 - kk : kk;
                 CU(cudaStreamWaitEvent(sc, e_t[k], 0));
                 for (int h = 0; h < 2; ++h) {
                     const int r0 = rr0[k][2 * h], r1 = rr0[k][2 * h + 1];

@@ -35,7 +35,8 @@ namespace pixsht {
 // 512 threads leave 128 registers per thread: the 15 / 16-point super-passes do not spill (the time per ring is flat between
 // 384 and 640 threads, profiles/r02/fft_edge_threads.txt: the phases are bound by their serial resource use, not by the warp
 // count).  Measured and rejected: loading a thread's next butterfly pair during the arithmetic of the current one (ptxas keeps the
-// second set of raw entries in local memory: 2 KB of spill traffic per thread).
+// second set of raw entries in local memory: 2 KB of spill traffic per thread), and two pairs per loop iteration with all 4 Q loads
+// issued first (no spills at 128 registers, but 5.01 against 4.82 ms at C4, profiles/r02/fft_edge_twopairs.txt).
 #ifndef PIXSHT_EF_MAXTHREADS
 #define PIXSHT_EF_MAXTHREADS 512
 #endif

@@ -620,7 +620,7 @@ def main():
                   "note": "un-pruned, north/south-folded count of SURVEY.md 8(d); per GPU"}
     traffic = {}
     try:
-        with open(os.path.join(ROOT, "profiles", "r01", "ncu_dram_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02", "ncu_dram_traffic.json")) as f:   # ncu capture of the kernels as they are now
             traffic = json.load(f).get(args.workload, {})
     except Exception:
         pass
@@ -645,6 +645,10 @@ def main():
                     "fp64_pipe_utilisation": dom["fp64_pipe_utilisation"], "launch_ms": dom["ms"],
                     "note": "dominant kernel; algorithmic = un-pruned, north/south-folded count of SURVEY.md 8(d) (12 FP64 FMA-class ops per "
                             "(l, m, ring pair) for spin 2); timed with CUDA events around the launch inside pixsht_execute",
+                    "traffic_note": "dram bytes per launch from ncu (profiles/r02/ncu_c4_metrics_final.csv). The kernel is FP64 bound; in the default "
+                                    "chunk-major grid order every chunk of ring pairs re-reads the (alpha, delta, gamma) column of its m and re-touches "
+                                    "the alm lines it adds to (about 56 B per (l, m, chunk): 154 GB = 0.7 TB/s at C4, 11 % of the HBM rate), against 9 GB "
+                                    "in m-major order (PIXSHT_LEG_ORDER=0), which runs 3 % slower (DESIGN.md 4.1)",
                     "kernels": kernels, "legendre_stage": stage_roof}
     else:
         roofline = dict(stage_roof, bound="fp64_fma", traffic=None, peak_source=peak_src)

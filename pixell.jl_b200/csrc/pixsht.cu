@@ -1125,7 +1125,12 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
     if (direction == PIXSHT_ALM2MAP) {
         // input copies: the spin-0 alm goes first, in m ranges of equal Legendre work, so that its synthesis starts after a
         // fraction of one component has arrived; the polarisation alm follow and arrive under the spin-0 work
-        const std::vector<double> f0 = piece_fractions(P->nsplit, P->mmax + 1, 1);
+        // A single spin-0 map has no polarisation work for its rows to leave under: its LAST m piece then carries half of the
+        // work and is synthesised in ring ranges whose rows leave one by one (pieces 1 2 4 8 15 thirtieths; tonly_rings below).
+        static const int graded_a2m = env_int("PIXSHT_PIECE_SHAPE", 1);
+        const bool tonly_rings = has0 && !has2 && graded_a2m && P->nsplit >= 5 && P->mmax + 1 >= 64 && leg_total_chunks(P, P->R0) >= env_int("PIXSHT_TONLY_MINCHUNKS", 16);   // large plans only: the pieces must outweigh their launches
+        std::vector<double> f0 = piece_fractions(P->nsplit, P->mmax + 1, 1);
+        if (tonly_rings) f0 = {0.0, 1.0 / 30, 3.0 / 30, 7.0 / 30, 15.0 / 30, 1.0};
         const int K0 = has0 ? (int)f0.size() - 1 : 0;
         std::vector<int> mb0(K0 + 1, 0);
         std::vector<cudaEvent_t> e_t(K0);
@@ -1166,10 +1171,42 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
                 if (i1 <= i0) continue;
                 if (f32) { PIXSHT_LAUNCH(k_cvt_f32_to_f64, cvt_grid, 256, 0, sc, (const float*)dalm[0] + 2 * i0, (double*)(dalm64[0] + i0), 2 * (i1 - i0)); P->launches++; }
                 rc = synth_prep(P, 0, dalm64[0], dalm64[0], sc, i0, i1 - i0); if (rc) return rc;
+                if (tonly_rings && k == K0 - 1) break;   // the last m piece goes in ring ranges, below
                 const LegJob J = {0, ncomp, 0, mb0[k], mb0[k + 1] - mb0[k], nullptr, 0, leg_total_chunks(P, P->R0), ph};
                 rc = synth_launch(P, J, sc); if (rc) return rc;
             }
-            rc = emit_rings(0, 1, 0, P->nrings); if (rc) return rc;
+            bool rings_done = false;
+            if (tonly_rings && mb0[K0] > mb0[K0 - 1]) {
+                // ring-pair ranges of equal Legendre work, polar side first: the last (exposed) rows are the fewest
+                const int R = P->R0, nch = leg_total_chunks(P, R);
+                const std::vector<double> fr = piece_fractions(P->nsplit, nch, 1);
+                const int K = (int)fr.size() - 1;
+                std::vector<int> cb(K + 1);
+                for (int k = 0; k <= K; ++k) cb[k] = (int)std::lround(nch * (2.0 / 3.14159265358979323846) * std::acos(1.0 - fr[k]));
+                cb[0] = 0; cb[K] = nch;
+                for (int k = 1; k <= K; ++k) cb[k] = std::max(cb[k], cb[k - 1]);
+                bool ok = true;
+                std::vector<std::array<int, 4>> rr(K);
+                for (int k = 0; k < K && ok; ++k) {
+                    int rng[2][2];
+                    ok = pair_range_rings(P, std::min(P->npairs, cb[k] * 32 * R), std::min(P->npairs, cb[k + 1] * 32 * R), rng);
+                    rr[k] = {rng[0][0], rng[0][1], rng[1][0], rng[1][1]};
+                }
+                if (ok) {
+                    for (int k = 0; k < K; ++k) {
+                        const LegJob J = {0, ncomp, 0, mb0[K0 - 1], mb0[K0] - mb0[K0 - 1], nullptr, cb[k], cb[k + 1] - cb[k], ph};
+                        rc = synth_launch(P, J, sc); if (rc) return rc;
+                        rc = emit_rings(0, 1, rr[k][0], rr[k][1]); if (rc) return rc;
+                        rc = emit_rings(0, 1, rr[k][2], rr[k][3]); if (rc) return rc;
+                    }
+                    rings_done = true;
+                }
+            }
+            if (tonly_rings && !rings_done) {
+                const LegJob J = {0, ncomp, 0, mb0[K0 - 1], mb0[K0] - mb0[K0 - 1], nullptr, 0, leg_total_chunks(P, P->R0), ph};
+                rc = synth_launch(P, J, sc); if (rc) return rc;
+            }
+            if (!rings_done) { rc = emit_rings(0, 1, 0, P->nrings); if (rc) return rc; }
         }
         if (has2) {
             CU(cudaStreamWaitEvent(sc, e_in[c0], 0));
@@ -1212,6 +1249,7 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
         // component's copy.  Sizes from the equator: 1, 2, 3, 3, ... chunks (the first piece is the exposed head of the call).
         // PIXSHT_PIECE_SHAPE=0: equal pieces, pole first (round-1 order).
         static const int graded = env_int("PIXSHT_PIECE_SHAPE", 1);
+        const bool tonly_m = has0 && !has2 && nch0 >= env_int("PIXSHT_TONLY_MINCHUNKS", 16);   // single spin-0 map of a large plan, see below
         std::vector<int> cb0;
         int K0 = 0;
         if (has0 && graded && nch0 >= 4 && P->nsplit >= 4) {
@@ -1220,6 +1258,9 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
             for (int k = 0; left > 0; ++k) {
                 int take = (k == 0) ? 1 : (k == 1 ? 2 : std::max(3, (nch0 - 3 + P->nsplit - 3) / std::max(1, P->nsplit - 2)));
                 if ((int)sz.size() == P->nsplit - 1 || take > left) take = left;
+                // a single spin-0 map: the polar 40 % of the chunks (a fifth of the work) stay together as the last piece, which is
+                // analysed in m ranges whose alm columns leave one by one (nothing else would cover that copy)
+                if (tonly_m && k > 0 && nch0 - left >= (nch0 * 3 + 4) / 5) take = left;
                 sz.push_back(take); left -= take;
             }
             K0 = (int)sz.size();
@@ -1297,6 +1338,7 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
         };
         for (int c = 0; c < ncomp; ++c) CU(cudaMemsetAsync(dalm64[c], 0, (size_t)P->nalm * sizeof(double2), sc));
         if (has0) {
+            bool t_alm_out = false;
             for (int kk = 0; kk < K0; ++kk) {
                 const int k = (eq_first && K0 > 1) ? K0 - 1 - kk : kk;
                 CU(cudaStreamWaitEvent(sc, e_t[k], 0));
@@ -1305,10 +1347,26 @@ static int execute_host(pixsht_plan* P, int direction, int ncomp, void* const* a
                     if (r1 <= r0) continue;
                     rc = stage_fft(P, PIXSHT_MAP2ALM, ncomp, 0, 1, P->d_phase.p + (long long)r0 * ncomp * P->MP, r0, r1 - r0, dmap, sc); if (rc) return rc;
                 }
+                if (tonly_m && eq_first && K0 > 1 && kk == K0 - 1) {
+                    // last piece of a single spin-0 map: m ranges of equal work, each followed by the copy of its alm columns
+                    const std::vector<double> fm = piece_fractions(P->nsplit, P->mmax + 1);
+                    const int KM = (int)fm.size() - 1;
+                    std::vector<int> mbt(KM + 1);
+                    for (int q = 0; q <= KM; ++q) mbt[q] = (int)std::lround((P->mmax + 1) * (1.0 - std::sqrt(1.0 - fm[q])));
+                    mbt[0] = 0; mbt[KM] = P->mmax + 1;
+                    for (int q = 1; q <= KM; ++q) mbt[q] = std::max(mbt[q], mbt[q - 1]);
+                    for (int q = 0; q < KM; ++q) {
+                        const LegJob J = {0, ncomp, 0, mbt[q], mbt[q + 1] - mbt[q], nullptr, cb0[k], cb0[k + 1] - cb0[k], ph};
+                        rc = anal_launch(P, J, dalm64[0], nullptr, sc); if (rc) return rc;
+                        rc = emit_alm(0, 1, mbt[q], mbt[q + 1]); if (rc) return rc;
+                    }
+                    t_alm_out = true;
+                    continue;
+                }
                 const LegJob J = {0, ncomp, 0, 0, P->mmax + 1, nullptr, cb0[k], cb0[k + 1] - cb0[k], ph};
                 rc = anal_launch(P, J, dalm64[0], nullptr, sc); if (rc) return rc;
             }
-            rc = emit_alm(0, 1, 0, P->mmax + 1); if (rc) return rc;
+            if (!t_alm_out) { rc = emit_alm(0, 1, 0, P->mmax + 1); if (rc) return rc; }
         }
         if (has2) {
             int chunksB = nch2;   // chunks left for the m-range launches below

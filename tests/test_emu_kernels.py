@@ -163,6 +163,36 @@ def test_emu_host_path_two_part_polarisation_analysis(emu_default, monkeypatch, 
         assert rel_rms(got[c].alm, ref[c]) < (1e-12 if dt == np.float64 else 1e-6)
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_emu_host_path_single_map_two_phase_pipelines(emu_default, monkeypatch, dt):
+    """A single spin-0 map through host pointers on a plan with many ring-pair chunks: alm2map synthesises its last m piece in ring
+    ranges whose rows leave one by one, map2alm analyses its last (polar) ring piece in m ranges whose alm columns leave one by one
+    (pixsht.cu, execute_host: tonly_rings / tonly_m).  One pair per lane and a lowered threshold make a 0.5 degree grid qualify."""
+    monkeypatch.setenv("PIXSHT_R0", "1"); monkeypatch.setenv("PIXSHT_R0A", "1")
+    monkeypatch.setenv("PIXSHT_TONLY_MINCHUNKS", "4")
+    shape, wcs = fullsky_geometry(0.5 * degree)          # 720 x 361: 181 ring pairs = 6 chunks of 32
+    lmax = 100
+    tol = 1e-12 if dt == np.float64 else 2e-6
+    alm = synth_alm(lmax, lmax, 611)
+    plan = Plan(pixsht.sht_band(shape, wcs), lmax, dtype=dt, lib=emu_default)
+    mp = plan.alm2map([alm.astype(plan.cdtype)])[0]
+    ref = oracle_alm2map(alm[None], shape, wcs, lmax, kind="d")[:, :, 0]
+    assert rel_rms(mp, ref) < tol
+    x = np.asfortranarray(np.random.default_rng(612).standard_normal(shape).astype(dt))
+    got = plan.map2alm([x])[0]
+    assert rel_rms(got, oracle_map2alm(Enmap(np.asfortranarray(x, dtype=np.float64), wcs), lmax, kind="d")[0]) < tol
+    plan.close()
+    # a cut-sky band (single rings without a mirror partner in the chunks) and mmax < lmax
+    full = Enmap(gen_spin0(shape, 1.5), wcs)
+    sub = full[:, 30:290]
+    plan = Plan(pixsht.sht_band(sub.data.shape, sub.wcs), 120, 80, dtype=dt, lib=emu_default)
+    got = plan.map2alm([np.asfortranarray(sub.data, dtype=dt)])[0]
+    assert rel_rms(got, oracle_map2alm(sub, 120, mmax=80)[0]) < tol
+    a = synth_alm(120, 80, 613)
+    assert rel_rms(plan.alm2map([a.astype(plan.cdtype)])[0], oracle_alm2map(a[None], sub.data.shape, sub.wcs, 120, mmax=80)[:, :, 0]) < tol
+    plan.close()
+
+
 def test_emu_ring_length_sweep(emu):
     """Ring FFT on lengths with every kind of factorisation (two samples, odd primes, squares of generic radices, powers of
     two, a prime above the in-register radices): map2alm / alm2map of a 5-ring grid against the oracle.  The full sweep

@@ -182,6 +182,8 @@ def test_emu_host_path_single_map_two_phase_pipelines(emu_default, monkeypatch, 
     got = plan.map2alm([x])[0]
     assert rel_rms(got, oracle_map2alm(Enmap(np.asfortranarray(x, dtype=np.float64), wcs), lmax, kind="d")[0]) < tol
     plan.close()
+    if dt == np.float32:
+        return
     # a cut-sky band (single rings without a mirror partner in the chunks) and mmax < lmax
     full = Enmap(gen_spin0(shape, 1.5), wcs)
     sub = full[:, 30:290]
